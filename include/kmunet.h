@@ -1,0 +1,219 @@
+/* kmunet.h -- C ABI of libkmunet.so: the B200 (sm_100a) hot path of KM-UNet.
+ *
+ * Every entry point replaces the arithmetic of one reference PyTorch module method (cited per function as
+ * <reference file>:<lines>, paths relative to the KM-UNet tree).  The host side that binds these symbols is
+ * km_unet_b200/_lib.py (ctypes); INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - All tensors are dense fp32, NCHW / (B,C,L) contiguous exactly as the reference modules hold them.
+ *   - Every pointer is a CUDA device pointer owned by the caller (the PyTorch caching allocator).  The library
+ *     never allocates or frees device memory, keeps no per-tensor state, and never synchronises: each call
+ *     only enqueues kernels on `stream` (a cudaStream_t) and is CUDA-graph capturable.
+ *   - Scratch space is passed in as `workspace` (>= the matching *_workspace_bytes(); may be uninitialised).
+ *   - Return value: KMU_OK (0) or a negative kmu_status; kmu_last_error() returns a thread-local message.
+ *     No exception crosses the boundary, nothing calls exit().  There is NO CPU path: host pointers are UB.
+ *   - Thread-safe: no global mutable state besides the thread-local error string.
+ */
+#ifndef KMUNET_H_
+#define KMUNET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KMU_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+  KMU_OK = 0,
+  KMU_ERR_BAD_ARG = -1,     /* null pointer, non-positive size, inconsistent shape */
+  KMU_ERR_UNSUPPORTED = -2, /* shape/precision outside what the kernel family implements */
+  KMU_ERR_WORKSPACE = -3,   /* workspace_bytes too small */
+  KMU_ERR_LAUNCH = -4,      /* cudaGetLastError() after a launch */
+  KMU_ERR_DEVICE = -5       /* current device is not sm_100 */
+} kmu_status;
+
+typedef enum {
+  KMU_PREC_FP32 = 0, /* CUDA-core fp32 FMA: matches the reference's fp32 modules to ~1e-6 (parity gate 1e-4)   */
+  KMU_PREC_BF16 = 1  /* tcgen05 tensor cores, bf16 operands / fp32 TMEM accumulation (parity gate 2e-2)        */
+} kmu_precision;
+
+typedef void* kmu_stream; /* cudaStream_t */
+
+int kmu_version(void);
+const char* kmu_last_error(void);
+/* 1 when the current CUDA device is compute capability 10.x (tcgen05/TMEM present), else 0. */
+int kmu_device_supported(void);
+/* number of kernels this library has launched from the calling thread (bench.py's gpu_launches). */
+uint64_t kmu_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K: KANConv2d / KANLinear         convKAN/KANConv2Dlayers.py:15-37, convKAN/KANlayers.py:577-610,644-660
+ *   y[b,o,ho,wo] = sum_f SiLU(p_f) Wb[o,f] + sum_f sum_j B_j(p_f; grid[f]) Ws[o,f,j] s[o,f]
+ *   p_f = zero-padded x[b, c, ho*stride - padding + ki, wo*stride - padding + kj],  f = c*k*k + ki*k + kj.
+ * KANLinear on (M,in) is the same call with B=M, Cin=in, H=W=1, ksize=1, stride=1, padding=0.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t B, Cin, H, W, Cout;
+  int32_t ksize, stride, padding;
+  int32_t grid_size, spline_order; /* n_basis = grid_size + spline_order; knots per feature = grid_size + 2*order + 1 */
+  int32_t precision;               /* kmu_precision */
+  int32_t has_scaler;              /* enable_standalone_scale_spline */
+} kmu_kanconv2d_desc;
+
+typedef struct {
+  kmu_kanconv2d_desc d;
+  const float* x;             /* (B,Cin,H,W) */
+  const float* base_weight;   /* (Cout, Cin*k*k) */
+  const float* spline_weight; /* (Cout, Cin*k*k, n_basis) */
+  const float* spline_scaler; /* (Cout, Cin*k*k) or NULL when !has_scaler */
+  const float* grid;          /* (Cin*k*k, n_knots) */
+  float* y;                   /* (B,Cout,Ho,Wo) */
+  void* workspace;
+  size_t workspace_bytes;
+} kmu_kanconv2d_fwd_args;
+
+typedef struct {
+  kmu_kanconv2d_desc d;
+  const float* x;
+  const float* dy; /* (B,Cout,Ho,Wo) */
+  const float* base_weight;
+  const float* spline_weight;
+  const float* spline_scaler;
+  const float* grid;
+  float* dx;             /* (B,Cin,H,W), overwritten; may be NULL to skip */
+  float* d_base_weight;  /* (Cout,Cin*k*k), overwritten; NULL skips all weight gradients */
+  float* d_spline_weight;
+  float* d_spline_scaler; /* NULL when !has_scaler */
+  void* workspace;
+  size_t workspace_bytes;
+} kmu_kanconv2d_bwd_args;
+
+size_t kmu_kanconv2d_fwd_workspace_bytes(const kmu_kanconv2d_desc* d);
+size_t kmu_kanconv2d_bwd_workspace_bytes(const kmu_kanconv2d_desc* d);
+int kmu_kanconv2d_fwd(const kmu_kanconv2d_fwd_args* a, kmu_stream stream);
+int kmu_kanconv2d_bwd(const kmu_kanconv2d_bwd_args* a, kmu_stream stream);
+/* Which kernel family a descriptor resolves to: 0 = fp32 CUDA-core, 1 = tcgen05 implicit GEMM.  The tensor path
+ * needs ksize 3, stride 1, padding 1, cubic splines with 8 basis functions, Cin % 8 == 0, Cout % 16 == 0,
+ * Cout <= 256 and one uniform knot row shared by all features; anything else runs the fp32 family
+ * (still on the GPU). */
+int kmu_kanconv2d_path(const kmu_kanconv2d_desc* d, int grid_is_uniform_shared);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * S: LayerNorm1D + HSMSSD          vim_block_init/vim_utils_init.py:50-59, vim_block_init/efficient_vim_init.py:33-61
+ *   x (B,C,L), L = H*H.  P = dw3x3(Wp x) ; Bm,Cm,dt = split(P) ; A = softmax_L(dt + A_param) ;
+ *   hs = x (A*Bm)^T ; [hh;z] = Whz hs ; ho = Wo (hh*SiLU(z) + hh*D) ; y = ho Cm.   Returns y and h = ho.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t B, C, L, H; /* L == H*H */
+  int32_t N;          /* state_dim (64 in KM-UNet) */
+} kmu_hsmssd_desc;
+
+typedef struct {
+  kmu_hsmssd_desc d;
+  const float* x;      /* (B,C,L) */
+  const float* w_bcdt; /* (3N,C) */
+  const float* w_dw;   /* (3N,3,3) */
+  const float* w_hz;   /* (2C,C) */
+  const float* w_out;  /* (C,C) */
+  const float* A;      /* (N) */
+  const float* D;      /* (1) */
+  float* y;            /* (B,C,L) */
+  float* h;            /* (B,C,N) = ho */
+  /* saved for backward (caller-owned, may all be NULL for inference) */
+  float* P;     /* (B,3N,L) */
+  float* stats; /* (B,2,N): row 0 = max_L(dt + A), row 1 = sum_L exp(dt + A - max) */
+  float* hs;    /* (B,C,N) */
+  float* hz;    /* (B,2C,N) */
+  void* workspace;
+  size_t workspace_bytes;
+} kmu_hsmssd_fwd_args;
+
+typedef struct {
+  kmu_hsmssd_desc d;
+  const float* x;
+  const float* dy; /* (B,C,L) gradient w.r.t. y */
+  const float* dh; /* (B,C,N) gradient w.r.t. h, or NULL (EfficientViMBlock discards h) */
+  const float* w_bcdt;
+  const float* w_dw;
+  const float* w_hz;
+  const float* w_out;
+  const float* A;
+  const float* D;
+  const float* P; /* saved by forward */
+  const float* stats;
+  const float* hs;
+  const float* hz;
+  const float* h; /* ho */
+  float* dx;      /* (B,C,L) overwritten */
+  float* d_w_bcdt;
+  float* d_w_dw;
+  float* d_w_hz;
+  float* d_w_out;
+  float* d_A; /* written with zeros: the over-L softmax cancels the shift */
+  float* d_D;
+  void* workspace;
+  size_t workspace_bytes;
+} kmu_hsmssd_bwd_args;
+
+size_t kmu_hsmssd_fwd_workspace_bytes(const kmu_hsmssd_desc* d);
+size_t kmu_hsmssd_bwd_workspace_bytes(const kmu_hsmssd_desc* d);
+int kmu_hsmssd_fwd(const kmu_hsmssd_fwd_args* a, kmu_stream stream);
+int kmu_hsmssd_bwd(const kmu_hsmssd_bwd_args* a, kmu_stream stream);
+
+/* LayerNorm1D over the channel axis of (B,C,L): y = (x-mean_c)/sqrt(var_c+eps)*w + b  (biased variance). */
+int kmu_layernorm1d_fwd(const float* x, const float* weight, const float* bias, float* y, float* rstd /* (B,L) or NULL */,
+                        int32_t B, int32_t C, int32_t L, float eps, kmu_stream stream);
+/* dweight/dbias are ACCUMULATED with atomics into zero-initialised (C) buffers. */
+int kmu_layernorm1d_bwd(const float* x, const float* weight, const float* dy, float* dx, float* dweight, float* dbias,
+                        int32_t B, int32_t C, int32_t L, float eps, kmu_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * D: DySample ('lp' style, dyscope off)        DySample_md.py:49-68
+ *   off = (conv1x1(x; Wo, bo)) * 0.25 + init_pos                                  (B, 2*G*s*s, H, W)
+ *   out[b, g*Cg+c, s*h+i, s*w+j] = bilinear(x[b, g*Cg+c]; row = clamp(h + off_y), col = clamp(w + off_x))
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t B, C, H, W;
+  int32_t scale, groups;
+} kmu_dysample_desc;
+
+typedef struct {
+  kmu_dysample_desc d;
+  const float* x;        /* (B,C,H,W) */
+  const float* w_offset; /* (2*G*s*s, C) */
+  const float* b_offset; /* (2*G*s*s) */
+  const float* init_pos; /* (2*G*s*s) */
+  float* offset;         /* (B,2*G*s*s,H,W) written (saved for backward) */
+  float* out;            /* (B,C,s*H,s*W) */
+} kmu_dysample_fwd_args;
+
+typedef struct {
+  kmu_dysample_desc d;
+  const float* x;
+  const float* w_offset;
+  const float* offset; /* saved by forward */
+  const float* dout;   /* (B,C,s*H,s*W) */
+  float* dx;           /* (B,C,H,W) overwritten */
+  float* d_w_offset;   /* (2*G*s*s, C) overwritten */
+  float* d_b_offset;   /* (2*G*s*s) overwritten */
+  void* workspace;
+  size_t workspace_bytes;
+} kmu_dysample_bwd_args;
+
+size_t kmu_dysample_bwd_workspace_bytes(const kmu_dysample_desc* d);
+int kmu_dysample_fwd(const kmu_dysample_fwd_args* a, kmu_stream stream);
+int kmu_dysample_bwd(const kmu_dysample_bwd_args* a, kmu_stream stream);
+/* The reference's DySample.sample(x, offset) alone (DySample_md.py:49-61), for styles that build the offset
+ * differently ('pl', dyscope). */
+int kmu_dysample_sample_fwd(const kmu_dysample_desc* d, const float* x, const float* offset, float* out, kmu_stream stream);
+int kmu_dysample_sample_bwd(const kmu_dysample_desc* d, const float* x, const float* offset, const float* dout,
+                            float* dx /* zero-initialised, accumulated */, float* doffset /* overwritten */,
+                            kmu_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMUNET_H_ */

@@ -1,0 +1,139 @@
+"""ctypes binding of libkmunet.so (the C ABI declared in include/kmunet.h).
+
+There is no CPU path and no fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkmunet.so")
+
+KMU_PREC_FP32 = 0
+KMU_PREC_BF16 = 1
+
+_f32p = C.c_void_p  # device pointers travel as integers
+
+
+class KanDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B", "Cin", "H", "W", "Cout", "ksize", "stride", "padding", "grid_size",
+                                         "spline_order", "precision", "has_scaler")]
+
+
+class KanFwdArgs(C.Structure):
+    _fields_ = [("d", KanDesc), ("x", _f32p), ("base_weight", _f32p), ("spline_weight", _f32p), ("spline_scaler", _f32p),
+                ("grid", _f32p), ("y", _f32p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+class KanBwdArgs(C.Structure):
+    _fields_ = [("d", KanDesc), ("x", _f32p), ("dy", _f32p), ("base_weight", _f32p), ("spline_weight", _f32p),
+                ("spline_scaler", _f32p), ("grid", _f32p), ("dx", _f32p), ("d_base_weight", _f32p),
+                ("d_spline_weight", _f32p), ("d_spline_scaler", _f32p), ("workspace", C.c_void_p),
+                ("workspace_bytes", C.c_size_t)]
+
+
+class HsmDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B", "C", "L", "H", "N")]
+
+
+class HsmFwdArgs(C.Structure):
+    _fields_ = [("d", HsmDesc)] + [(n, _f32p) for n in ("x", "w_bcdt", "w_dw", "w_hz", "w_out", "A", "D", "y", "h", "P",
+                                                        "stats", "hs", "hz")] + \
+               [("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+class HsmBwdArgs(C.Structure):
+    _fields_ = [("d", HsmDesc)] + [(n, _f32p) for n in ("x", "dy", "dh", "w_bcdt", "w_dw", "w_hz", "w_out", "A", "D", "P", "stats",
+                                                        "hs", "hz", "h", "dx", "d_w_bcdt", "d_w_dw", "d_w_hz", "d_w_out",
+                                                        "d_A", "d_D")] + \
+               [("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+class DysDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B", "C", "H", "W", "scale", "groups")]
+
+
+class DysFwdArgs(C.Structure):
+    _fields_ = [("d", DysDesc)] + [(n, _f32p) for n in ("x", "w_offset", "b_offset", "init_pos", "offset", "out")]
+
+
+class DysBwdArgs(C.Structure):
+    _fields_ = [("d", DysDesc)] + [(n, _f32p) for n in ("x", "w_offset", "offset", "dout", "dx", "d_w_offset", "d_b_offset")] + \
+               [("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+# every symbol include/kmunet.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "kmu_version": (C.c_int, []),
+    "kmu_last_error": (C.c_char_p, []),
+    "kmu_device_supported": (C.c_int, []),
+    "kmu_launch_count": (C.c_uint64, []),
+    "kmu_kanconv2d_fwd_workspace_bytes": (C.c_size_t, [C.POINTER(KanDesc)]),
+    "kmu_kanconv2d_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(KanDesc)]),
+    "kmu_kanconv2d_fwd": (C.c_int, [C.POINTER(KanFwdArgs), C.c_void_p]),
+    "kmu_kanconv2d_bwd": (C.c_int, [C.POINTER(KanBwdArgs), C.c_void_p]),
+    "kmu_kanconv2d_path": (C.c_int, [C.POINTER(KanDesc), C.c_int]),
+    "kmu_hsmssd_fwd_workspace_bytes": (C.c_size_t, [C.POINTER(HsmDesc)]),
+    "kmu_hsmssd_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(HsmDesc)]),
+    "kmu_hsmssd_fwd": (C.c_int, [C.POINTER(HsmFwdArgs), C.c_void_p]),
+    "kmu_hsmssd_bwd": (C.c_int, [C.POINTER(HsmBwdArgs), C.c_void_p]),
+    "kmu_layernorm1d_fwd": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                      C.c_void_p]),
+    "kmu_layernorm1d_bwd": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                      C.c_void_p]),
+    "kmu_dysample_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(DysDesc)]),
+    "kmu_dysample_fwd": (C.c_int, [C.POINTER(DysFwdArgs), C.c_void_p]),
+    "kmu_dysample_bwd": (C.c_int, [C.POINTER(DysBwdArgs), C.c_void_p]),
+    "kmu_dysample_sample_fwd": (C.c_int, [C.POINTER(DysDesc), _f32p, _f32p, _f32p, C.c_void_p]),
+    "kmu_dysample_sample_bwd": (C.c_int, [C.POINTER(DysDesc), _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libkmunet.so once; raise loudly if it has not been built (python -m km_unet_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m km_unet_b200.build` (or __graft_entry__.build()). "
+                "km_unet_b200 has no CPU or PyTorch fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(handle, name)  # AttributeError here = header and library out of sync
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def last_error():
+    return lib().kmu_last_error().decode("utf-8", "replace")
+
+
+def check(status, what):
+    if status != 0:
+        raise RuntimeError(f"{what} failed (kmu_status {status}): {last_error()}")
+
+
+def ptr(t):
+    """Device pointer of a contiguous fp32 CUDA tensor (or NULL for None)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("km_unet_b200 kernels take CUDA tensors only (there is no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"km_unet_b200 kernels take float32 tensors, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError("km_unet_b200 kernels take contiguous tensors")
+    return t.data_ptr()
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count():
+    return int(lib().kmu_launch_count())

@@ -1,0 +1,14 @@
+"""Process-wide knobs of the drop-in modules."""
+import os
+
+# "fp32": CUDA-core fp32 kernels (1e-4 parity gate).  "bf16": tcgen05 tensor-core kernels where the shape allows
+# (2e-2 parity gate), fp32 family otherwise.  Both run on the GPU; there is no CPU path.
+kan_precision = os.environ.get("KMU_KAN_PRECISION", "fp32")
+
+
+def precision_code(name=None):
+    from ._lib import KMU_PREC_BF16, KMU_PREC_FP32
+    name = kan_precision if name is None else name
+    if name not in ("fp32", "bf16"):
+        raise ValueError(f"unknown KAN precision {name!r} (expected 'fp32' or 'bf16')")
+    return KMU_PREC_BF16 if name == "bf16" else KMU_PREC_FP32

@@ -1,0 +1,41 @@
+// common.cu -- error channel, version, device probe, launch accounting.
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace kmu {
+static thread_local char g_err[512] = "";
+static thread_local uint64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void count_launches(int n) { g_launches += (uint64_t)n; }
+
+int finish_launch(const char* what) {
+  g_launches += 1;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    return KMU_ERR_LAUNCH;
+  }
+  return KMU_OK;
+}
+}  // namespace kmu
+
+extern "C" {
+int kmu_version(void) { return KMU_VERSION; }
+const char* kmu_last_error(void) { return kmu::g_err; }
+uint64_t kmu_launch_count(void) { return kmu::g_launches; }
+int kmu_device_supported(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+}

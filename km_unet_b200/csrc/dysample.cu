@@ -1,0 +1,401 @@
+// dysample.cu -- DySample ('lp' style) offset generation + bilinear point-sampling upsample, forward and backward.
+//
+// Replaces DySample_md.py:49-68: the reference's conv1x1 -> *0.25 + init_pos -> meshgrid/normalise/pixel_shuffle/permute
+// -> F.grid_sample(bilinear, border, align_corners=False) chain collapses to
+//     out[b, g*Cg+c, s*h+i, s*w+j] = bilinear(x[b, g*Cg+c]; row = clamp(h + off_y, 0, H-1), col = clamp(w + off_x, 0, W-1))
+// with off_x = offset[b, (g*s+i)*s+j, h, w], off_y = offset[b, G*s*s + (g*s+i)*s+j, h, w]   (SURVEY appendix A.3).
+// HBM-bound gather: reads x once, writes s*s times as much; stores are 128-bit, loads of the four taps of
+// neighbouring output pixels fall in the same cache lines.
+#include "common.cuh"
+
+namespace kmu {
+namespace dys {
+
+struct Dims {
+  int B, C, H, W, s, G, Cg, NOFF, OH, OW;
+};
+
+static Dims make_dims(const kmu_dysample_desc& d) {
+  Dims r;
+  r.B = d.B; r.C = d.C; r.H = d.H; r.W = d.W; r.s = d.scale; r.G = d.groups;
+  r.Cg = d.C / d.groups;
+  r.NOFF = 2 * d.groups * d.scale * d.scale;
+  r.OH = d.H * d.scale; r.OW = d.W * d.scale;
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------- offset conv (fwd)
+// thread = input pixel; 32 offset channels per pass (blockIdx.y); weights transposed in smem as [c][32].
+__global__ void __launch_bounds__(128) dys_offset_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, const float* __restrict__ init_pos,
+                                                             float* __restrict__ offset, Dims d) {
+  extern __shared__ __align__(16) float smem[];
+  float* w_s = smem;  // [C][32]
+  const int j0 = blockIdx.y * 32;
+  for (int i = threadIdx.x; i < d.C * 32; i += 128) {
+    int c = i >> 5, j = i & 31;
+    w_s[i] = (j0 + j < d.NOFF) ? w[(size_t)(j0 + j) * d.C + c] : 0.f;
+  }
+  __syncthreads();
+  const long long HW = (long long)d.H * d.W;
+  long long p = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (p >= d.B * HW) return;
+  int b = (int)(p / HW);
+  long long r = p - b * HW;
+  const float* xp = x + (size_t)b * d.C * HW + r;
+  float acc[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+  for (int c = 0; c < d.C; ++c) {
+    float xv = __ldg(xp + (size_t)c * HW);
+    const float4* wr = reinterpret_cast<const float4*>(w_s + c * 32);
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      float4 ww = wr[j4];
+      acc[j4 * 4 + 0] = fmaf(xv, ww.x, acc[j4 * 4 + 0]);
+      acc[j4 * 4 + 1] = fmaf(xv, ww.y, acc[j4 * 4 + 1]);
+      acc[j4 * 4 + 2] = fmaf(xv, ww.z, acc[j4 * 4 + 2]);
+      acc[j4 * 4 + 3] = fmaf(xv, ww.w, acc[j4 * 4 + 3]);
+    }
+  }
+  float* op = offset + (size_t)b * d.NOFF * HW + r;
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if (j0 + j < d.NOFF) op[(size_t)(j0 + j) * HW] = (acc[j] + bias[j0 + j]) * 0.25f + init_pos[j0 + j];
+}
+
+// ---------------------------------------------------------------------------------------------- sampling helpers
+struct Coord {
+  int x0, y0;
+  float fx, fy;
+  bool x1ok, y1ok;   // the +1 neighbour lies inside the image
+  bool gx, gy;       // coordinate was not clipped -> offset gradient flows (PyTorch clip_coordinates_set_grad)
+};
+
+__device__ __forceinline__ Coord make_coord(float rx, float ry, int W, int H) {
+  Coord c;
+  c.gx = rx > 0.f && rx < (float)(W - 1);
+  c.gy = ry > 0.f && ry < (float)(H - 1);
+  float sx = fminf(fmaxf(rx, 0.f), (float)(W - 1));
+  float sy = fminf(fmaxf(ry, 0.f), (float)(H - 1));
+  float fx0 = floorf(sx), fy0 = floorf(sy);
+  c.x0 = (int)fx0;
+  c.y0 = (int)fy0;
+  c.fx = sx - fx0;
+  c.fy = sy - fy0;
+  c.x1ok = c.x0 + 1 < W;
+  c.y1ok = c.y0 + 1 < H;
+  return c;
+}
+
+// ---------------------------------------------------------------------------------------------- sample (fwd)
+// thread = VEC consecutive output columns of one (b, channel, output row)
+template <int VEC>
+__global__ void __launch_bounds__(256) dys_sample_fwd_kernel(const float* __restrict__ x, const float* __restrict__ offset,
+                                                             float* __restrict__ out, Dims d) {
+  const int owv = d.OW / VEC;
+  long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  long long total = (long long)d.B * d.C * d.OH * owv;
+  if (idx >= total) return;
+  int ow0 = (int)(idx % owv) * VEC;
+  long long t = idx / owv;
+  int oh = (int)(t % d.OH);
+  t /= d.OH;
+  int c = (int)(t % d.C);
+  int b = (int)(t / d.C);
+  int g = c / d.Cg;
+  int h = oh / d.s, i = oh - h * d.s;
+  const long long HW = (long long)d.H * d.W;
+  const float* xp = x + ((size_t)b * d.C + c) * HW;
+  const float* offb = offset + (size_t)b * d.NOFF * HW + (size_t)h * d.W;
+  const int ss = d.s * d.s;
+  float res[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) {
+    int ow = ow0 + e;
+    int w = ow / d.s, j = ow - w * d.s;
+    int ch = (g * d.s + i) * d.s + j;
+    float ox = __ldg(offb + (size_t)ch * HW + w);
+    float oy = __ldg(offb + (size_t)(d.G * ss + ch) * HW + w);
+    Coord q = make_coord((float)w + ox, (float)h + oy, d.W, d.H);
+    const float* r0 = xp + (size_t)q.y0 * d.W + q.x0;
+    float v00 = __ldg(r0);
+    float v01 = q.x1ok ? __ldg(r0 + 1) : 0.f;
+    float v10 = q.y1ok ? __ldg(r0 + d.W) : 0.f;
+    float v11 = (q.x1ok && q.y1ok) ? __ldg(r0 + d.W + 1) : 0.f;
+    float wx1 = q.fx, wx0 = 1.f - q.fx, wy1 = q.fy, wy0 = 1.f - q.fy;
+    res[e] = v00 * (wx0 * wy0) + v01 * (wx1 * wy0) + v10 * (wx0 * wy1) + v11 * (wx1 * wy1);
+  }
+  float* op = out + (((size_t)b * d.C + c) * d.OH + oh) * d.OW + ow0;
+  if (VEC == 4) {
+    *reinterpret_cast<float4*>(op) = make_float4(res[0], res[1], res[2], res[3]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) op[e] = res[e];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- sample (bwd)
+// thread = one output pixel of one (b, group): loops over the group's channels, scatters dX with fp32 atomics (like
+// PyTorch's grid_sampler backward) and keeps the offset gradient in registers (no atomics: one owner per offset).
+__global__ void __launch_bounds__(256) dys_sample_bwd_kernel(const float* __restrict__ x, const float* __restrict__ offset,
+                                                             const float* __restrict__ dout, float* __restrict__ dx,
+                                                             float* __restrict__ doffset, Dims d) {
+  long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  long long total = (long long)d.B * d.G * d.OH * d.OW;
+  if (idx >= total) return;
+  int ow = (int)(idx % d.OW);
+  long long t = idx / d.OW;
+  int oh = (int)(t % d.OH);
+  t /= d.OH;
+  int g = (int)(t % d.G);
+  int b = (int)(t / d.G);
+  int h = oh / d.s, i = oh - h * d.s;
+  int w = ow / d.s, j = ow - w * d.s;
+  const long long HW = (long long)d.H * d.W, OHW = (long long)d.OH * d.OW;
+  const int ss = d.s * d.s;
+  int ch = (g * d.s + i) * d.s + j;
+  size_t offi = (size_t)b * d.NOFF * HW + (size_t)ch * HW + (size_t)h * d.W + w;
+  float ox = offset[offi], oy = offset[offi + (size_t)d.G * ss * HW];
+  Coord q = make_coord((float)w + ox, (float)h + oy, d.W, d.H);
+  float wx1 = q.fx, wx0 = 1.f - q.fx, wy1 = q.fy, wy0 = 1.f - q.fy;
+  size_t base = ((size_t)b * d.C + (size_t)g * d.Cg) * HW + (size_t)q.y0 * d.W + q.x0;
+  const float* dop = dout + ((size_t)b * d.C + (size_t)g * d.Cg) * OHW + (size_t)oh * d.OW + ow;
+  float gx = 0.f, gy = 0.f;
+  for (int c = 0; c < d.Cg; ++c) {
+    float go = __ldg(dop + (size_t)c * OHW);
+    const float* r0 = x + base + (size_t)c * HW;
+    float* g0 = dx + base + (size_t)c * HW;
+    float v00 = __ldg(r0);
+    float v01 = q.x1ok ? __ldg(r0 + 1) : 0.f;
+    float v10 = q.y1ok ? __ldg(r0 + d.W) : 0.f;
+    float v11 = (q.x1ok && q.y1ok) ? __ldg(r0 + d.W + 1) : 0.f;
+    atomicAdd(g0, go * (wx0 * wy0));
+    if (q.x1ok) atomicAdd(g0 + 1, go * (wx1 * wy0));
+    if (q.y1ok) atomicAdd(g0 + d.W, go * (wx0 * wy1));
+    if (q.x1ok && q.y1ok) atomicAdd(g0 + d.W + 1, go * (wx1 * wy1));
+    gx = fmaf(go, (v01 - v00) * wy0 + (v11 - v10) * wy1, gx);
+    gy = fmaf(go, (v10 - v00) * wx0 + (v11 - v01) * wx1, gy);
+  }
+  doffset[offi] = q.gx ? gx : 0.f;
+  doffset[offi + (size_t)d.G * ss * HW] = q.gy ? gy : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------- offset conv (bwd)
+// thread = input pixel, 32 offset channels per pass.  dX += W^T (0.25 dOff) with atomics (several passes / the sampler's
+// scatter share dX); per-block partials of dW = (0.25 dOff) x^T and db go to the workspace, reduced in fixed order.
+__global__ void __launch_bounds__(128) dys_offset_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ doffset, float* __restrict__ dx,
+                                                             float* __restrict__ partial, Dims d) {
+  extern __shared__ __align__(16) float smem[];
+  float* w_s = smem;                    // [C][32]
+  float* g_s = w_s + d.C * 32;          // [128][33]
+  float* x_s = g_s + 128 * 33;          // [128][36]
+  const int tid = threadIdx.x;
+  const int j0 = blockIdx.y * 32;
+  for (int i = tid; i < d.C * 32; i += 128) {
+    int c = i >> 5, j = i & 31;
+    w_s[i] = (j0 + j < d.NOFF) ? w[(size_t)(j0 + j) * d.C + c] : 0.f;
+  }
+  const long long HW = (long long)d.H * d.W;
+  long long p = (long long)blockIdx.x * 128 + tid;
+  const bool valid = p < d.B * HW;
+  int b = valid ? (int)(p / HW) : 0;
+  long long r = valid ? p - b * HW : 0;
+  float g[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    g[j] = (valid && j0 + j < d.NOFF) ? 0.25f * doffset[(size_t)b * d.NOFF * HW + (size_t)(j0 + j) * HW + r] : 0.f;
+    g_s[tid * 33 + j] = g[j];
+  }
+  __syncthreads();
+  // dX
+  if (valid) {
+    float* dxp = dx + (size_t)b * d.C * HW + r;
+    for (int c = 0; c < d.C; ++c) {
+      const float4* wr = reinterpret_cast<const float4*>(w_s + c * 32);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        float4 ww = wr[j4];
+        s0 = fmaf(g[j4 * 4 + 0], ww.x, s0);
+        s1 = fmaf(g[j4 * 4 + 1], ww.y, s1);
+        s2 = fmaf(g[j4 * 4 + 2], ww.z, s2);
+        s3 = fmaf(g[j4 * 4 + 3], ww.w, s3);
+      }
+      atomicAdd(dxp + (size_t)c * HW, (s0 + s1) + (s2 + s3));
+    }
+  }
+  // dW partial: thread owns offset channel j = lane, channels cq*8..cq*8+7 of each 32-channel chunk (cq = warp id)
+  const int j = tid & 31, cq = tid >> 5;
+  float* pb = partial + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * (32 * d.C + 32);
+  for (int c0 = 0; c0 < d.C; c0 += 32) {
+    __syncthreads();
+    for (int cc = 0; cc < 32; ++cc) {
+      int c = c0 + cc;
+      x_s[tid * 36 + cc] = (valid && c < d.C) ? __ldg(x + (size_t)b * d.C * HW + (size_t)c * HW + r) : 0.f;
+    }
+    __syncthreads();
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int px = 0; px < 128; ++px) {
+      float gv = g_s[px * 33 + j];
+      const float4* xr = reinterpret_cast<const float4*>(x_s + px * 36 + cq * 8);
+      float4 a = xr[0], c4 = xr[1];
+      acc[0] = fmaf(gv, a.x, acc[0]);
+      acc[1] = fmaf(gv, a.y, acc[1]);
+      acc[2] = fmaf(gv, a.z, acc[2]);
+      acc[3] = fmaf(gv, a.w, acc[3]);
+      acc[4] = fmaf(gv, c4.x, acc[4]);
+      acc[5] = fmaf(gv, c4.y, acc[5]);
+      acc[6] = fmaf(gv, c4.z, acc[6]);
+      acc[7] = fmaf(gv, c4.w, acc[7]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int c = c0 + cq * 8 + i;
+      if (c < d.C) pb[(size_t)j * d.C + c] = acc[i];
+    }
+  }
+  if (cq == 0) {
+    float sb = 0.f;
+    for (int px = 0; px < 128; ++px) sb += g_s[px * 33 + j];
+    pb[(size_t)32 * d.C + j] = sb;
+  }
+}
+
+__global__ void dys_offset_bwd_reduce_kernel(const float* __restrict__ partial, int nblk, int npass, float* __restrict__ dw,
+                                             float* __restrict__ db, Dims d) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  int per = 32 * d.C + 32;
+  if (idx >= npass * per) return;
+  int pass = idx / per, e = idx - pass * per;
+  float s = 0.f;
+  for (int k = 0; k < nblk; ++k) s += partial[((size_t)pass * nblk + k) * per + e];
+  if (e < 32 * d.C) {
+    int j = pass * 32 + e / d.C, c = e % d.C;
+    if (j < d.NOFF) dw[(size_t)j * d.C + c] = s;
+  } else {
+    int j = pass * 32 + (e - 32 * d.C);
+    if (j < d.NOFF) db[j] = s;
+  }
+}
+
+__global__ void zero_kernel(float* __restrict__ p, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = 0.f;
+}
+
+static int check(const kmu_dysample_desc* d, const char* who) {
+  KMU_REQUIRE(d != nullptr, KMU_ERR_BAD_ARG, "%s: null descriptor", who);
+  KMU_REQUIRE(d->B > 0 && d->C > 0 && d->H > 0 && d->W > 0 && d->scale > 0 && d->groups > 0, KMU_ERR_BAD_ARG,
+              "%s: non-positive shape", who);
+  KMU_REQUIRE(d->C % d->groups == 0, KMU_ERR_BAD_ARG, "%s: channels %d not divisible by groups %d", who, d->C, d->groups);
+  KMU_REQUIRE(d->C <= 1024, KMU_ERR_UNSUPPORTED, "%s: C=%d > 1024 not supported", who, d->C);
+  return KMU_OK;
+}
+
+static int launch_sample_fwd(const Dims& d, const float* x, const float* offset, float* out, cudaStream_t st) {
+  if (d.OW % 4 == 0) {
+    long long total = (long long)d.B * d.C * d.OH * (d.OW / 4);
+    dys_sample_fwd_kernel<4><<<cdiv(total, 256), 256, 0, st>>>(x, offset, out, d);
+  } else {
+    long long total = (long long)d.B * d.C * d.OH * d.OW;
+    dys_sample_fwd_kernel<1><<<cdiv(total, 256), 256, 0, st>>>(x, offset, out, d);
+  }
+  KMU_LAUNCH_CHECK("dys_sample_fwd");
+  return KMU_OK;
+}
+
+static int launch_sample_bwd(const Dims& d, const float* x, const float* offset, const float* dout, float* dx, float* doffset,
+                             cudaStream_t st) {
+  long long total = (long long)d.B * d.G * d.OH * d.OW;
+  dys_sample_bwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(x, offset, dout, dx, doffset, d);
+  KMU_LAUNCH_CHECK("dys_sample_bwd");
+  return KMU_OK;
+}
+
+}  // namespace dys
+}  // namespace kmu
+
+using namespace kmu;
+using namespace kmu::dys;
+
+extern "C" {
+
+size_t kmu_dysample_bwd_workspace_bytes(const kmu_dysample_desc* dd) {
+  if (check(dd, "dysample_bwd_workspace_bytes") != KMU_OK) return 0;
+  Dims d = make_dims(*dd);
+  long long npix = (long long)d.B * d.H * d.W;
+  size_t doff = align_up((size_t)d.B * d.NOFF * d.H * d.W * 4, 256);
+  size_t part = (size_t)cdiv(npix, 128) * cdiv(d.NOFF, 32) * (32 * d.C + 32) * 4;
+  return doff + align_up(part, 256);
+}
+
+int kmu_dysample_fwd(const kmu_dysample_fwd_args* a, kmu_stream stream) {
+  KMU_REQUIRE(a != nullptr, KMU_ERR_BAD_ARG, "dysample_fwd: null args");
+  int st_ = check(&a->d, "dysample_fwd");
+  if (st_ != KMU_OK) return st_;
+  KMU_REQUIRE(a->x && a->w_offset && a->b_offset && a->init_pos && a->offset && a->out, KMU_ERR_BAD_ARG,
+              "dysample_fwd: null tensor");
+  Dims d = make_dims(a->d);
+  cudaStream_t st = (cudaStream_t)stream;
+  long long npix = (long long)d.B * d.H * d.W;
+  size_t smem = (size_t)d.C * 32 * 4;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(dys_offset_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dys_offset_fwd_kernel<<<dim3(cdiv(npix, 128), cdiv(d.NOFF, 32)), 128, smem, st>>>(a->x, a->w_offset, a->b_offset, a->init_pos,
+                                                                                   a->offset, d);
+  KMU_LAUNCH_CHECK("dys_offset_fwd");
+  return launch_sample_fwd(d, a->x, a->offset, a->out, st);
+}
+
+int kmu_dysample_sample_fwd(const kmu_dysample_desc* dd, const float* x, const float* offset, float* out, kmu_stream stream) {
+  int st_ = check(dd, "dysample_sample_fwd");
+  if (st_ != KMU_OK) return st_;
+  KMU_REQUIRE(x && offset && out, KMU_ERR_BAD_ARG, "dysample_sample_fwd: null tensor");
+  return launch_sample_fwd(make_dims(*dd), x, offset, out, (cudaStream_t)stream);
+}
+
+int kmu_dysample_sample_bwd(const kmu_dysample_desc* dd, const float* x, const float* offset, const float* dout, float* dx,
+                            float* doffset, kmu_stream stream) {
+  int st_ = check(dd, "dysample_sample_bwd");
+  if (st_ != KMU_OK) return st_;
+  KMU_REQUIRE(x && offset && dout && dx && doffset, KMU_ERR_BAD_ARG, "dysample_sample_bwd: null tensor");
+  return launch_sample_bwd(make_dims(*dd), x, offset, dout, dx, doffset, (cudaStream_t)stream);
+}
+
+int kmu_dysample_bwd(const kmu_dysample_bwd_args* a, kmu_stream stream) {
+  KMU_REQUIRE(a != nullptr, KMU_ERR_BAD_ARG, "dysample_bwd: null args");
+  int st_ = check(&a->d, "dysample_bwd");
+  if (st_ != KMU_OK) return st_;
+  KMU_REQUIRE(a->x && a->w_offset && a->offset && a->dout && a->dx && a->d_w_offset && a->d_b_offset, KMU_ERR_BAD_ARG,
+              "dysample_bwd: null tensor");
+  size_t need = kmu_dysample_bwd_workspace_bytes(&a->d);
+  KMU_REQUIRE(a->workspace && a->workspace_bytes >= need, KMU_ERR_WORKSPACE, "dysample_bwd: workspace %zu < %zu",
+              a->workspace_bytes, need);
+  Dims d = make_dims(a->d);
+  cudaStream_t st = (cudaStream_t)stream;
+  long long npix = (long long)d.B * d.H * d.W;
+  float* doff = (float*)a->workspace;
+  float* partial = (float*)((char*)a->workspace + align_up((size_t)d.B * d.NOFF * d.H * d.W * 4, 256));
+  long long nx = npix * d.C;
+  zero_kernel<<<(int)std::min<long long>(cdiv(nx, 1024), 148 * 8), 256, 0, st>>>(a->dx, nx);
+  KMU_LAUNCH_CHECK("dys_zero");
+  st_ = launch_sample_bwd(d, a->x, a->offset, a->dout, a->dx, doff, st);
+  if (st_ != KMU_OK) return st_;
+  int nblk = cdiv(npix, 128), npass = cdiv(d.NOFF, 32);
+  size_t smem = ((size_t)d.C * 32 + 128 * 33 + 128 * 36) * 4;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(dys_offset_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dys_offset_bwd_kernel<<<dim3(nblk, npass), 128, smem, st>>>(a->x, a->w_offset, doff, a->dx, partial, d);
+  KMU_LAUNCH_CHECK("dys_offset_bwd");
+  int n = npass * (32 * d.C + 32);
+  dys_offset_bwd_reduce_kernel<<<cdiv(n, 128), 128, 0, st>>>(partial, nblk, npass, a->d_w_offset, a->d_b_offset, d);
+  KMU_LAUNCH_CHECK("dys_offset_bwd_reduce");
+  return KMU_OK;
+}
+
+}  // extern "C"

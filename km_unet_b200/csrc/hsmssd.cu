@@ -1,0 +1,892 @@
+// hsmssd.cu -- EfficientViM HSM-SSD hidden-state mixer, forward and backward, plus LayerNorm1D.
+//
+// Replaces vim_block_init/efficient_vim_init.py:33-61 (HSMSSD.forward) and vim_utils_init.py:50-59 (LayerNorm1D.forward)
+// and the autograd graph PyTorch builds for them.  Arithmetic, x (B,C,L), L = H*H, N = 64 states:
+//     Q = Wp x ; P = dw3x3(Q) ; [Bm; Cm; dt] = P ; A = softmax_L(dt)   (the per-state shift A_param cancels under the
+//     over-L softmax, efficient_vim_init.py:46, so it is neither read nor given a gradient)
+//     hs = x (A.Bm)^T ; [hh; z] = Whz hs ; ho = Wo (hh.SiLU(z) + hh D) ; y = ho Cm
+// Forward kernels
+//     hsm_proj_dw      x -> P          1x1 projection recomputed on a 1-pixel halo, depthwise 3x3 from shared memory
+//     hsm_softmax_hs   P,x -> per-tile online-softmax partials (max, sum, unnormalised hs): one sweep over L
+//     hsm_combine_gate partials -> stats, hs, hz, ho (one CTA per batch element; all (C,64)-sized)
+//     hsm_out          ho,P -> y
+// Backward kernels (three sweeps over L; the softmax-backward reduction sum_L(dA.A) equals sum_c dhs.hs, so it needs none)
+//     hsm_contract     dy,Cm -> dho partials
+//     hsm_gate_bwd     -> dhs, r, per-batch dWo / dWhz / dD
+//     hsm_dp           -> dP = [dBm; dCm; ddt] and the direct part of dx
+//     hsm_proj_dw_bwd  dP -> dx += Wp^T dQ, per-CTA partials of dWp and dWd ; hsm_wgrad_reduce sums them in fixed order.
+// P is materialised in fp32 (B,192,L): with 180 GB of HBM3e that is cheaper than recomputing the projection in the
+// three backward sweeps on CUDA cores.  All reductions are deterministic (no atomics).
+#include "common.cuh"
+
+namespace kmu {
+namespace hsm {
+
+constexpr int N = 64;         // states
+constexpr int N3 = 192;       // projected channels
+constexpr int TH = 8, TW = 32, HW_ = TW + 2, HH_ = TH + 2, NHALO = HW_ * HH_;  // spatial tile + 1-pixel halo (340)
+constexpr int SUB = 256;      // positions per sub-tile in the over-L sweeps
+constexpr int SUBS_PER_CTA = 4;
+
+struct Dims {
+  int B, C, L, H;
+  int tiles_x, tiles_y;  // spatial tiling (TH x TW)
+  int T;                 // CTAs per batch element in the over-L sweeps
+};
+
+static Dims make_dims(const kmu_hsmssd_desc& s) {
+  Dims d;
+  d.B = s.B; d.C = s.C; d.L = s.L; d.H = s.H;
+  d.tiles_x = cdiv(s.H, TW);
+  d.tiles_y = cdiv(s.H, TH);
+  d.T = cdiv(s.L, SUB * SUBS_PER_CTA);
+  return d;
+}
+
+// ================================================================================================ forward
+// ---- P = dw3x3(Wp x).  grid (tiles, B, 192/NCH), 256 threads = 8x32 interior positions.
+template <int NCH>
+__global__ void __launch_bounds__(256) hsm_proj_dw_kernel(const float* __restrict__ x, const float* __restrict__ wp,
+                                                          const float* __restrict__ wd, float* __restrict__ P, Dims d) {
+  extern __shared__ __align__(16) float smem[];
+  float* q_s = smem;                    // [NCH][NHALO]
+  float* wp_s = q_s + NCH * NHALO;      // [C][NCH]
+  float* wd_s = wp_s + d.C * NCH;       // [NCH][9]
+  const int tid = threadIdx.x;
+  const int ty0 = (blockIdx.x / d.tiles_x) * TH, tx0 = (blockIdx.x % d.tiles_x) * TW;
+  const int b = blockIdx.y, n0 = blockIdx.z * NCH;
+  for (int i = tid; i < d.C * NCH; i += 256) {
+    int c = i / NCH, nn = i - c * NCH;
+    wp_s[i] = wp[(size_t)(n0 + nn) * d.C + c];
+  }
+  for (int i = tid; i < NCH * 9; i += 256) wd_s[i] = wd[(size_t)n0 * 9 + i];
+  __syncthreads();
+  const float* xb = x + (size_t)b * d.C * d.L;
+  for (int pos = tid; pos < NHALO; pos += 256) {
+    int hy = pos / HW_, hx = pos - hy * HW_;
+    int gy = ty0 + hy - 1, gx = tx0 + hx - 1;
+    float q[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) q[i] = 0.f;
+    if (gy >= 0 && gy < d.H && gx >= 0 && gx < d.H) {
+      const float* xp = xb + (size_t)gy * d.H + gx;
+      for (int c = 0; c < d.C; ++c) {
+        float xv = __ldg(xp + (size_t)c * d.L);
+        const float4* w4 = reinterpret_cast<const float4*>(wp_s + c * NCH);
+#pragma unroll
+        for (int i = 0; i < NCH / 4; ++i) {
+          float4 w = w4[i];
+          q[4 * i + 0] = fmaf(xv, w.x, q[4 * i + 0]);
+          q[4 * i + 1] = fmaf(xv, w.y, q[4 * i + 1]);
+          q[4 * i + 2] = fmaf(xv, w.z, q[4 * i + 2]);
+          q[4 * i + 3] = fmaf(xv, w.w, q[4 * i + 3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) q_s[i * NHALO + pos] = q[i];
+  }
+  __syncthreads();
+  const int ly = tid >> 5, lx = tid & 31;
+  const int gy = ty0 + ly, gx = tx0 + lx;
+  if (gy < d.H && gx < d.H) {
+    float* pp = P + ((size_t)b * N3 + n0) * d.L + (size_t)gy * d.H + gx;
+#pragma unroll 4
+    for (int nn = 0; nn < NCH; ++nn) {
+      const float* qr = q_s + nn * NHALO + ly * HW_ + lx;
+      const float* w = wd_s + nn * 9;
+      float s = qr[0] * w[0] + qr[1] * w[1] + qr[2] * w[2];
+      s += qr[HW_] * w[3] + qr[HW_ + 1] * w[4] + qr[HW_ + 2] * w[5];
+      s += qr[2 * HW_] * w[6] + qr[2 * HW_ + 1] * w[7] + qr[2 * HW_ + 2] * w[8];
+      pp[(size_t)nn * d.L] = s;
+    }
+  }
+}
+
+// ---- shared inner product over a sub-tile: acc[k] += sum_l u_s[c_k][l] * v_s[l][n]  (u_s [C][SUB], v_s [SUB][65])
+template <int CPT>
+__device__ __forceinline__ void contract_subtile(const float* __restrict__ u_s, const float* __restrict__ v_s, int n, int cg,
+                                                 int C, float* acc) {
+  for (int l4 = 0; l4 < SUB; l4 += 4) {
+    float v0 = v_s[(l4 + 0) * 65 + n], v1 = v_s[(l4 + 1) * 65 + n], v2 = v_s[(l4 + 2) * 65 + n], v3 = v_s[(l4 + 3) * 65 + n];
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      int c = cg + 4 * k;
+      if (c < C) {
+        float4 u = *reinterpret_cast<const float4*>(u_s + c * SUB + l4);
+        acc[k] = fmaf(u.x, v0, fmaf(u.y, v1, fmaf(u.z, v2, fmaf(u.w, v3, acc[k]))));
+      }
+    }
+  }
+}
+
+// ---- one sweep over L: online softmax of dt along L fused with hs_partial = x (e.Bm)^T.  grid (T, B), 256 threads.
+template <int CPT>
+__global__ void __launch_bounds__(256) hsm_softmax_hs_kernel(const float* __restrict__ x, const float* __restrict__ P,
+                                                             float* __restrict__ part_m, float* __restrict__ part_s,
+                                                             float* __restrict__ part_hs, Dims d) {
+  extern __shared__ __align__(16) float smem[];
+  float* w_s = smem;               // [SUB][65]
+  float* x_s = w_s + SUB * 65;     // [C][SUB]
+  float* m_run = x_s + d.C * SUB;  // [64]
+  float* s_run = m_run + 64;
+  float* scale_s = s_run + 64;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int b = blockIdx.y, t = blockIdx.x;
+  const int n = tid & 63, cg = tid >> 6;
+  if (tid < 64) { m_run[tid] = -INFINITY; s_run[tid] = 0.f; }
+  float acc[CPT];
+#pragma unroll
+  for (int k = 0; k < CPT; ++k) acc[k] = 0.f;
+  const float* xb = x + (size_t)b * d.C * d.L;
+  const float* Pb = P + (size_t)b * N3 * d.L;
+  for (int sub = 0; sub < SUBS_PER_CTA; ++sub) {
+    const int l0 = (t * SUBS_PER_CTA + sub) * SUB;
+    if (l0 >= d.L) break;
+    __syncthreads();
+    for (int i = tid; i < d.C * SUB; i += 256) {
+      int c = i / SUB, li = i - c * SUB;
+      x_s[i] = (l0 + li < d.L) ? __ldg(xb + (size_t)c * d.L + l0 + li) : 0.f;
+    }
+    for (int j = 0; j < 8; ++j) {
+      const int ns = wid * 8 + j;
+      float dtv[8], mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        int l = l0 + lane + 32 * k;
+        dtv[k] = (l < d.L) ? __ldg(Pb + (size_t)(2 * N + ns) * d.L + l) : -INFINITY;
+        mx = fmaxf(mx, dtv[k]);
+      }
+      mx = warp_max(mx);
+      const float m_old = m_run[ns];
+      const float m_new = fmaxf(m_old, mx);
+      float ssum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        int l = l0 + lane + 32 * k;
+        float e = (l < d.L) ? expf(dtv[k] - m_new) : 0.f;
+        ssum += e;
+        float bm = (l < d.L) ? __ldg(Pb + (size_t)ns * d.L + l) : 0.f;
+        w_s[(lane + 32 * k) * 65 + ns] = e * bm;
+      }
+      ssum = warp_sum(ssum);
+      __syncwarp();
+      if (lane == 0) {
+        float sc = (m_old == -INFINITY) ? 0.f : expf(m_old - m_new);
+        scale_s[ns] = sc;
+        s_run[ns] = s_run[ns] * sc + ssum;
+        m_run[ns] = m_new;
+      }
+    }
+    __syncthreads();
+    const float sc = scale_s[n];
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) acc[k] *= sc;
+    contract_subtile<CPT>(x_s, w_s, n, cg, d.C, acc);
+  }
+  __syncthreads();
+  const size_t bt = (size_t)b * d.T + t;
+  if (cg == 0) { part_m[bt * 64 + n] = m_run[n]; part_s[bt * 64 + n] = s_run[n]; }
+#pragma unroll
+  for (int k = 0; k < CPT; ++k) {
+    int c = cg + 4 * k;
+    if (c < d.C) part_hs[(bt * d.C + c) * 64 + n] = acc[k];
+  }
+}
+
+// ---- combine the T partials of one batch element, then the (C,64)-sized gate.  grid B, 256 threads.
+__global__ void __launch_bounds__(256) hsm_combine_gate_kernel(const float* __restrict__ part_m, const float* __restrict__ part_s,
+                                                               const float* __restrict__ part_hs, const float* __restrict__ whz,
+                                                               const float* __restrict__ wo, const float* __restrict__ Dp,
+                                                               float* __restrict__ stats, float* __restrict__ hs_out,
+                                                               float* __restrict__ hz_out, float* __restrict__ ho_out, Dims d) {
+  extern __shared__ __align__(16) float smem[];
+  float* hs_s = smem;                  // [C][64]
+  float* hz_s = hs_s + d.C * 64;       // [2C][64]
+  float* v_s = hz_s + 2 * d.C * 64;    // [C][64]
+  const int tid = threadIdx.x, n = tid & 63, cg = tid >> 6, b = blockIdx.x, C = d.C;
+  const float* pm = part_m + (size_t)b * d.T * 64 + n;
+  const float* ps = part_s + (size_t)b * d.T * 64 + n;
+  float m = -INFINITY;
+  for (int t = 0; t < d.T; ++t) m = fmaxf(m, pm[t * 64]);
+  float s = 0.f;
+  for (int t = 0; t < d.T; ++t) s += ps[t * 64] * expf(pm[t * 64] - m);
+  const float inv_s = 1.0f / s;
+  if (cg == 0 && stats) { stats[(size_t)b * 128 + n] = m; stats[(size_t)b * 128 + 64 + n] = s; }
+  for (int c = cg; c < C; c += 4) {
+    float a = 0.f;
+    for (int t = 0; t < d.T; ++t) a = fmaf(part_hs[(((size_t)b * d.T + t) * C + c) * 64 + n], expf(pm[t * 64] - m), a);
+    a *= inv_s;
+    hs_s[c * 64 + n] = a;
+    if (hs_out) hs_out[((size_t)b * C + c) * 64 + n] = a;
+  }
+  __syncthreads();
+  for (int dd = cg; dd < 2 * C; dd += 4) {
+    float a = 0.f;
+    for (int c = 0; c < C; ++c) a = fmaf(__ldg(whz + (size_t)dd * C + c), hs_s[c * 64 + n], a);
+    hz_s[dd * 64 + n] = a;
+    if (hz_out) hz_out[((size_t)b * 2 * C + dd) * 64 + n] = a;
+  }
+  __syncthreads();
+  const float Dv = Dp[0];
+  for (int c = cg; c < C; c += 4) {
+    float hh = hz_s[c * 64 + n], z = hz_s[(C + c) * 64 + n];
+    v_s[c * 64 + n] = hh * siluf_(z) + hh * Dv;
+  }
+  __syncthreads();
+  for (int dd = cg; dd < C; dd += 4) {
+    float a = 0.f;
+    for (int c = 0; c < C; ++c) a = fmaf(__ldg(wo + (size_t)dd * C + c), v_s[c * 64 + n], a);
+    ho_out[((size_t)b * C + dd) * 64 + n] = a;
+  }
+}
+
+// ---- y[b,c,l] = sum_n ho[b,c,n] Cm[b,n,l].  thread = position, 64 states in registers.  grid (ceil(L/256), B).
+__global__ void __launch_bounds__(256) hsm_out_kernel(const float* __restrict__ ho, const float* __restrict__ P,
+                                                      float* __restrict__ y, Dims d) {
+  extern __shared__ __align__(16) float smem[];
+  float* ho_s = smem;  // [C][64]
+  const int tid = threadIdx.x, b = blockIdx.y;
+  for (int i = tid; i < d.C * 64; i += 256) ho_s[i] = ho[(size_t)b * d.C * 64 + i];
+  __syncthreads();
+  const int l = blockIdx.x * 256 + tid;
+  if (l >= d.L) return;
+  float cm[64];
+  const float* pc = P + ((size_t)b * N3 + N) * d.L + l;
+#pragma unroll
+  for (int nn = 0; nn < 64; ++nn) cm[nn] = __ldg(pc + (size_t)nn * d.L);
+  float* yb = y + (size_t)b * d.C * d.L + l;
+  for (int c = 0; c < d.C; ++c) {
+    const float4* h4 = reinterpret_cast<const float4*>(ho_s + c * 64);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float4 h = h4[i];
+      s0 = fmaf(h.x, cm[4 * i + 0], s0);
+      s1 = fmaf(h.y, cm[4 * i + 1], s1);
+      s2 = fmaf(h.z, cm[4 * i + 2], s2);
+      s3 = fmaf(h.w, cm[4 * i + 3], s3);
+    }
+    yb[(size_t)c * d.L] = (s0 + s1) + (s2 + s3);
+  }
+}
+
+// ================================================================================================ backward
+// ---- dho partials: part[b,t,c,n] = sum_{l in CTA range} dy[b,c,l] Cm[b,n,l].  grid (T, B).
+template <int CPT>
+__global__ void __launch_bounds__(256) hsm_contract_kernel(const float* __restrict__ u, const float* __restrict__ P,
+                                                           float* __restrict__ part, Dims d) {
+  extern __shared__ __align__(16) float smem[];
+  float* v_s = smem;            // [SUB][65]
+  float* u_s = v_s + SUB * 65;  // [C][SUB]
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int b = blockIdx.y, t = blockIdx.x, n = tid & 63, cg = tid >> 6;
+  float acc[CPT];
+#pragma unroll
+  for (int k = 0; k < CPT; ++k) acc[k] = 0.f;
+  const float* ub = u + (size_t)b * d.C * d.L;
+  const float* Pc = P + ((size_t)b * N3 + N) * d.L;
+  for (int sub = 0; sub < SUBS_PER_CTA; ++sub) {
+    const int l0 = (t * SUBS_PER_CTA + sub) * SUB;
+    if (l0 >= d.L) break;
+    __syncthreads();
+    for (int i = tid; i < d.C * SUB; i += 256) {
+      int c = i / SUB, li = i - c * SUB;
+      u_s[i] = (l0 + li < d.L) ? __ldg(ub + (size_t)c * d.L + l0 + li) : 0.f;
+    }
+    for (int j = 0; j < 8; ++j) {
+      const int ns = wid * 8 + j;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        int l = l0 + lane + 32 * k;
+        v_s[(lane + 32 * k) * 65 + ns] = (l < d.L) ? __ldg(Pc + (size_t)ns * d.L + l) : 0.f;
+      }
+    }
+    __syncthreads();
+    contract_subtile<CPT>(u_s, v_s, n, cg, d.C, acc);
+  }
+  const size_t bt = (size_t)b * d.T + t;
+#pragma unroll
+  for (int k = 0; k < CPT; ++k) {
+    int c = cg + 4 * k;
+    if (c < d.C) part[(bt * d.C + c) * 64 + n] = acc[k];
+  }
+}
+
+// ---- gate backward on (C,64) tiles.  grid B, 256 threads.  Per-batch weight-gradient partials -> wpart[b][...]
+//      layout of wpart[b]: dWo (C*C) | dWhz (2C*C) | dD (1)
+__global__ void __launch_bounds__(256) hsm_gate_bwd_kernel(const float* __restrict__ part_dho, const float* __restrict__ dh,
+                                                           const float* __restrict__ hs,
+                                                           const float* __restrict__ hz, const float* __restrict__ whz,
+                                                           const float* __restrict__ wo, const float* __restrict__ Dp,
+                                                           float* __restrict__ dhs_out, float* __restrict__ r_out,
+                                                           float* __restrict__ wpart, Dims d) {
+  extern __shared__ __align__(16) float smem[];
+  const int C = d.C;
+  float* dho_s = smem;               // [C][64]
+  float* v_s = dho_s + C * 64;       // [C][64]
+  float* hs_s = v_s + C * 64;        // [C][64]
+  float* dhz_s = hs_s + C * 64;      // [2C][64]
+  float* red_s = dhz_s + 2 * C * 64; // [256]
+  const int tid = threadIdx.x, n = tid & 63, cg = tid >> 6, b = blockIdx.x;
+  const float Dv = Dp[0];
+  for (int c = cg; c < C; c += 4) {
+    float a = 0.f;
+    for (int t = 0; t < d.T; ++t) a += part_dho[(((size_t)b * d.T + t) * C + c) * 64 + n];
+    if (dh) a += dh[((size_t)b * C + c) * 64 + n];
+    dho_s[c * 64 + n] = a;
+    hs_s[c * 64 + n] = hs[((size_t)b * C + c) * 64 + n];
+    float hh = hz[((size_t)b * 2 * C + c) * 64 + n], z = hz[((size_t)b * 2 * C + C + c) * 64 + n];
+    v_s[c * 64 + n] = hh * (siluf_(z) + Dv);
+  }
+  __syncthreads();
+  float dD_local = 0.f;
+  for (int c = cg; c < C; c += 4) {
+    float dv = 0.f;
+    for (int dd = 0; dd < C; ++dd) dv = fmaf(__ldg(wo + (size_t)dd * C + c), dho_s[dd * 64 + n], dv);
+    float hh = hz[((size_t)b * 2 * C + c) * 64 + n], z = hz[((size_t)b * 2 * C + C + c) * 64 + n];
+    dhz_s[c * 64 + n] = dv * (siluf_(z) + Dv);
+    dhz_s[(C + c) * 64 + n] = dv * hh * silu_gradf_(z);
+    dD_local = fmaf(dv, hh, dD_local);
+  }
+  red_s[tid] = dD_local;
+  __syncthreads();
+  float rn = 0.f;
+  for (int c = cg; c < C; c += 4) {
+    float a = 0.f;
+    for (int dd = 0; dd < 2 * C; ++dd) a = fmaf(__ldg(whz + (size_t)dd * C + c), dhz_s[dd * 64 + n], a);
+    dhs_out[((size_t)b * C + c) * 64 + n] = a;
+    rn = fmaf(a, hs_s[c * 64 + n], rn);
+  }
+  // r[n] = sum_c dhs[c][n] hs[c][n]: four channel groups hold partial sums for the same n
+  __syncthreads();
+  float dD_tot = 0.f;
+  if (tid == 0) {
+    for (int i = 0; i < 256; ++i) dD_tot += red_s[i];
+  }
+  __syncthreads();
+  red_s[tid] = rn;
+  __syncthreads();
+  if (cg == 0) r_out[(size_t)b * 64 + n] = (red_s[n] + red_s[64 + n]) + (red_s[128 + n] + red_s[192 + n]);
+  float* wb = wpart + (size_t)b * (3 * C * C + 1);
+  if (tid == 0) wb[3 * C * C] = dD_tot;
+  // dWo[dd][c] = sum_n dho[dd][n] v[c][n] ; dWhz[dd][c] = sum_n dhz[dd][n] hs[c][n]
+  for (int i = tid; i < 3 * C * C; i += 256) {
+    const float *ar, *br;
+    if (i < C * C) { ar = dho_s + (i / C) * 64; br = v_s + (i % C) * 64; }
+    else { int k = i - C * C; ar = dhz_s + (k / C) * 64; br = hs_s + (k % C) * 64; }
+    float a = 0.f;
+    for (int k = 0; k < 64; ++k) {
+      int nn = (k + tid) & 63;  // rotate the start so the 32 lanes hit 32 different banks
+      a = fmaf(ar[nn], br[nn], a);
+    }
+    wb[i] = a;
+  }
+}
+
+// ---- dP = [dBm; dCm; ddt] and the direct part of dx.  thread = position.  grid (ceil(L/256), B).
+__global__ void __launch_bounds__(256) hsm_dp_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                     const float* __restrict__ P, const float* __restrict__ stats,
+                                                     const float* __restrict__ dhs, const float* __restrict__ ho,
+                                                     const float* __restrict__ r, float* __restrict__ dP, float* __restrict__ dx,
+                                                     Dims d) {
+  extern __shared__ __align__(16) float smem[];
+  const int C = d.C;
+  float* dhs_s = smem;            // [C][64]
+  float* ho_s = dhs_s + C * 64;   // [C][64]
+  float* m_s = ho_s + C * 64;     // [64] max, [64] 1/sum, [64] r
+  const int tid = threadIdx.x, b = blockIdx.y;
+  for (int i = tid; i < C * 64; i += 256) {
+    dhs_s[i] = dhs[(size_t)b * C * 64 + i];
+    ho_s[i] = ho[(size_t)b * C * 64 + i];
+  }
+  if (tid < 64) {
+    m_s[tid] = stats[(size_t)b * 128 + tid];
+    m_s[64 + tid] = 1.0f / stats[(size_t)b * 128 + 64 + tid];
+    m_s[128 + tid] = r[(size_t)b * 64 + tid];
+  }
+  __syncthreads();
+  const int l = blockIdx.x * 256 + tid;
+  if (l >= d.L) return;
+  const float* xb = x + (size_t)b * C * d.L + l;
+  const float* dyb = dy + (size_t)b * C * d.L + l;
+  const float* Pb = P + (size_t)b * N3 * d.L + l;
+  float* dPb = dP + (size_t)b * N3 * d.L + l;
+  float t[64];
+#pragma unroll
+  for (int nn = 0; nn < 64; ++nn) t[nn] = 0.f;
+  // dG[n] = sum_c dhs[c][n] x[c]
+  for (int c = 0; c < C; ++c) {
+    float xv = __ldg(xb + (size_t)c * d.L);
+    const float4* g4 = reinterpret_cast<const float4*>(dhs_s + c * 64);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float4 g = g4[i];
+      t[4 * i + 0] = fmaf(g.x, xv, t[4 * i + 0]);
+      t[4 * i + 1] = fmaf(g.y, xv, t[4 * i + 1]);
+      t[4 * i + 2] = fmaf(g.z, xv, t[4 * i + 2]);
+      t[4 * i + 3] = fmaf(g.w, xv, t[4 * i + 3]);
+    }
+  }
+#pragma unroll
+  for (int nn = 0; nn < 64; ++nn) {
+    float dtv = __ldg(Pb + (size_t)(2 * N + nn) * d.L);
+    float bm = __ldg(Pb + (size_t)nn * d.L);
+    float a = expf(dtv - m_s[nn]) * m_s[64 + nn];
+    float dG = t[nn];
+    dPb[(size_t)nn * d.L] = dG * a;                                   // dBm
+    dPb[(size_t)(2 * N + nn) * d.L] = a * (dG * bm - m_s[128 + nn]);  // ddt
+    t[nn] = a * bm;
+  }
+  // direct dx[c] = sum_n dhs[c][n] A[n] Bm[n]
+  float* dxb = dx + (size_t)b * C * d.L + l;
+  for (int c = 0; c < C; ++c) {
+    const float4* g4 = reinterpret_cast<const float4*>(dhs_s + c * 64);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float4 g = g4[i];
+      s0 = fmaf(g.x, t[4 * i + 0], s0);
+      s1 = fmaf(g.y, t[4 * i + 1], s1);
+      s2 = fmaf(g.z, t[4 * i + 2], s2);
+      s3 = fmaf(g.w, t[4 * i + 3], s3);
+    }
+    dxb[(size_t)c * d.L] = (s0 + s1) + (s2 + s3);
+  }
+  // dCm[n] = sum_c ho[c][n] dy[c]
+#pragma unroll
+  for (int nn = 0; nn < 64; ++nn) t[nn] = 0.f;
+  for (int c = 0; c < C; ++c) {
+    float gv = __ldg(dyb + (size_t)c * d.L);
+    const float4* h4 = reinterpret_cast<const float4*>(ho_s + c * 64);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float4 h = h4[i];
+      t[4 * i + 0] = fmaf(h.x, gv, t[4 * i + 0]);
+      t[4 * i + 1] = fmaf(h.y, gv, t[4 * i + 1]);
+      t[4 * i + 2] = fmaf(h.z, gv, t[4 * i + 2]);
+      t[4 * i + 3] = fmaf(h.w, gv, t[4 * i + 3]);
+    }
+  }
+#pragma unroll
+  for (int nn = 0; nn < 64; ++nn) dPb[(size_t)(N + nn) * d.L] = t[nn];
+}
+
+// ---- projection / depthwise backward on a spatial tile.  grid (tiles, B), 256 threads = 8x32 interior positions.
+//      dQ = dw3x3^T(dP) ; dx += Wp^T dQ ; per-CTA partials of dWp[n][c] = sum dQ x and dWd[n][tap] = sum Q(l+tap) dP(l).
+//      partial layout per CTA: dWp (192*C) | dWd (192*9)
+constexpr int BN = 16;  // projected channels per pass
+__global__ void __launch_bounds__(256) hsm_proj_dw_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wp,
+                                                              const float* __restrict__ wd, const float* __restrict__ dP,
+                                                              float* __restrict__ dx, float* __restrict__ partial, Dims d) {
+  extern __shared__ __align__(16) float smem[];
+  const int C = d.C;
+  float* dp_s = smem;                 // [BN][NHALO]
+  float* q_s = dp_s + BN * NHALO;     // [BN][NHALO]
+  float* dq_s = q_s + BN * NHALO;     // [256][BN+1]
+  float* x_s = dq_s + 256 * (BN + 1); // [C][256]
+  float* wp_s = x_s + C * 256;        // [C][BN]  (c-major for the Q recompute)
+  float* wpt_s = wp_s + C * BN;       // [BN][C]  (n-major for dx)
+  float* wd_s = wpt_s + BN * C;       // [BN][9]
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int ty0 = (blockIdx.x / d.tiles_x) * TH, tx0 = (blockIdx.x % d.tiles_x) * TW;
+  const int b = blockIdx.y;
+  const int ly = tid >> 5, lx = tid & 31;
+  const int gy = ty0 + ly, gx = tx0 + lx;
+  const bool inside = gy < d.H && gx < d.H;
+  const float* xb = x + (size_t)b * C * d.L;
+  for (int c = 0; c < C; ++c) x_s[c * 256 + tid] = inside ? __ldg(xb + (size_t)c * d.L + (size_t)gy * d.H + gx) : 0.f;
+  float* pb = partial + ((size_t)b * gridDim.x + blockIdx.x) * (size_t)(N3 * C + N3 * 9);
+  float dxa[64];
+#pragma unroll
+  for (int c = 0; c < 64; ++c) dxa[c] = 0.f;
+
+  for (int n0 = 0; n0 < N3; n0 += BN) {
+    __syncthreads();
+    for (int i = tid; i < C * BN; i += 256) {
+      int c = i / BN, nn = i - c * BN;
+      float w = wp[(size_t)(n0 + nn) * C + c];
+      wp_s[i] = w;
+      wpt_s[nn * C + c] = w;
+    }
+    for (int i = tid; i < BN * 9; i += 256) wd_s[i] = wd[(size_t)n0 * 9 + i];
+    // dP tile with halo (zero outside the image)
+    for (int i = tid; i < BN * NHALO; i += 256) {
+      int nn = i / NHALO, pos = i - nn * NHALO;
+      int hy = pos / HW_, hx = pos - hy * HW_;
+      int yy = ty0 + hy - 1, xx = tx0 + hx - 1;
+      dp_s[i] = (yy >= 0 && yy < d.H && xx >= 0 && xx < d.H)
+                    ? __ldg(dP + ((size_t)b * N3 + n0 + nn) * d.L + (size_t)yy * d.H + xx) : 0.f;
+    }
+    __syncthreads();
+    // Q on the halo (recomputed projection)
+    for (int pos = tid; pos < NHALO; pos += 256) {
+      int hy = pos / HW_, hx = pos - hy * HW_;
+      int yy = ty0 + hy - 1, xx = tx0 + hx - 1;
+      float q[BN];
+#pragma unroll
+      for (int i = 0; i < BN; ++i) q[i] = 0.f;
+      if (yy >= 0 && yy < d.H && xx >= 0 && xx < d.H) {
+        const float* xp = xb + (size_t)yy * d.H + xx;
+        for (int c = 0; c < C; ++c) {
+          float xv = __ldg(xp + (size_t)c * d.L);
+          const float4* w4 = reinterpret_cast<const float4*>(wp_s + c * BN);
+#pragma unroll
+          for (int i = 0; i < BN / 4; ++i) {
+            float4 w = w4[i];
+            q[4 * i + 0] = fmaf(xv, w.x, q[4 * i + 0]);
+            q[4 * i + 1] = fmaf(xv, w.y, q[4 * i + 1]);
+            q[4 * i + 2] = fmaf(xv, w.z, q[4 * i + 2]);
+            q[4 * i + 3] = fmaf(xv, w.w, q[4 * i + 3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < BN; ++i) q_s[i * NHALO + pos] = q[i];
+    }
+    // dQ at the interior position (transposed depthwise conv) and dx accumulation
+    {
+      float dq[BN];
+#pragma unroll
+      for (int nn = 0; nn < BN; ++nn) {
+        const float* w = wd_s + nn * 9;
+        const float* g = dp_s + nn * NHALO + (ly + 2) * HW_ + (lx + 2);
+        float s = w[0] * g[0] + w[1] * g[-1] + w[2] * g[-2];
+        s += w[3] * g[-HW_] + w[4] * g[-HW_ - 1] + w[5] * g[-HW_ - 2];
+        s += w[6] * g[-2 * HW_] + w[7] * g[-2 * HW_ - 1] + w[8] * g[-2 * HW_ - 2];
+        dq[nn] = inside ? s : 0.f;
+        dq_s[tid * (BN + 1) + nn] = dq[nn];
+      }
+#pragma unroll
+      for (int nn = 0; nn < BN; ++nn) {
+        const float* wr = wpt_s + nn * C;
+#pragma unroll
+        for (int c = 0; c < 64; ++c)
+          if (c < C) dxa[c] = fmaf(wr[c], dq[nn], dxa[c]);
+      }
+    }
+    __syncthreads();
+    // dWp partial: thread owns projected channel nn = tid % BN, input channels c = tid / BN + 16 k
+    {
+      const int nn = tid % BN, c0 = tid / BN;  // c0 in [0,16)
+      for (int c = c0; c < C; c += 256 / BN) {
+        float a = 0.f;
+        const float* xr = x_s + c * 256;
+        for (int p = 0; p < 256; ++p) a = fmaf(dq_s[p * (BN + 1) + nn], xr[p], a);
+        pb[(size_t)(n0 + nn) * C + c] = a;
+      }
+    }
+    // dWd partial: warp handles channels nn = wid*2, wid*2+1; lanes stride the 256 interior positions
+    for (int j = 0; j < BN / 8; ++j) {
+      const int nn = wid * (BN / 8) + j;
+      float a[9];
+#pragma unroll
+      for (int tp = 0; tp < 9; ++tp) a[tp] = 0.f;
+      for (int p = lane; p < 256; p += 32) {
+        int py = p >> 5, px = p & 31;
+        float g = dp_s[nn * NHALO + (py + 1) * HW_ + (px + 1)];
+        const float* qr = q_s + nn * NHALO + py * HW_ + px;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) a[ky * 3 + kx] = fmaf(qr[ky * HW_ + kx], g, a[ky * 3 + kx]);
+      }
+#pragma unroll
+      for (int tp = 0; tp < 9; ++tp) {
+        float s = warp_sum(a[tp]);
+        if (lane == 0) pb[(size_t)N3 * C + (size_t)(n0 + nn) * 9 + tp] = s;
+      }
+    }
+  }
+  if (inside) {
+    float* dxb = dx + (size_t)b * C * d.L + (size_t)gy * d.H + gx;
+#pragma unroll
+    for (int c = 0; c < 64; ++c)
+      if (c < C) dxb[(size_t)c * d.L] += dxa[c];
+  }
+}
+
+// ---- fixed-order reductions of the weight-gradient partials
+__global__ void hsm_wgrad_reduce_kernel(const float* __restrict__ partial, int nparts, int per, float* __restrict__ out0, int n0,
+                                        float* __restrict__ out1, int n1, float* __restrict__ out2, int n2) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n0 + n1 + n2) return;
+  float s = 0.f;
+  for (int k = 0; k < nparts; ++k) s += partial[(size_t)k * per + idx];
+  if (idx < n0) out0[idx] = s;
+  else if (idx < n0 + n1) out1[idx - n0] = s;
+  else out2[idx - n0 - n1] = s;
+}
+
+__global__ void fill_kernel(float* __restrict__ p, int n, float v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ================================================================================================ LayerNorm1D
+__global__ void __launch_bounds__(256) ln1d_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, float* __restrict__ y,
+                                                       float* __restrict__ rstd_out, int B, int C, int L, float eps) {
+  long long p = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (p >= (long long)B * L) return;
+  int b = (int)(p / L), l = (int)(p - (long long)b * L);
+  const float* xp = x + (size_t)b * C * L + l;
+  float mean = 0.f;
+  for (int c = 0; c < C; ++c) mean += __ldg(xp + (size_t)c * L);
+  mean /= (float)C;
+  float var = 0.f;
+  for (int c = 0; c < C; ++c) {
+    float dlt = __ldg(xp + (size_t)c * L) - mean;
+    var = fmaf(dlt, dlt, var);
+  }
+  var /= (float)C;
+  float sd = sqrtf(var + eps);
+  float* yp = y + (size_t)b * C * L + l;
+  for (int c = 0; c < C; ++c) yp[(size_t)c * L] = (__ldg(xp + (size_t)c * L) - mean) / sd * w[c] + bias[c];
+  if (rstd_out) rstd_out[p] = 1.0f / sd;
+}
+
+__global__ void __launch_bounds__(256) ln1d_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                       const float* __restrict__ dy, float* __restrict__ dx,
+                                                       float* __restrict__ dw, float* __restrict__ db, int B, int C, int L,
+                                                       float eps) {
+  extern __shared__ float red[];  // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += 256) red[i] = 0.f;
+  __syncthreads();
+  long long p = (long long)blockIdx.x * 256 + threadIdx.x;
+  const bool valid = p < (long long)B * L;
+  int b = valid ? (int)(p / L) : 0, l = valid ? (int)(p - (long long)b * L) : 0;
+  const float* xp = x + (size_t)b * C * L + l;
+  const float* gp = dy + (size_t)b * C * L + l;
+  float mean = 0.f, var = 0.f, rstd = 0.f, m1 = 0.f, m2 = 0.f;
+  if (valid) {
+    for (int c = 0; c < C; ++c) mean += __ldg(xp + (size_t)c * L);
+    mean /= (float)C;
+    for (int c = 0; c < C; ++c) {
+      float dlt = __ldg(xp + (size_t)c * L) - mean;
+      var = fmaf(dlt, dlt, var);
+    }
+    var /= (float)C;
+    rstd = 1.0f / sqrtf(var + eps);
+    for (int c = 0; c < C; ++c) {
+      float xh = (__ldg(xp + (size_t)c * L) - mean) * rstd;
+      float g = __ldg(gp + (size_t)c * L) * w[c];
+      m1 += g;
+      m2 = fmaf(g, xh, m2);
+    }
+    m1 /= (float)C;
+    m2 /= (float)C;
+  }
+  const int lane = threadIdx.x & 31;
+  for (int c = 0; c < C; ++c) {
+    float xh = 0.f, gy = 0.f;
+    if (valid) {
+      xh = (__ldg(xp + (size_t)c * L) - mean) * rstd;
+      gy = __ldg(gp + (size_t)c * L);
+      dx[(size_t)b * C * L + (size_t)c * L + l] = rstd * (gy * w[c] - m1 - xh * m2);
+    }
+    float sw = warp_sum(gy * xh), sb = warp_sum(gy);
+    if (lane == 0) { atomicAdd(&red[c], sw); atomicAdd(&red[C + c], sb); }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += 256) { atomicAdd(dw + i, red[i]); atomicAdd(db + i, red[C + i]); }
+}
+
+static int check(const kmu_hsmssd_desc* d, const char* who) {
+  KMU_REQUIRE(d != nullptr, KMU_ERR_BAD_ARG, "%s: null descriptor", who);
+  KMU_REQUIRE(d->B > 0 && d->C > 0 && d->L > 0 && d->H > 0, KMU_ERR_BAD_ARG, "%s: non-positive shape", who);
+  KMU_REQUIRE(d->H * d->H == d->L, KMU_ERR_BAD_ARG, "%s: L=%d is not H*H with H=%d (the reference requires square maps)", who,
+              d->L, d->H);
+  KMU_REQUIRE(d->N == N, KMU_ERR_UNSUPPORTED, "%s: state_dim %d != 64", who, d->N);
+  KMU_REQUIRE(d->C <= 64 && d->C % 4 == 0, KMU_ERR_UNSUPPORTED, "%s: C=%d must be a multiple of 4 and <= 64", who, d->C);
+  KMU_REQUIRE(d->B <= 65535, KMU_ERR_UNSUPPORTED, "%s: B=%d > 65535", who, d->B);
+  return KMU_OK;
+}
+
+struct FwdWs { size_t part_m, part_s, part_hs, total; };
+static FwdWs fwd_ws(const Dims& d) {
+  FwdWs w;
+  size_t o = 0;
+  w.part_m = o; o += align_up((size_t)d.B * d.T * 64 * 4, 256);
+  w.part_s = o; o += align_up((size_t)d.B * d.T * 64 * 4, 256);
+  w.part_hs = o; o += align_up((size_t)d.B * d.T * d.C * 64 * 4, 256);
+  w.total = o;
+  return w;
+}
+struct BwdWs { size_t part_dho, dhs, r, wpart, dP, tpart, total; };
+static BwdWs bwd_ws(const Dims& d) {
+  BwdWs w;
+  size_t o = 0;
+  w.part_dho = o; o += align_up((size_t)d.B * d.T * d.C * 64 * 4, 256);
+  w.dhs = o; o += align_up((size_t)d.B * d.C * 64 * 4, 256);
+  w.r = o; o += align_up((size_t)d.B * 64 * 4, 256);
+  w.wpart = o; o += align_up((size_t)d.B * (3 * d.C * d.C + 1) * 4, 256);
+  w.dP = o; o += align_up((size_t)d.B * N3 * d.L * 4, 256);
+  w.tpart = o; o += align_up((size_t)d.B * d.tiles_x * d.tiles_y * (N3 * d.C + N3 * 9) * 4, 256);
+  w.total = o;
+  return w;
+}
+
+template <typename K>
+static void opt_in_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+}  // namespace hsm
+}  // namespace kmu
+
+using namespace kmu;
+using namespace kmu::hsm;
+
+extern "C" {
+
+size_t kmu_hsmssd_fwd_workspace_bytes(const kmu_hsmssd_desc* dd) {
+  if (check(dd, "hsmssd_fwd_workspace_bytes") != KMU_OK) return 0;
+  return fwd_ws(make_dims(*dd)).total;
+}
+size_t kmu_hsmssd_bwd_workspace_bytes(const kmu_hsmssd_desc* dd) {
+  if (check(dd, "hsmssd_bwd_workspace_bytes") != KMU_OK) return 0;
+  return bwd_ws(make_dims(*dd)).total;
+}
+
+int kmu_hsmssd_fwd(const kmu_hsmssd_fwd_args* a, kmu_stream stream) {
+  KMU_REQUIRE(a != nullptr, KMU_ERR_BAD_ARG, "hsmssd_fwd: null args");
+  int st_ = check(&a->d, "hsmssd_fwd");
+  if (st_ != KMU_OK) return st_;
+  KMU_REQUIRE(a->x && a->w_bcdt && a->w_dw && a->w_hz && a->w_out && a->D && a->y && a->h && a->P, KMU_ERR_BAD_ARG,
+              "hsmssd_fwd: null tensor (P scratch is required)");
+  Dims d = make_dims(a->d);
+  FwdWs w = fwd_ws(d);
+  KMU_REQUIRE(a->workspace && a->workspace_bytes >= w.total, KMU_ERR_WORKSPACE, "hsmssd_fwd: workspace %zu < %zu",
+              a->workspace_bytes, w.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)a->workspace;
+  float* part_m = (float*)(ws + w.part_m);
+  float* part_s = (float*)(ws + w.part_s);
+  float* part_hs = (float*)(ws + w.part_hs);
+  {
+    constexpr int NCH = 32;
+    size_t smem = ((size_t)NCH * NHALO + (size_t)d.C * NCH + NCH * 9) * 4;
+    opt_in_smem(hsm_proj_dw_kernel<NCH>, smem);
+    hsm_proj_dw_kernel<NCH><<<dim3(d.tiles_x * d.tiles_y, d.B, N3 / NCH), 256, smem, st>>>(a->x, a->w_bcdt, a->w_dw, a->P, d);
+    KMU_LAUNCH_CHECK("hsm_proj_dw");
+  }
+  {
+    size_t smem = ((size_t)SUB * 65 + (size_t)d.C * SUB + 192) * 4;
+    dim3 grid(d.T, d.B);
+    if (d.C <= 16) {
+      opt_in_smem(hsm_softmax_hs_kernel<4>, smem);
+      hsm_softmax_hs_kernel<4><<<grid, 256, smem, st>>>(a->x, a->P, part_m, part_s, part_hs, d);
+    } else if (d.C <= 32) {
+      opt_in_smem(hsm_softmax_hs_kernel<8>, smem);
+      hsm_softmax_hs_kernel<8><<<grid, 256, smem, st>>>(a->x, a->P, part_m, part_s, part_hs, d);
+    } else {
+      opt_in_smem(hsm_softmax_hs_kernel<16>, smem);
+      hsm_softmax_hs_kernel<16><<<grid, 256, smem, st>>>(a->x, a->P, part_m, part_s, part_hs, d);
+    }
+    KMU_LAUNCH_CHECK("hsm_softmax_hs");
+  }
+  {
+    size_t smem = (size_t)4 * d.C * 64 * 4;
+    opt_in_smem(hsm_combine_gate_kernel, smem);
+    hsm_combine_gate_kernel<<<d.B, 256, smem, st>>>(part_m, part_s, part_hs, a->w_hz, a->w_out, a->D, a->stats, a->hs, a->hz,
+                                                    a->h, d);
+    KMU_LAUNCH_CHECK("hsm_combine_gate");
+  }
+  {
+    size_t smem = (size_t)d.C * 64 * 4;
+    hsm_out_kernel<<<dim3(cdiv(d.L, 256), d.B), 256, smem, st>>>(a->h, a->P, a->y, d);
+    KMU_LAUNCH_CHECK("hsm_out");
+  }
+  return KMU_OK;
+}
+
+int kmu_hsmssd_bwd(const kmu_hsmssd_bwd_args* a, kmu_stream stream) {
+  KMU_REQUIRE(a != nullptr, KMU_ERR_BAD_ARG, "hsmssd_bwd: null args");
+  int st_ = check(&a->d, "hsmssd_bwd");
+  if (st_ != KMU_OK) return st_;
+  KMU_REQUIRE(a->x && a->dy && a->w_bcdt && a->w_dw && a->w_hz && a->w_out && a->D && a->P && a->stats && a->hs && a->hz && a->h,
+              KMU_ERR_BAD_ARG, "hsmssd_bwd: null input tensor");
+  KMU_REQUIRE(a->dx && a->d_w_bcdt && a->d_w_dw && a->d_w_hz && a->d_w_out && a->d_D, KMU_ERR_BAD_ARG,
+              "hsmssd_bwd: null output tensor");
+  Dims d = make_dims(a->d);
+  BwdWs w = bwd_ws(d);
+  KMU_REQUIRE(a->workspace && a->workspace_bytes >= w.total, KMU_ERR_WORKSPACE, "hsmssd_bwd: workspace %zu < %zu",
+              a->workspace_bytes, w.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)a->workspace;
+  float* part_dho = (float*)(ws + w.part_dho);
+  float* dhs = (float*)(ws + w.dhs);
+  float* r = (float*)(ws + w.r);
+  float* wpart = (float*)(ws + w.wpart);
+  float* dP = (float*)(ws + w.dP);
+  float* tpart = (float*)(ws + w.tpart);
+  const int C = d.C;
+  {
+    size_t smem = ((size_t)SUB * 65 + (size_t)C * SUB) * 4;
+    dim3 grid(d.T, d.B);
+    if (C <= 16) {
+      opt_in_smem(hsm_contract_kernel<4>, smem);
+      hsm_contract_kernel<4><<<grid, 256, smem, st>>>(a->dy, a->P, part_dho, d);
+    } else if (C <= 32) {
+      opt_in_smem(hsm_contract_kernel<8>, smem);
+      hsm_contract_kernel<8><<<grid, 256, smem, st>>>(a->dy, a->P, part_dho, d);
+    } else {
+      opt_in_smem(hsm_contract_kernel<16>, smem);
+      hsm_contract_kernel<16><<<grid, 256, smem, st>>>(a->dy, a->P, part_dho, d);
+    }
+    KMU_LAUNCH_CHECK("hsm_contract");
+  }
+  {
+    size_t smem = ((size_t)5 * C * 64 + 256) * 4;
+    opt_in_smem(hsm_gate_bwd_kernel, smem);
+    hsm_gate_bwd_kernel<<<d.B, 256, smem, st>>>(part_dho, a->dh, a->hs, a->hz, a->w_hz, a->w_out, a->D, dhs, r, wpart, d);
+    KMU_LAUNCH_CHECK("hsm_gate_bwd");
+    int n = 3 * C * C + 1;
+    hsm_wgrad_reduce_kernel<<<cdiv(n, 128), 128, 0, st>>>(wpart, d.B, n, a->d_w_out, C * C, a->d_w_hz, 2 * C * C, a->d_D, 1);
+    KMU_LAUNCH_CHECK("hsm_wgrad_reduce(gate)");
+  }
+  {
+    size_t smem = ((size_t)2 * C * 64 + 192) * 4;
+    opt_in_smem(hsm_dp_kernel, smem);
+    hsm_dp_kernel<<<dim3(cdiv(d.L, 256), d.B), 256, smem, st>>>(a->x, a->dy, a->P, a->stats, dhs, a->h, r, dP, a->dx, d);
+    KMU_LAUNCH_CHECK("hsm_dp");
+  }
+  {
+    size_t smem = ((size_t)2 * BN * NHALO + 256 * (BN + 1) + (size_t)C * 256 + 2 * (size_t)C * BN + BN * 9) * 4;
+    opt_in_smem(hsm_proj_dw_bwd_kernel, smem);
+    int tiles = d.tiles_x * d.tiles_y;
+    hsm_proj_dw_bwd_kernel<<<dim3(tiles, d.B), 256, smem, st>>>(a->x, a->w_bcdt, a->w_dw, dP, a->dx, tpart, d);
+    KMU_LAUNCH_CHECK("hsm_proj_dw_bwd");
+    int per = N3 * C + N3 * 9;
+    hsm_wgrad_reduce_kernel<<<cdiv(per, 128), 128, 0, st>>>(tpart, tiles * d.B, per, a->d_w_bcdt, N3 * C, a->d_w_dw, N3 * 9,
+                                                            nullptr, 0);
+    KMU_LAUNCH_CHECK("hsm_wgrad_reduce(proj)");
+  }
+  if (a->d_A) {
+    fill_kernel<<<1, 64, 0, st>>>(a->d_A, N, 0.f);
+    KMU_LAUNCH_CHECK("hsm_fill_dA");
+  }
+  return KMU_OK;
+}
+
+int kmu_layernorm1d_fwd(const float* x, const float* weight, const float* bias, float* y, float* rstd, int32_t B, int32_t C,
+                        int32_t L, float eps, kmu_stream stream) {
+  KMU_REQUIRE(x && weight && bias && y && B > 0 && C > 0 && L > 0, KMU_ERR_BAD_ARG, "layernorm1d_fwd: bad argument");
+  ln1d_fwd_kernel<<<cdiv((long long)B * L, 256), 256, 0, (cudaStream_t)stream>>>(x, weight, bias, y, rstd, B, C, L, eps);
+  KMU_LAUNCH_CHECK("ln1d_fwd");
+  return KMU_OK;
+}
+
+int kmu_layernorm1d_bwd(const float* x, const float* weight, const float* dy, float* dx, float* dweight, float* dbias, int32_t B,
+                        int32_t C, int32_t L, float eps, kmu_stream stream) {
+  KMU_REQUIRE(x && weight && dy && dx && dweight && dbias && B > 0 && C > 0 && L > 0, KMU_ERR_BAD_ARG,
+              "layernorm1d_bwd: bad argument");
+  KMU_REQUIRE(C <= 4096, KMU_ERR_UNSUPPORTED, "layernorm1d_bwd: C=%d > 4096", C);
+  ln1d_bwd_kernel<<<cdiv((long long)B * L, 256), 256, (size_t)2 * C * 4, (cudaStream_t)stream>>>(x, weight, dy, dx, dweight, dbias,
+                                                                                                B, C, L, eps);
+  KMU_LAUNCH_CHECK("ln1d_bwd");
+  return KMU_OK;
+}
+
+}  // extern "C"

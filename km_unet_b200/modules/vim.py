@@ -1,0 +1,143 @@
+"""EfficientViM building blocks with the reference's names, constructor signatures and state_dict layout
+(vim_block_init/vim_utils_init.py:34-130, vim_block_init/efficient_vim_init.py:14-97).
+
+LayerNorm1D and the HSM-SSD mixer run in libkmunet.so.  The depthwise-conv/BatchNorm/FFN shell of the block is still
+composed from torch.nn modules in this round (SURVEY section 8f rank 2 -- next to be fused).
+"""
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+
+class LayerNorm1D(nn.Module):
+    """Channel LayerNorm of (B,C,L)."""
+
+    def __init__(self, num_channels, eps=1e-5, affine=True):
+        super().__init__()
+        self.num_channels, self.eps, self.affine = num_channels, eps, affine
+        if affine:
+            self.weight = nn.Parameter(torch.ones(1, num_channels, 1))
+            self.bias = nn.Parameter(torch.zeros(1, num_channels, 1))
+        else:
+            self.register_parameter("weight", None)
+            self.register_parameter("bias", None)
+
+    def forward(self, x):
+        if self.affine:
+            return ops.layernorm1d(x, self.weight, self.bias, self.eps)
+        one = torch.ones(1, self.num_channels, 1, device=x.device)
+        return ops.layernorm1d(x, one, torch.zeros_like(one), self.eps)
+
+
+class LayerNorm2D(nn.Module):
+    """Channel LayerNorm of (B,C,H,W) (unused by KM-UNet; kept for import parity)."""
+
+    def __init__(self, num_channels, eps=1e-5, affine=True):
+        super().__init__()
+        self.num_channels, self.eps, self.affine = num_channels, eps, affine
+        if affine:
+            self.weight = nn.Parameter(torch.ones(1, num_channels, 1, 1))
+            self.bias = nn.Parameter(torch.zeros(1, num_channels, 1, 1))
+        else:
+            self.register_parameter("weight", None)
+            self.register_parameter("bias", None)
+
+    def forward(self, x):
+        B, C, H, W = x.shape
+        w = self.weight if self.affine else torch.ones(1, C, 1, device=x.device)
+        b = self.bias if self.affine else torch.zeros(1, C, 1, device=x.device)
+        return ops.layernorm1d(x.reshape(B, C, H * W), w.reshape(1, C, 1), b.reshape(1, C, 1), self.eps).reshape(B, C, H, W)
+
+
+class _ConvLayer(nn.Module):
+    conv_cls = None
+
+    def _finish(self, out_dim, norm, act_layer, bn_weight_init):
+        self.norm = norm(num_features=out_dim) if norm else None
+        self.act = act_layer() if act_layer else None
+        if self.norm:
+            nn.init.constant_(self.norm.weight, bn_weight_init)
+            nn.init.constant_(self.norm.bias, 0)
+
+    def forward(self, x):
+        x = self.conv(x)
+        if self.norm:
+            x = self.norm(x)
+        if self.act:
+            x = self.act(x)
+        return x
+
+
+class ConvLayer2D(_ConvLayer):
+    def __init__(self, in_dim, out_dim, kernel_size=3, stride=1, padding=0, dilation=1, groups=1, norm=nn.BatchNorm2d,
+                 act_layer=nn.ReLU, bn_weight_init=1):
+        super().__init__()
+        self.conv = nn.Conv2d(in_dim, out_dim, (kernel_size, kernel_size), (stride, stride), (padding, padding),
+                              (dilation, dilation), groups, bias=False)
+        self._finish(out_dim, norm, act_layer, bn_weight_init)
+
+
+class ConvLayer1D(_ConvLayer):
+    def __init__(self, in_dim, out_dim, kernel_size=3, stride=1, padding=0, dilation=1, groups=1, norm=nn.BatchNorm1d,
+                 act_layer=nn.ReLU, bn_weight_init=1):
+        super().__init__()
+        self.conv = nn.Conv1d(in_dim, out_dim, kernel_size, stride, padding, dilation, groups, bias=False)
+        self._finish(out_dim, norm, act_layer, bn_weight_init)
+
+
+class FFN(nn.Module):
+    def __init__(self, in_dim, dim):
+        super().__init__()
+        self.fc1 = ConvLayer2D(in_dim, dim, 1)
+        self.fc2 = ConvLayer2D(dim, in_dim, 1, act_layer=None, bn_weight_init=0)
+
+    def forward(self, x):
+        return self.fc2(self.fc1(x))
+
+
+class HSMSSD(nn.Module):
+    """Hidden-state mixer.  Parameters live in the same child modules as the reference (BCdt_proj.conv, dw.conv,
+    hz_proj.conv, out_proj.conv, A, D) so checkpoints load unchanged; forward() hands their weights to one fused op."""
+
+    def __init__(self, d_model, ssd_expand=1, A_init_range=(1, 16), state_dim=64):
+        super().__init__()
+        self.ssd_expand = ssd_expand
+        self.d_inner = int(ssd_expand * d_model)
+        self.state_dim = state_dim
+        if self.d_inner != d_model:
+            raise NotImplementedError("km_unet_b200.HSMSSD implements ssd_expand == 1 (the only value KM-UNet uses)")
+        conv_dim = 3 * state_dim
+        self.BCdt_proj = ConvLayer1D(d_model, conv_dim, 1, norm=None, act_layer=None)
+        self.dw = ConvLayer2D(conv_dim, conv_dim, 3, 1, 1, groups=conv_dim, norm=None, act_layer=None, bn_weight_init=0)
+        self.hz_proj = ConvLayer1D(d_model, 2 * self.d_inner, 1, norm=None, act_layer=None)
+        self.out_proj = ConvLayer1D(self.d_inner, d_model, 1, norm=None, act_layer=None, bn_weight_init=0)
+        self.A = nn.Parameter(torch.empty(state_dim, dtype=torch.float32).uniform_(*A_init_range))
+        self.act = nn.SiLU()
+        self.D = nn.Parameter(torch.ones(1))
+        self.D._no_weight_decay = True
+
+    def forward(self, x):
+        return ops.hsmssd(x, self.BCdt_proj.conv.weight, self.dw.conv.weight, self.hz_proj.conv.weight,
+                          self.out_proj.conv.weight, self.A, self.D, self.state_dim)
+
+
+class EfficientViMBlock(nn.Module):
+    def __init__(self, dim, mlp_ratio=4., ssd_expand=1, state_dim=64):
+        super().__init__()
+        self.dim, self.mlp_ratio = dim, mlp_ratio
+        self.mixer = HSMSSD(d_model=dim, ssd_expand=ssd_expand, state_dim=state_dim)
+        self.norm = LayerNorm1D(dim)
+        self.dwconv1 = ConvLayer2D(dim, dim, 3, padding=1, groups=dim, bn_weight_init=0, act_layer=None)
+        self.dwconv2 = ConvLayer2D(dim, dim, 3, padding=1, groups=dim, bn_weight_init=0, act_layer=None)
+        self.ffn = FFN(in_dim=dim, dim=int(dim * mlp_ratio))
+        self.alpha = nn.Parameter(1e-4 * torch.ones(4, dim), requires_grad=True)
+
+    def forward(self, x):
+        a = torch.sigmoid(self.alpha).view(4, -1, 1, 1)
+        x = (1 - a[0]) * x + a[0] * self.dwconv1(x)
+        mixed, _ = self.mixer(self.norm(x.flatten(2)))
+        x = (1 - a[1]) * x + a[1] * mixed
+        x = (1 - a[2]) * x + a[2] * self.dwconv2(x)
+        x = (1 - a[3]) * x + a[3] * self.ffn(x)
+        return x

@@ -1,0 +1,268 @@
+"""torch.autograd bridges to the C ABI (one C call per autograd node).
+
+PyTorch is used for plumbing only: device memory (the caching allocator owns every buffer), the current stream and
+autograd bookkeeping.  All arithmetic happens in libkmunet.so.  CPU tensors raise -- there is no fallback.
+"""
+import ctypes as C
+
+import torch
+from torch.amp import custom_bwd, custom_fwd
+
+from . import _lib
+from ._lib import (DysBwdArgs, DysDesc, DysFwdArgs, HsmBwdArgs, HsmDesc, HsmFwdArgs, KanBwdArgs, KanDesc, KanFwdArgs,
+                   KMU_PREC_BF16, KMU_PREC_FP32, check, ptr, stream_ptr)
+
+__all__ = ["kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dysample_sample", "KMU_PREC_FP32", "KMU_PREC_BF16"]
+
+
+def _workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _f32c(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------------ KANConv2d
+class _KanConv2dFn(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, base_weight, spline_weight, spline_scaler, grid, ksize, stride, padding, grid_size, spline_order,
+                precision):
+        lib = _lib.lib()
+        x = x.contiguous()
+        B, Cin, H, W = x.shape
+        Cout = base_weight.shape[0]
+        desc = KanDesc(B, Cin, H, W, Cout, ksize, stride, padding, grid_size, spline_order, precision,
+                       0 if spline_scaler is None else 1)
+        Ho = (H + 2 * padding - ksize) // stride + 1
+        Wo = (W + 2 * padding - ksize) // stride + 1
+        bw, sw, gr = base_weight.contiguous(), spline_weight.contiguous(), grid.contiguous()
+        sc = None if spline_scaler is None else spline_scaler.contiguous()
+        nbytes = lib.kmu_kanconv2d_fwd_workspace_bytes(C.byref(desc))
+        if nbytes == 0:
+            raise RuntimeError("kanconv2d: " + _lib.last_error())
+        ws = _workspace(nbytes, x.device)
+        y = torch.empty(B, Cout, Ho, Wo, dtype=torch.float32, device=x.device)
+        args = KanFwdArgs(desc, ptr(x), ptr(bw), ptr(sw), ptr(sc), ptr(gr), ptr(y), ws.data_ptr(), ws.numel())
+        check(lib.kmu_kanconv2d_fwd(C.byref(args), stream_ptr()), "kmu_kanconv2d_fwd")
+        ctx.save_for_backward(x, bw, sw, sc, gr)
+        ctx.desc = desc
+        return y
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        lib = _lib.lib()
+        x, bw, sw, sc, gr = ctx.saved_tensors
+        desc = ctx.desc
+        dy = dy.to(torch.float32).contiguous()
+        need_x = ctx.needs_input_grad[0]
+        need_w = any(ctx.needs_input_grad[1:4])
+        dx = torch.empty_like(x) if need_x else None
+        dbw = torch.empty_like(bw) if need_w else None
+        dsw = torch.empty_like(sw) if need_w else None
+        dsc = torch.empty_like(sc) if (need_w and sc is not None) else None
+        nbytes = lib.kmu_kanconv2d_bwd_workspace_bytes(C.byref(desc))
+        ws = _workspace(nbytes, x.device)
+        args = KanBwdArgs(desc, ptr(x), ptr(dy), ptr(bw), ptr(sw), ptr(sc), ptr(gr), ptr(dx), ptr(dbw), ptr(dsw), ptr(dsc),
+                          ws.data_ptr(), ws.numel())
+        check(lib.kmu_kanconv2d_bwd(C.byref(args), stream_ptr()), "kmu_kanconv2d_bwd")
+        return dx, dbw, dsw, dsc, None, None, None, None, None, None, None
+
+
+def kanconv2d(x, base_weight, spline_weight, spline_scaler, grid, kernel_size, stride=1, padding=0, grid_size=5,
+              spline_order=3, precision=KMU_PREC_FP32):
+    """KANConv2d.forward (convKAN/KANConv2Dlayers.py:15-37): x (B,Cin,H,W) -> (B,Cout,Ho,Wo)."""
+    if not x.is_cuda:
+        raise RuntimeError("km_unet_b200.kanconv2d: CUDA tensors only (no CPU fallback)")
+    return _KanConv2dFn.apply(x, base_weight, spline_weight, spline_scaler, grid, int(kernel_size), int(stride), int(padding),
+                              int(grid_size), int(spline_order), int(precision))
+
+
+def kanlinear(x, base_weight, spline_weight, spline_scaler, grid, grid_size=5, spline_order=3, precision=KMU_PREC_FP32):
+    """KANLinear.forward (convKAN/KANlayers.py:652-660): x (M,in) -> (M,out), as a 1x1 'convolution' over M pixels."""
+    M, F = x.shape
+    y = kanconv2d(x.reshape(M, F, 1, 1), base_weight, spline_weight, spline_scaler, grid, 1, 1, 0, grid_size, spline_order,
+                  precision)
+    return y.reshape(M, -1)
+
+
+# ------------------------------------------------------------------------------------------------------ LayerNorm1D
+class _LayerNorm1dFn(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, weight, bias, eps):
+        lib = _lib.lib()
+        x = x.contiguous()
+        B, Cc, L = x.shape
+        w, b = weight.reshape(-1).contiguous(), bias.reshape(-1).contiguous()
+        y = torch.empty_like(x)
+        check(lib.kmu_layernorm1d_fwd(ptr(x), ptr(w), ptr(b), ptr(y), None, B, Cc, L, float(eps), stream_ptr()),
+              "kmu_layernorm1d_fwd")
+        ctx.save_for_backward(x, w)
+        ctx.eps = float(eps)
+        ctx.wshape = weight.shape
+        return y
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        lib = _lib.lib()
+        x, w = ctx.saved_tensors
+        B, Cc, L = x.shape
+        dy = dy.to(torch.float32).contiguous()
+        dx = torch.empty_like(x)
+        dw = torch.zeros_like(w)
+        db = torch.zeros_like(w)
+        check(lib.kmu_layernorm1d_bwd(ptr(x), ptr(w), ptr(dy), ptr(dx), ptr(dw), ptr(db), B, Cc, L, ctx.eps, stream_ptr()),
+              "kmu_layernorm1d_bwd")
+        return dx, dw.reshape(ctx.wshape), db.reshape(ctx.wshape), None
+
+
+def layernorm1d(x, weight, bias, eps=1e-5):
+    """LayerNorm1D.forward (vim_block_init/vim_utils_init.py:50-59) on (B,C,L)."""
+    if not x.is_cuda:
+        raise RuntimeError("km_unet_b200.layernorm1d: CUDA tensors only (no CPU fallback)")
+    return _LayerNorm1dFn.apply(x, weight, bias, eps)
+
+
+# ------------------------------------------------------------------------------------------------------ HSMSSD
+class _HsmssdFn(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, w_bcdt, w_dw, w_hz, w_out, A, D, state_dim):
+        lib = _lib.lib()
+        x = x.contiguous()
+        B, Cc, L = x.shape
+        H = int(round(L ** 0.5))
+        N = int(state_dim)
+        desc = HsmDesc(B, Cc, L, H, N)
+        nbytes = lib.kmu_hsmssd_fwd_workspace_bytes(C.byref(desc))
+        if nbytes == 0:
+            raise RuntimeError("hsmssd: " + _lib.last_error())
+        dev = x.device
+        ws = _workspace(nbytes, dev)
+        wp, wd, whz, wo = w_bcdt.contiguous(), w_dw.contiguous(), w_hz.contiguous(), w_out.contiguous()
+        Ac, Dc = A.contiguous(), D.contiguous()
+        y = torch.empty(B, Cc, L, dtype=torch.float32, device=dev)
+        h = torch.empty(B, Cc, N, dtype=torch.float32, device=dev)
+        P = torch.empty(B, 3 * N, L, dtype=torch.float32, device=dev)
+        stats = torch.empty(B, 2, N, dtype=torch.float32, device=dev)
+        hs = torch.empty(B, Cc, N, dtype=torch.float32, device=dev)
+        hz = torch.empty(B, 2 * Cc, N, dtype=torch.float32, device=dev)
+        args = HsmFwdArgs(desc, ptr(x), ptr(wp), ptr(wd), ptr(whz), ptr(wo), ptr(Ac), ptr(Dc), ptr(y), ptr(h), ptr(P),
+                          ptr(stats), ptr(hs), ptr(hz), ws.data_ptr(), ws.numel())
+        check(lib.kmu_hsmssd_fwd(C.byref(args), stream_ptr()), "kmu_hsmssd_fwd")
+        ctx.save_for_backward(x, wp, wd, whz, wo, Ac, Dc, P, stats, hs, hz, h)
+        ctx.desc = desc
+        ctx.shapes = (w_bcdt.shape, w_dw.shape, w_hz.shape, w_out.shape)
+        return y.view(B, Cc, H, H), h
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dy, dh):
+        lib = _lib.lib()
+        x, wp, wd, whz, wo, Ac, Dc, P, stats, hs, hz, h = ctx.saved_tensors
+        desc = ctx.desc
+        dev = x.device
+        dy = dy.to(torch.float32).reshape(x.shape).contiguous()
+        dh = None if dh is None else dh.to(torch.float32).contiguous()
+        dx = torch.empty_like(x)
+        dwp, dwd, dwhz, dwo = (torch.empty_like(t) for t in (wp, wd, whz, wo))
+        dA, dD = torch.empty_like(Ac), torch.empty_like(Dc)
+        nbytes = lib.kmu_hsmssd_bwd_workspace_bytes(C.byref(desc))
+        ws = _workspace(nbytes, dev)
+        args = HsmBwdArgs(desc, ptr(x), ptr(dy), ptr(dh), ptr(wp), ptr(wd), ptr(whz), ptr(wo), ptr(Ac), ptr(Dc), ptr(P),
+                          ptr(stats), ptr(hs), ptr(hz), ptr(h), ptr(dx), ptr(dwp), ptr(dwd), ptr(dwhz), ptr(dwo), ptr(dA),
+                          ptr(dD), ws.data_ptr(), ws.numel())
+        check(lib.kmu_hsmssd_bwd(C.byref(args), stream_ptr()), "kmu_hsmssd_bwd")
+        s = ctx.shapes
+        return dx, dwp.reshape(s[0]), dwd.reshape(s[1]), dwhz.reshape(s[2]), dwo.reshape(s[3]), dA, dD, None
+
+
+def hsmssd(x, w_bcdt, w_dw, w_hz, w_out, A, D, state_dim=64):
+    """HSMSSD.forward (vim_block_init/efficient_vim_init.py:33-61): x (B,C,L) -> (y (B,C,H,H), h (B,C,N))."""
+    if not x.is_cuda:
+        raise RuntimeError("km_unet_b200.hsmssd: CUDA tensors only (no CPU fallback)")
+    return _HsmssdFn.apply(x, w_bcdt, w_dw, w_hz, w_out, A, D, state_dim)
+
+
+# ------------------------------------------------------------------------------------------------------ DySample
+class _DySampleFn(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, w_offset, b_offset, init_pos, scale, groups):
+        lib = _lib.lib()
+        x = x.contiguous()
+        B, Cc, H, W = x.shape
+        noff = 2 * groups * scale * scale
+        desc = DysDesc(B, Cc, H, W, scale, groups)
+        w = w_offset.reshape(noff, Cc).contiguous()
+        b = b_offset.contiguous()
+        ip = init_pos.reshape(-1).contiguous()
+        offset = torch.empty(B, noff, H, W, dtype=torch.float32, device=x.device)
+        out = torch.empty(B, Cc, scale * H, scale * W, dtype=torch.float32, device=x.device)
+        args = DysFwdArgs(desc, ptr(x), ptr(w), ptr(b), ptr(ip), ptr(offset), ptr(out))
+        check(lib.kmu_dysample_fwd(C.byref(args), stream_ptr()), "kmu_dysample_fwd")
+        ctx.save_for_backward(x, w, offset)
+        ctx.desc = desc
+        ctx.wshape = w_offset.shape
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dout):
+        lib = _lib.lib()
+        x, w, offset = ctx.saved_tensors
+        desc = ctx.desc
+        dout = dout.to(torch.float32).contiguous()
+        dx = torch.empty_like(x)
+        dw = torch.empty_like(w)
+        db = torch.empty(w.shape[0], dtype=torch.float32, device=x.device)
+        ws = _workspace(lib.kmu_dysample_bwd_workspace_bytes(C.byref(desc)), x.device)
+        args = DysBwdArgs(desc, ptr(x), ptr(w), ptr(offset), ptr(dout), ptr(dx), ptr(dw), ptr(db), ws.data_ptr(), ws.numel())
+        check(lib.kmu_dysample_bwd(C.byref(args), stream_ptr()), "kmu_dysample_bwd")
+        return dx, dw.reshape(ctx.wshape), db, None, None, None
+
+
+def dysample(x, w_offset, b_offset, init_pos, scale=2, groups=4):
+    """DySample.forward_lp without dyscope (DySample_md.py:63-68): x (B,C,H,W) -> (B,C,scale*H,scale*W)."""
+    if not x.is_cuda:
+        raise RuntimeError("km_unet_b200.dysample: CUDA tensors only (no CPU fallback)")
+    return _DySampleFn.apply(x, w_offset, b_offset, init_pos, int(scale), int(groups))
+
+
+class _DySampleSampleFn(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, offset, scale, groups):
+        lib = _lib.lib()
+        x, offset = x.contiguous(), offset.contiguous()
+        B, Cc, H, W = x.shape
+        desc = DysDesc(B, Cc, H, W, scale, groups)
+        out = torch.empty(B, Cc, scale * H, scale * W, dtype=torch.float32, device=x.device)
+        check(lib.kmu_dysample_sample_fwd(C.byref(desc), ptr(x), ptr(offset), ptr(out), stream_ptr()),
+              "kmu_dysample_sample_fwd")
+        ctx.save_for_backward(x, offset)
+        ctx.desc = desc
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dout):
+        lib = _lib.lib()
+        x, offset = ctx.saved_tensors
+        dout = dout.to(torch.float32).contiguous()
+        dx = torch.zeros_like(x)
+        doff = torch.empty_like(offset)
+        check(lib.kmu_dysample_sample_bwd(C.byref(ctx.desc), ptr(x), ptr(offset), ptr(dout), ptr(dx), ptr(doff), stream_ptr()),
+              "kmu_dysample_sample_bwd")
+        return dx, doff, None, None
+
+
+def dysample_sample(x, offset, scale=2, groups=4):
+    """DySample.sample (DySample_md.py:49-61) for a caller-built offset tensor (B, 2*groups*scale^2, H, W)."""
+    if not x.is_cuda:
+        raise RuntimeError("km_unet_b200.dysample_sample: CUDA tensors only (no CPU fallback)")
+    return _DySampleSampleFn.apply(x, offset, int(scale), int(groups))

@@ -1,0 +1,82 @@
+"""GPU parity of DySample (drop-in module -> ctypes -> C ABI) against the reference's golden vectors and the oracle."""
+import pytest
+import torch
+
+from conftest import Golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.mark.parametrize("name,ch", [("dysample_8_g4", 8), ("dysample_64_init", 64)])
+def test_dysample_golden(name, ch):
+    from km_unet_b200 import DySample
+    g = Golden(name)
+    m = DySample(ch)
+    m.load_state_dict(g.sd())
+    m = m.cuda()
+    x = g.t("in0", "cuda").requires_grad_(True)
+    y = m(x)
+    assert y.shape == g.t("out0").shape
+    assert rel_err(y, g.t("out0")) < TOL
+    y.backward(g.t("gout", "cuda"))
+    assert rel_err(x.grad, g.t("grad_in0")) < TOL
+    want = g.grads()
+    assert rel_err(m.offset.weight.grad, want["offset.weight"]) < TOL
+    assert rel_err(m.offset.bias.grad, want["offset.bias"]) < TOL
+
+
+@pytest.mark.parametrize("B,C,H,W,std", [(2, 64, 16, 16, 0.001), (1, 64, 32, 32, 0.05), (2, 16, 9, 7, 0.3), (1, 8, 5, 5, 1.0)])
+def test_dysample_vs_oracle(B, C, H, W, std):
+    from km_unet_b200 import DySample
+    from oracle import dysample as O
+    torch.manual_seed(H * W)
+    m = DySample(C)
+    with torch.no_grad():
+        m.offset.weight.normal_(0, std)
+        m.offset.bias.uniform_(-0.3, 0.3)
+    x = torch.randn(B, C, H, W)
+    xd = x.double().requires_grad_(True)
+    wd = m.offset.weight.detach().double().requires_grad_(True)
+    bd = m.offset.bias.detach().double().requires_grad_(True)
+    want = O.dysample_lp(xd, wd, bd, m.init_pos.double())
+    gout = torch.randn(want.shape)
+    want.backward(gout.double())
+    m = m.cuda()
+    xc = x.cuda().requires_grad_(True)
+    y = m(xc)
+    assert rel_err(y, want) < TOL
+    y.backward(gout.cuda())
+    assert rel_err(xc.grad, xd.grad) < TOL
+    assert rel_err(m.offset.weight.grad, wd.grad) < TOL
+    assert rel_err(m.offset.bias.grad, bd.grad) < TOL
+
+
+def test_dysample_constant_image_is_reproduced_full_size():
+    """Property at config-5 size (64 ch, 128x128 -> 256x256): bilinear weights sum to 1 away from the clipped border,
+    so a per-channel constant image upsamples to the same constant."""
+    from km_unet_b200 import DySample
+    torch.manual_seed(0)
+    m = DySample(64).cuda()
+    with torch.no_grad():
+        m.offset.weight.zero_()
+        m.offset.bias.zero_()
+    const = torch.arange(64, dtype=torch.float32, device="cuda").view(1, 64, 1, 1).expand(2, 64, 128, 128).contiguous()
+    y = m(const)
+    assert y.shape == (2, 64, 256, 256)
+    assert torch.allclose(y, const[:, :, :1, :1].expand_as(y), atol=1e-5)
+
+
+def test_pl_style_and_dyscope_use_the_cuda_sampler():
+    from km_unet_b200 import DySample
+    from oracle import dysample as O
+    torch.manual_seed(4)
+    m = DySample(16, style="lp", dyscope=True)
+    with torch.no_grad():
+        m.offset.weight.normal_(0, 0.2)
+        m.scope.weight.normal_(0, 0.5)
+    x = torch.randn(1, 16, 6, 6)
+    off = m.offset(x) * m.scope(x).sigmoid() * 0.5 + m.init_pos
+    want = O.sample(x.double(), off.detach().double())
+    y = m.cuda()(x.cuda())
+    assert rel_err(y, want) < TOL
