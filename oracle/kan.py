@@ -23,20 +23,16 @@ def make_grid(in_features, grid_size=5, spline_order=3, grid_range=(-1.0, 1.0), 
 
 def bspline_basis(x, grid, spline_order=3):
     """x (M, in), grid (in, T) -> (M, in, T - spline_order - 1), half-open order-0 indicators then
-    `spline_order` Cox-de Boor levels."""
+    `spline_order` Cox-de Boor levels (vectorised over the knot axis)."""
     assert x.dim() == 2 and x.shape[1] == grid.shape[0]
-    T = grid.shape[1]
     g = grid.to(x.dtype)
     xe = x[:, :, None]
-    level = [((xe[..., 0] >= g[:, j]) & (xe[..., 0] < g[:, j + 1])).to(x.dtype) for j in range(T - 1)]
+    level = ((xe >= g[:, :-1]) & (xe < g[:, 1:])).to(x.dtype)
     for p in range(1, spline_order + 1):
-        nxt = []
-        for j in range(len(level) - 1):
-            left = (x - g[:, j]) / (g[:, j + p] - g[:, j])
-            right = (g[:, j + p + 1] - x) / (g[:, j + p + 1] - g[:, j + 1])
-            nxt.append(left * level[j] + right * level[j + 1])
-        level = nxt
-    return torch.stack(level, dim=-1)
+        span_lo = g[:, p:-1] - g[:, :-(p + 1)]
+        span_hi = g[:, p + 1:] - g[:, 1:-p]
+        level = (xe - g[:, :-(p + 1)]) / span_lo * level[..., :-1] + (g[:, p + 1:] - xe) / span_hi * level[..., 1:]
+    return level
 
 
 def bspline_basis_and_derivative(x, grid, spline_order=3):
@@ -88,17 +84,13 @@ def kan_linear(x, base_weight, spline_weight, spline_scaler, grid, spline_order=
 
 
 def unfold_patches(x, kernel_size, stride, padding):
-    """(B,C,H,W) -> (B*Ho*Wo, C*k*k) with feature index c*k*k + ki*k + kj and zero padding."""
+    """(B,C,H,W) -> (B*Ho*Wo, C*k*k) with feature index c*k*k + ki*k + kj and zero padding (im2col)."""
     B, C, H, W = x.shape
     k = kernel_size
     Ho = (H + 2 * padding - k) // stride + 1
     Wo = (W + 2 * padding - k) // stride + 1
-    xp = F.pad(x, (padding, padding, padding, padding))
-    cols = x.new_empty(B, Ho, Wo, C, k, k)
-    for ki in range(k):
-        for kj in range(k):
-            cols[..., ki, kj] = xp[:, :, ki:ki + stride * Ho:stride, kj:kj + stride * Wo:stride].permute(0, 2, 3, 1)
-    return cols.reshape(B * Ho * Wo, C * k * k), (Ho, Wo)
+    cols = F.unfold(x, kernel_size=k, stride=stride, padding=padding)          # (B, C*k*k, Ho*Wo)
+    return cols.transpose(1, 2).reshape(B * Ho * Wo, C * k * k), (Ho, Wo)
 
 
 def kanconv2d(x, base_weight, spline_weight, spline_scaler, grid, kernel_size=3, stride=1, padding=0, spline_order=3):

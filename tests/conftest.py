@@ -14,6 +14,10 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # The parts of the model that are still torch library calls (cuDNN convs of the EfficientViMBlock shell) must not
+    # silently drop to TF32 while we check a 1e-4 parity gate.
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def pytest_collection_modifyitems(config, items):

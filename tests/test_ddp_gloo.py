@@ -1,0 +1,70 @@
+"""N>1 path on CPU: world_size-2 gloo run of the bucketed gradient all-reduce (km_unet_b200/ddp.py)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from km_unet_b200.ddp import BucketedGradAllReduce, broadcast_parameters
+    torch.manual_seed(100 + rank)                      # different init per rank: broadcast must fix it
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+    dead = torch.nn.Parameter(torch.ones(4))           # never used, like the dead KAN twin in StableHybridKANConv
+    broadcast_parameters(net)
+    red = BucketedGradAllReduce(list(net.parameters()), bucket_bytes=64)   # tiny buckets -> several of them
+    assert len(red.buckets) >= 2
+    g = torch.Generator().manual_seed(7)
+    data = torch.randn(world, 4, 6, generator=g)
+    for step in range(2):                              # two steps: hooks must re-arm
+        net.zero_grad(set_to_none=True)
+        loss = net(data[rank]).square().mean()
+        loss.backward()
+        nbytes = red.finish()
+    grads = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+    if rank == 0:
+        torch.save({"grads": grads, "state": net.state_dict(), "nbytes": nbytes}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+    assert dead.grad is None
+
+
+def test_bucketed_allreduce_equals_mean_of_per_rank_grads(tmp_path):
+    world = 2
+    out = str(tmp_path / "rank0.pt")
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    got = torch.load(out)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+    net.load_state_dict(got["state"])
+    g = torch.Generator().manual_seed(7)
+    data = torch.randn(world, 4, 6, generator=g)
+    per_rank = []
+    for r in range(world):
+        net.zero_grad(set_to_none=True)
+        net(data[r]).square().mean().backward()
+        per_rank.append(torch.cat([p.grad.reshape(-1) for p in net.parameters()]))
+    want = torch.stack(per_rank).mean(0)
+    assert torch.allclose(got["grads"], want, atol=1e-6)
+    assert got["nbytes"] == 4 * want.numel()
+
+
+def test_single_process_is_identity():
+    from km_unet_b200.ddp import BucketedGradAllReduce
+    lin = torch.nn.Linear(3, 2)
+    red = BucketedGradAllReduce(list(lin.parameters()))
+    lin(torch.ones(1, 3)).sum().backward()
+    before = lin.weight.grad.clone()
+    red.finish()
+    assert torch.equal(lin.weight.grad, before)
