@@ -61,6 +61,11 @@ typedef struct {
   int32_t grid_size, spline_order; /* n_basis = grid_size + spline_order; knots per feature = grid_size + 2*order + 1 */
   int32_t precision;               /* kmu_precision */
   int32_t has_scaler;              /* enable_standalone_scale_spline */
+  /* Caller-asserted fact about `grid` (checked once per module on the host, KANLinear never changes it outside
+   * update_grid): every feature row equals the same uniform knot vector t_j = grid_t0 + j*grid_h.  Required by the
+   * tcgen05 family (Phi is then a function of the pixel alone); 0 routes the call to the fp32 family. */
+  int32_t grid_uniform;
+  float grid_t0, grid_h;
 } kmu_kanconv2d_desc;
 
 typedef struct {
@@ -95,11 +100,10 @@ size_t kmu_kanconv2d_fwd_workspace_bytes(const kmu_kanconv2d_desc* d);
 size_t kmu_kanconv2d_bwd_workspace_bytes(const kmu_kanconv2d_desc* d);
 int kmu_kanconv2d_fwd(const kmu_kanconv2d_fwd_args* a, kmu_stream stream);
 int kmu_kanconv2d_bwd(const kmu_kanconv2d_bwd_args* a, kmu_stream stream);
-/* Which kernel family a descriptor resolves to: 0 = fp32 CUDA-core, 1 = tcgen05 implicit GEMM.  The tensor path
- * needs ksize 3, stride 1, padding 1, cubic splines with 8 basis functions, Cin % 8 == 0, Cout % 16 == 0,
- * Cout <= 256 and one uniform knot row shared by all features; anything else runs the fp32 family
- * (still on the GPU). */
-int kmu_kanconv2d_path(const kmu_kanconv2d_desc* d, int grid_is_uniform_shared);
+/* Which kernel family the FORWARD of a descriptor resolves to: 0 = fp32 CUDA-core, 1 = tcgen05 implicit GEMM.  The
+ * tensor path needs precision KMU_PREC_BF16, ksize 3, stride 1, padding 1, cubic splines with 8 basis functions,
+ * Cin % 16 == 0, Cout in {16,32,64} and grid_uniform; anything else runs the fp32 family (still on the GPU). */
+int kmu_kanconv2d_path(const kmu_kanconv2d_desc* d);
 
 /* ------------------------------------------------------------------------------------------------------------
  * S: LayerNorm1D + HSMSSD          vim_block_init/vim_utils_init.py:50-59, vim_block_init/efficient_vim_init.py:33-61
@@ -124,7 +128,7 @@ typedef struct {
   float* h;            /* (B,C,N) = ho */
   /* saved for backward (caller-owned, may all be NULL for inference) */
   float* P;     /* (B,3N,L) */
-  float* stats; /* (B,2,N): row 0 = max_L(dt + A), row 1 = sum_L exp(dt + A - max) */
+  float* stats; /* (B,2,N): row 0 = max_L(dt), row 1 = sum_L exp(dt - max)  (the A shift cancels) */
   float* hs;    /* (B,C,N) */
   float* hz;    /* (B,2C,N) */
   void* workspace;

@@ -18,7 +18,8 @@ _f32p = C.c_void_p  # device pointers travel as integers
 
 class KanDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("B", "Cin", "H", "W", "Cout", "ksize", "stride", "padding", "grid_size",
-                                         "spline_order", "precision", "has_scaler")]
+                                         "spline_order", "precision", "has_scaler", "grid_uniform")] + \
+               [("grid_t0", C.c_float), ("grid_h", C.c_float)]
 
 
 class KanFwdArgs(C.Structure):
@@ -73,7 +74,7 @@ SYMBOLS = {
     "kmu_kanconv2d_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(KanDesc)]),
     "kmu_kanconv2d_fwd": (C.c_int, [C.POINTER(KanFwdArgs), C.c_void_p]),
     "kmu_kanconv2d_bwd": (C.c_int, [C.POINTER(KanBwdArgs), C.c_void_p]),
-    "kmu_kanconv2d_path": (C.c_int, [C.POINTER(KanDesc), C.c_int]),
+    "kmu_kanconv2d_path": (C.c_int, [C.POINTER(KanDesc)]),
     "kmu_hsmssd_fwd_workspace_bytes": (C.c_size_t, [C.POINTER(HsmDesc)]),
     "kmu_hsmssd_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(HsmDesc)]),
     "kmu_hsmssd_fwd": (C.c_int, [C.POINTER(HsmFwdArgs), C.c_void_p]),

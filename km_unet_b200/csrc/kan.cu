@@ -23,16 +23,14 @@ static int check_desc(const kmu_kanconv2d_desc* d, const char* who) {
 
 extern "C" {
 
-int kmu_kanconv2d_path(const kmu_kanconv2d_desc* d, int grid_is_uniform_shared) {
+int kmu_kanconv2d_path(const kmu_kanconv2d_desc* d) {
   if (!d) return 0;
-  bool tc = d->precision == KMU_PREC_BF16 && grid_is_uniform_shared && d->ksize == 3 && d->stride == 1 && d->padding == 1 &&
-            d->spline_order == 3 && d->grid_size == 5 && d->Cin % 8 == 0 && d->Cout % 16 == 0 && d->Cout <= 256;
-  (void)tc;
-  return 0;  // tcgen05 family not linked in this build yet
+  return (d->precision == KMU_PREC_BF16 && tc::supported(*d)) ? 1 : 0;
 }
 
 size_t kmu_kanconv2d_fwd_workspace_bytes(const kmu_kanconv2d_desc* d) {
   if (check_desc(d, "kanconv2d_fwd_workspace_bytes") != KMU_OK) return 0;
+  if (kmu_kanconv2d_path(d)) return tc::fwd_workspace(make_dims(*d));
   return simt_fwd_workspace(make_dims(*d));
 }
 
@@ -49,6 +47,10 @@ int kmu_kanconv2d_fwd(const kmu_kanconv2d_fwd_args* a, kmu_stream stream) {
   KMU_REQUIRE(!a->d.has_scaler || a->spline_scaler, KMU_ERR_BAD_ARG, "kanconv2d_fwd: has_scaler set but spline_scaler is null");
   kmu_kanconv2d_fwd_args b = *a;
   if (!b.d.has_scaler) b.spline_scaler = nullptr;
+  if (kmu_kanconv2d_path(&a->d)) {
+    KMU_REQUIRE(kmu_device_supported(), KMU_ERR_DEVICE, "kanconv2d_fwd: the tcgen05 family needs an sm_100 device");
+    return tc::forward(&b, make_dims(a->d), (cudaStream_t)stream);
+  }
   return simt_forward(&b, make_dims(a->d), (cudaStream_t)stream);
 }
 

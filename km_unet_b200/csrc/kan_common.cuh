@@ -68,5 +68,12 @@ size_t simt_bwd_workspace(const Dims& d);
 int simt_forward(const kmu_kanconv2d_fwd_args* a, const Dims& d, cudaStream_t st);
 int simt_backward(const kmu_kanconv2d_bwd_args* a, const Dims& d, cudaStream_t st);
 
+// tcgen05 / TMEM family (kan_tc.cu)
+namespace tc {
+bool supported(const kmu_kanconv2d_desc& s);
+size_t fwd_workspace(const Dims& d);
+int forward(const kmu_kanconv2d_fwd_args* a, const Dims& d, cudaStream_t st);
+}  // namespace tc
+
 }  // namespace kan
 }  // namespace kmu

@@ -82,12 +82,20 @@ class KANLinear(nn.Module):
     def _precision(self):
         return config.precision_code(self.precision)
 
+    def _grid_meta(self):
+        """Cached (uniform_and_shared, t0, h) of the knot table, refreshed when the buffer is modified or moved."""
+        key = (self.grid._version, self.grid.data_ptr())
+        if getattr(self, "_grid_meta_key", None) != key:
+            self._grid_meta_val = ops.grid_info(self.grid)
+            self._grid_meta_key = key
+        return self._grid_meta_val
+
     # -- hot path ----------------------------------------------------------------------------------------------
     def forward(self, x):
         assert x.dim() == 2 and x.size(1) == self.in_features
         scaler = self.spline_scaler if self.enable_standalone_scale_spline else None
         return ops.kanlinear(x, self.base_weight, self.spline_weight, scaler, self.grid, self.grid_size, self.spline_order,
-                             self._precision())
+                             self._precision(), self._grid_meta())
 
     @torch.no_grad()
     def update_grid(self, x, margin=0.01):
@@ -128,7 +136,7 @@ class KANConv2d(nn.Module):
         k = self.kanlayer
         scaler = k.spline_scaler if k.enable_standalone_scale_spline else None
         return ops.kanconv2d(x, k.base_weight, k.spline_weight, scaler, k.grid, self.kernel_size, self.stride, self.padding,
-                             k.grid_size, k.spline_order, k._precision())
+                             k.grid_size, k.spline_order, k._precision(), k._grid_meta())
 
 
 KAN_Convolutional_Layer = KANConv2d  # name used by BASELINE.json's north_star

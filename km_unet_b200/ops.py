@@ -28,13 +28,14 @@ class _KanConv2dFn(torch.autograd.Function):
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, x, base_weight, spline_weight, spline_scaler, grid, ksize, stride, padding, grid_size, spline_order,
-                precision):
+                precision, grid_info):
         lib = _lib.lib()
         x = x.contiguous()
         B, Cin, H, W = x.shape
         Cout = base_weight.shape[0]
+        uniform, t0, h = grid_info if grid_info is not None else (False, 0.0, 0.0)
         desc = KanDesc(B, Cin, H, W, Cout, ksize, stride, padding, grid_size, spline_order, precision,
-                       0 if spline_scaler is None else 1)
+                       0 if spline_scaler is None else 1, 1 if uniform else 0, float(t0), float(h))
         Ho = (H + 2 * padding - ksize) // stride + 1
         Wo = (W + 2 * padding - ksize) // stride + 1
         bw, sw, gr = base_weight.contiguous(), spline_weight.contiguous(), grid.contiguous()
@@ -68,23 +69,38 @@ class _KanConv2dFn(torch.autograd.Function):
         args = KanBwdArgs(desc, ptr(x), ptr(dy), ptr(bw), ptr(sw), ptr(sc), ptr(gr), ptr(dx), ptr(dbw), ptr(dsw), ptr(dsc),
                           ws.data_ptr(), ws.numel())
         check(lib.kmu_kanconv2d_bwd(C.byref(args), stream_ptr()), "kmu_kanconv2d_bwd")
-        return dx, dbw, dsw, dsc, None, None, None, None, None, None, None
+        return dx, dbw, dsw, dsc, None, None, None, None, None, None, None, None
+
+
+def grid_info(grid):
+    """(uniform_and_shared, t0, h) of a KANLinear knot table (in_features, n_knots): True when every row is the same
+    uniform knot vector.  One small D2H copy; callers cache it per grid version."""
+    g = grid.detach().double().cpu()
+    n = g.shape[1]
+    t0 = g[0, 0].item()
+    h = ((g[0, -1] - g[0, 0]) / (n - 1)).item()
+    if not h > 0:
+        return (False, t0, h)
+    ideal = t0 + h * torch.arange(n, dtype=torch.float64)
+    return (bool((g - ideal).abs().max().item() <= 1e-5 * h), t0, h)
 
 
 def kanconv2d(x, base_weight, spline_weight, spline_scaler, grid, kernel_size, stride=1, padding=0, grid_size=5,
-              spline_order=3, precision=KMU_PREC_FP32):
-    """KANConv2d.forward (convKAN/KANConv2Dlayers.py:15-37): x (B,Cin,H,W) -> (B,Cout,Ho,Wo)."""
+              spline_order=3, precision=KMU_PREC_FP32, grid_meta=None):
+    """KANConv2d.forward (convKAN/KANConv2Dlayers.py:15-37): x (B,Cin,H,W) -> (B,Cout,Ho,Wo).
+    grid_meta = grid_info(grid) lets the bf16 precision take the tcgen05 path; None keeps the fp32 family."""
     if not x.is_cuda:
         raise RuntimeError("km_unet_b200.kanconv2d: CUDA tensors only (no CPU fallback)")
     return _KanConv2dFn.apply(x, base_weight, spline_weight, spline_scaler, grid, int(kernel_size), int(stride), int(padding),
-                              int(grid_size), int(spline_order), int(precision))
+                              int(grid_size), int(spline_order), int(precision), grid_meta)
 
 
-def kanlinear(x, base_weight, spline_weight, spline_scaler, grid, grid_size=5, spline_order=3, precision=KMU_PREC_FP32):
+def kanlinear(x, base_weight, spline_weight, spline_scaler, grid, grid_size=5, spline_order=3, precision=KMU_PREC_FP32,
+              grid_meta=None):
     """KANLinear.forward (convKAN/KANlayers.py:652-660): x (M,in) -> (M,out), as a 1x1 'convolution' over M pixels."""
     M, F = x.shape
     y = kanconv2d(x.reshape(M, F, 1, 1), base_weight, spline_weight, spline_scaler, grid, 1, 1, 0, grid_size, spline_order,
-                  precision)
+                  precision, grid_meta)
     return y.reshape(M, -1)
 
 

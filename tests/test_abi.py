@@ -41,7 +41,7 @@ def test_header_symbols_are_exported_and_bound(libpath):
 def test_bad_descriptor_is_reported_not_crashed(libpath):
     from km_unet_b200 import _lib
     lib = _lib.lib()
-    d = _lib.KanDesc(1, 4, 8, 8, 8, 3, 1, 1, 7, 5, 0, 1)       # grid_size 7 / order 5: not implemented
+    d = _lib.KanDesc(1, 4, 8, 8, 8, 3, 1, 1, 7, 5, 0, 1, 0, 0.0, 0.0)       # grid_size 7 / order 5: not implemented
     assert lib.kmu_kanconv2d_fwd_workspace_bytes(ctypes.byref(d)) == 0
     assert "cubic" in _lib.last_error()
     h = _lib.HsmDesc(1, 16, 65, 8, 64)                          # L != H*H
