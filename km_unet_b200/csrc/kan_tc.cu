@@ -17,9 +17,11 @@
 //     warps 10-13 epilogue: tcgen05.ld accumulators -> fp32 NCHW stores, overlapped with the next strip's MMAs
 // mbarrier pipelines: phi full/empty, weight full/empty (tx-count), accumulator full/empty.
 //
-// K order: per 16-channel block, slot 0 = the two SiLU groups (8 channels each), slots 1..8 = spline groups of channel
-// pairs; each slot is used by 9 taps x TT tiles = 9*TT MMAs, then released.  Weights are re-streamed from L2 per strip;
-// TT=4 keeps that at ~2.7 TB/s aggregate for the 64->64 microbench.
+// K order: per 16-channel block, slots 0..7 = spline groups of channel pairs (ring of Phi slots), slot 8 = the two SiLU
+// groups (8 channels each) which the producers fill 2 bytes at a time while they evaluate the splines of the same x
+// (double-buffered side region).  Each slot is used by 9 taps x TT tiles = 9*TT MMAs, then released.  x values are
+// prefetched into registers one slot ahead so the global-load latency overlaps the previous slot's math.  Weights are
+// re-streamed from L2 per strip; TT=4 keeps that at ~2.7 TB/s aggregate for the 64->64 microbench.
 #include <cuda_bf16.h>
 
 #include <cstdio>
@@ -185,11 +187,11 @@ __global__ void kan_tc_pack_kernel(const float* __restrict__ base_w, const float
   int cb = slot / 9, j = slot - cb * 9;
   int F = Cin * 9;
   float v;
-  if (j == 0) {
+  if (j == 8) {
     int c = cb * 16 + gi * 8 + e;
     v = base_w[(size_t)n * F + c * 9 + tap];
   } else {
-    int c = cb * 16 + 2 * (j - 1) + gi;
+    int c = cb * 16 + 2 * j + gi;
     size_t of = (size_t)n * F + c * 9 + tap;
     v = spline_w[of * NB + e] * (scaler ? scaler[of] : 1.0f);
   }
@@ -208,9 +210,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) kan_fwd_tc_kernel(const float*
   constexpr uint32_t IDESC = make_idesc_bf16(128, N);
   static_assert(2 * TT * N <= 512, "accumulators exceed TMEM");
   extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int UPT = (2 * NPOS + NUM_PRODUCER_WARPS * 32 - 1) / (NUM_PRODUCER_WARPS * 32);  // units per producer thread
   const int R = d.phi_stages;
   uint8_t* phi_base = smem;
-  uint8_t* w_base = smem + (size_t)R * SLOT;
+  uint8_t* silu_base = smem + (size_t)R * SLOT;            // 2 x SLOT
+  uint8_t* w_base = silu_base + 2 * (size_t)SLOT;
   uint64_t* bars = reinterpret_cast<uint64_t*>(w_base + (size_t)W_STAGES * WSTAGE);
   uint64_t* phi_full = bars;
   uint64_t* phi_empty = bars + R;
@@ -218,7 +222,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) kan_fwd_tc_kernel(const float*
   uint64_t* w_empty = w_full + W_STAGES;
   uint64_t* acc_full = w_empty + W_STAGES;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* silu_full = acc_empty + 2;
+  uint64_t* silu_empty = silu_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(silu_empty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -234,6 +240,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) kan_fwd_tc_kernel(const float*
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&acc_full[i]), 1);
       mbar_init(smem_u32(&acc_empty[i]), 4);
+      mbar_init(smem_u32(&silu_full[i]), NUM_PRODUCER_WARPS);
+      mbar_init(smem_u32(&silu_empty[i]), 1);
     }
     fence_barrier_init();
   }
@@ -248,73 +256,113 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) kan_fwd_tc_kernel(const float*
 
   if (warp < NUM_PRODUCER_WARPS) {
     // ===================================================================== Phi producers
-    uint32_t it = 0;
+    uint32_t it = 0, bc = 0;  // ring iteration, 16-channel block counter
+    const int pairs = d.Cin / 2;
     for (int tile = blockIdx.x; tile < d.num_tiles; tile += gridDim.x) {
       const int b = tile / tiles_per_img;
       const int tr = tile - b * tiles_per_img;
       const int ty0 = (tr / d.tiles_x) * (16 * TT), tx0 = (tr % d.tiles_x) * 8;
       const float* xb = x + (size_t)b * d.Cin * HW;
-      for (int s = 0; s < d.slots; ++s, ++it) {
+      // per-thread units: (halo position, which channel of the pair); fixed for the whole strip
+      int uoff[UPT];   // pixel offset inside the image plane, -1 = zero padding, -2 = no unit
+      int ugi[UPT], upos[UPT];
+#pragma unroll
+      for (int k = 0; k < UPT; ++k) {
+        const int u = tid + k * (NUM_PRODUCER_WARPS * 32);
+        const int gi = u >= NPOS ? 1 : 0;
+        const int pos = u - gi * NPOS;
+        const int py = pos / PITCH, px = pos - py * PITCH;
+        const int gy = ty0 - 1 + py, gx = tx0 - 1 + px;
+        ugi[k] = gi;
+        upos[k] = pos;
+        uoff[k] = (u >= 2 * NPOS) ? -2 : ((gy >= 0 && gy < d.H && gx >= 0 && gx < d.W) ? gy * d.W + gx : -1);
+      }
+      float xr[UPT];
+#pragma unroll
+      for (int k = 0; k < UPT; ++k) xr[k] = uoff[k] >= 0 ? __ldg(xb + (size_t)ugi[k] * HW + uoff[k]) : 0.f;
+      for (int ps = 0; ps < pairs; ++ps, ++it) {
+        float xn[UPT];
+        if (ps + 1 < pairs) {                      // prefetch the next channel pair: latency overlaps this slot's math
+          const float* xc = xb + (size_t)(2 * (ps + 1)) * HW;
+#pragma unroll
+          for (int k = 0; k < UPT; ++k) xn[k] = uoff[k] >= 0 ? __ldg(xc + (size_t)ugi[k] * HW + uoff[k]) : 0.f;
+        } else {
+#pragma unroll
+          for (int k = 0; k < UPT; ++k) xn[k] = 0.f;
+        }
+        const int j = ps & 7;
+        const uint32_t sb = bc & 1u;
+        if (j == 0) mbar_wait(smem_u32(&silu_empty[sb]), ((bc >> 1) & 1u) ^ 1u);
         const int r = it % R;
-        const uint32_t ph = (it / R) & 1u;
-        mbar_wait(smem_u32(&phi_empty[r]), ph ^ 1u);
+        mbar_wait(smem_u32(&phi_empty[r]), ((it / R) & 1u) ^ 1u);
         uint8_t* slot = phi_base + (size_t)r * SLOT;
-        const int cb = s / 9, j = s - cb * 9;
-        for (int u = tid; u < 2 * NPOS; u += NUM_PRODUCER_WARPS * 32) {
-          const int gi = u >= NPOS ? 1 : 0;
-          const int pos = u - gi * NPOS;
-          const int py = pos / PITCH, px = pos - py * PITCH;
-          const int gy = ty0 - 1 + py, gx = tx0 - 1 + px;
-          const bool in = gy >= 0 && gy < d.H && gx >= 0 && gx < d.W;
-          uint4 v;
-          if (j == 0) {
-            float f[8];
-            const float* p = xb + (size_t)(cb * 16 + gi * 8) * HW + (in ? (size_t)gy * d.W + gx : 0);
+        uint8_t* sslot = silu_base + (size_t)sb * SLOT;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = in ? __ldg(p + (size_t)e * HW) : 0.f;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = silu_fast(f[e]);
-            v = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-          } else {
-            const int c = cb * 16 + 2 * (j - 1) + gi;
-            const float xv = in ? __ldg(xb + (size_t)c * HW + ((size_t)gy * d.W + gx)) : 0.f;
-            v = spline_group(xv, d.t0, d.inv_h);
+        for (int k = 0; k < UPT; ++k) {
+          if (uoff[k] != -2) {
+            const uint4 v = spline_group(xr[k], d.t0, d.inv_h);
+            *reinterpret_cast<uint4*>(slot + (size_t)ugi[k] * PLANE + (size_t)upos[k] * 16) = v;
+            const int cl = 2 * j + ugi[k];          // channel inside the 16-channel block
+            const __nv_bfloat16 sv = __float2bfloat16_rn(silu_fast(xr[k]));
+            *reinterpret_cast<__nv_bfloat16*>(sslot + (size_t)(cl >> 3) * PLANE + (size_t)upos[k] * 16 + (cl & 7) * 2) = sv;
           }
-          *reinterpret_cast<uint4*>(slot + (size_t)gi * PLANE + (size_t)pos * 16) = v;
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&phi_full[r]));
+        if (lane == 0) {
+          mbar_arrive(smem_u32(&phi_full[r]));
+          if (j == 7) mbar_arrive(smem_u32(&silu_full[sb]));
+        }
+        if (j == 7) ++bc;
+#pragma unroll
+        for (int k = 0; k < UPT; ++k) xr[k] = xn[k];
       }
     }
   } else if (warp == WARP_MMA) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
-      uint32_t it = 0, tcount = 0;
+      uint32_t it = 0, wit = 0, bc = 0, tcount = 0;
+      const int blocks = d.Cin / 16;
       for (int tile = blockIdx.x; tile < d.num_tiles; tile += gridDim.x, ++tcount) {
         const uint32_t buf = tcount & 1u;
         mbar_wait(smem_u32(&acc_empty[buf]), ((tcount >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * 256u;
-        for (int s = 0; s < d.slots; ++s, ++it) {
-          const int r = it % R, ws = it % W_STAGES;
-          mbar_wait(smem_u32(&phi_full[r]), (it / R) & 1u);
-          mbar_wait(smem_u32(&w_full[ws]), (it / W_STAGES) & 1u);
-          tc_fence_after();
-          const uint32_t a0 = smem_u32(phi_base + (size_t)r * SLOT);
-          const uint32_t b0 = smem_u32(w_base + (size_t)ws * WSTAGE);
-#pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            const int ki = t / 3, kj = t - ki * 3;
-            const uint64_t bdesc = make_smem_desc(b0 + (uint32_t)t * (2 * N * 16), N * 16, 128);
-#pragma unroll
-            for (int i = 0; i < TT; ++i) {
-              const uint64_t adesc = make_smem_desc(a0 + (uint32_t)(((i * 16 + ki) * PITCH + kj) * 16), PLANE, PITCH * 16);
-              umma_bf16(d_tmem + (uint32_t)(i * N), adesc, bdesc, IDESC, (s > 0 || t > 0) ? 1u : 0u);
+        for (int cb = 0; cb < blocks; ++cb, ++bc) {
+          for (int j = 0; j < 9; ++j, ++wit) {
+            const int ws = wit % W_STAGES;
+            uint32_t a0;
+            int r = 0;
+            const uint32_t sb = bc & 1u;
+            if (j < 8) {
+              r = it % R;
+              mbar_wait(smem_u32(&phi_full[r]), (it / R) & 1u);
+              a0 = smem_u32(phi_base + (size_t)r * SLOT);
+            } else {
+              mbar_wait(smem_u32(&silu_full[sb]), (bc >> 1) & 1u);
+              a0 = smem_u32(silu_base + (size_t)sb * SLOT);
             }
+            mbar_wait(smem_u32(&w_full[ws]), (wit / W_STAGES) & 1u);
+            tc_fence_after();
+            const uint32_t b0 = smem_u32(w_base + (size_t)ws * WSTAGE);
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              const int ki = t / 3, kj = t - ki * 3;
+              const uint64_t bdesc = make_smem_desc(b0 + (uint32_t)t * (2 * N * 16), N * 16, 128);
+#pragma unroll
+              for (int i = 0; i < TT; ++i) {
+                const uint64_t adesc = make_smem_desc(a0 + (uint32_t)(((i * 16 + ki) * PITCH + kj) * 16), PLANE, PITCH * 16);
+                umma_bf16(d_tmem + (uint32_t)(i * N), adesc, bdesc, IDESC, (cb > 0 || j > 0 || t > 0) ? 1u : 0u);
+              }
+            }
+            if (j < 8) {
+              umma_commit(smem_u32(&phi_empty[r]));
+              ++it;
+            } else {
+              umma_commit(smem_u32(&silu_empty[sb]));
+            }
+            umma_commit(smem_u32(&w_empty[ws]));
           }
-          umma_commit(smem_u32(&phi_empty[r]));
-          umma_commit(smem_u32(&w_empty[ws]));
         }
         umma_commit(smem_u32(&acc_full[buf]));
       }
@@ -379,7 +427,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) kan_fwd_tc_kernel(const float*
 // ------------------------------------------------------------------------------------------------ host side
 static size_t smem_bytes(int N, int TT, int R) {
   size_t npos = (size_t)PITCH * (16 * TT + 2);
-  return (size_t)R * 2 * npos * 16 + (size_t)W_STAGES * 9 * 2 * N * 16 + (size_t)(2 * R + 2 * W_STAGES + 4) * 8 + 16;
+  return (size_t)(R + 2) * 2 * npos * 16 + (size_t)W_STAGES * 9 * 2 * N * 16 + (size_t)(2 * R + 2 * W_STAGES + 8) * 8 + 16;
 }
 static int pick_phi_stages(int N, int TT) {
   int r = 8;
