@@ -100,10 +100,12 @@ size_t kmu_kanconv2d_fwd_workspace_bytes(const kmu_kanconv2d_desc* d);
 size_t kmu_kanconv2d_bwd_workspace_bytes(const kmu_kanconv2d_desc* d);
 int kmu_kanconv2d_fwd(const kmu_kanconv2d_fwd_args* a, kmu_stream stream);
 int kmu_kanconv2d_bwd(const kmu_kanconv2d_bwd_args* a, kmu_stream stream);
-/* Which kernel family the FORWARD of a descriptor resolves to: 0 = fp32 CUDA-core, 1 = tcgen05 implicit GEMM.  The
+/* Which kernel family (forward AND backward) a descriptor resolves to: 0 = fp32 CUDA-core, 1 = tcgen05 implicit GEMM.  The
  * tensor path needs precision KMU_PREC_BF16, ksize 3, stride 1, padding 1, cubic splines with 8 basis functions,
  * Cin % 16 == 0, Cout in {16,32,64} and grid_uniform; anything else runs the fp32 family (still on the GPU). */
 int kmu_kanconv2d_path(const kmu_kanconv2d_desc* d);
+/* Bring-up / test hook, not part of the drop-in surface: process-wide kernel debug switches (0 = production). */
+void kmu_debug_flags(int flags);
 
 /* ------------------------------------------------------------------------------------------------------------
  * S: LayerNorm1D + HSMSSD          vim_block_init/vim_utils_init.py:50-59, vim_block_init/efficient_vim_init.py:33-61

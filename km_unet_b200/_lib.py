@@ -75,6 +75,7 @@ SYMBOLS = {
     "kmu_kanconv2d_fwd": (C.c_int, [C.POINTER(KanFwdArgs), C.c_void_p]),
     "kmu_kanconv2d_bwd": (C.c_int, [C.POINTER(KanBwdArgs), C.c_void_p]),
     "kmu_kanconv2d_path": (C.c_int, [C.POINTER(KanDesc)]),
+    "kmu_debug_flags": (None, [C.c_int]),
     "kmu_hsmssd_fwd_workspace_bytes": (C.c_size_t, [C.POINTER(HsmDesc)]),
     "kmu_hsmssd_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(HsmDesc)]),
     "kmu_hsmssd_fwd": (C.c_int, [C.POINTER(HsmFwdArgs), C.c_void_p]),

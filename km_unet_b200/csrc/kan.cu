@@ -36,6 +36,7 @@ size_t kmu_kanconv2d_fwd_workspace_bytes(const kmu_kanconv2d_desc* d) {
 
 size_t kmu_kanconv2d_bwd_workspace_bytes(const kmu_kanconv2d_desc* d) {
   if (check_desc(d, "kanconv2d_bwd_workspace_bytes") != KMU_OK) return 0;
+  if (kmu_kanconv2d_path(d)) return tc::bwd_workspace(make_dims(*d));
   return simt_bwd_workspace(make_dims(*d));
 }
 
@@ -65,7 +66,13 @@ int kmu_kanconv2d_bwd(const kmu_kanconv2d_bwd_args* a, kmu_stream stream) {
               "kanconv2d_bwd: d_spline_scaler is null");
   kmu_kanconv2d_bwd_args b = *a;
   if (!b.d.has_scaler) { b.spline_scaler = nullptr; b.d_spline_scaler = nullptr; }
+  if (kmu_kanconv2d_path(&a->d)) {
+    KMU_REQUIRE(kmu_device_supported(), KMU_ERR_DEVICE, "kanconv2d_bwd: the tcgen05 family needs an sm_100 device");
+    return tc::backward(&b, make_dims(a->d), (cudaStream_t)stream);
+  }
   return simt_backward(&b, make_dims(a->d), (cudaStream_t)stream);
 }
+
+void kmu_debug_flags(int flags) { tc::set_debug_flags(flags); }
 
 }  // extern "C"

@@ -73,6 +73,9 @@ namespace tc {
 bool supported(const kmu_kanconv2d_desc& s);
 size_t fwd_workspace(const Dims& d);
 int forward(const kmu_kanconv2d_fwd_args* a, const Dims& d, cudaStream_t st);
+size_t bwd_workspace(const Dims& d);
+int backward(const kmu_kanconv2d_bwd_args* a, const Dims& d, cudaStream_t st);
+void set_debug_flags(int flags);
 }  // namespace tc
 
 }  // namespace kan

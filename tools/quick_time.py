@@ -41,6 +41,10 @@ def main():
         gf = 2 * B * S * S * cout * cin * 81 / 1e9
         res[f"kan_{cin}_{cout}_{S}_B{B}"] = {"fwd_ms": f, "fwdbwd_ms": t, "fwd_TF": gf / f, "fwdbwd_TF": 3 * gf / t}
         print(res, flush=True)
+    if os.environ.get("QT_ONLY") == "kan":
+        os.makedirs("gpurun_out", exist_ok=True)
+        json.dump(res, open("gpurun_out/quick_time.json", "w"), indent=1)
+        return
     for (C, S) in [(16, 128), (32, 64), (64, 32)]:
         m = K.HSMSSD(C).to(dev)
         x = torch.randn(B, C, S * S, device=dev, requires_grad=True)
