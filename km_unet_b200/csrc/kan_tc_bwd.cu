@@ -47,7 +47,7 @@ __device__ __forceinline__ uint4 pack8_bf16(const float* v) {
 
 // ================================================================================================ dX
 constexpr int DX_N = 144;              // 16 channels x 9 Phi components
-constexpr int DX_STAGERS = 4, DX_WARP_MMA = 4, DX_WARP_LOAD = 5, DX_WARP_EPI0 = 6, DX_EPI_WARPS = 8;
+constexpr int DX_STAGERS = 8, DX_WARP_MMA = 8, DX_WARP_EPI0 = 9, DX_EPI_WARPS = 8;
 constexpr int DX_THREADS = (DX_WARP_EPI0 + DX_EPI_WARPS) * 32;
 
 struct BwdDims {
@@ -169,37 +169,57 @@ __global__ void __launch_bounds__(DX_THREADS, 1) kan_bwd_dx_tc_kernel(const floa
 
   if (warp < DX_STAGERS) {
     // ===================================================================== dY stagers: fp32 NCHW -> bf16 [og][pos][8 o]
-    uint32_t it = 0;
-    for (int tile = first; tile < d.num_tiles; tile += step, ++it) {
+    // Every thread owns UPT (o-group, halo position) units; the 8*UPT global loads of the NEXT tile are issued right after
+    // the current tile has been written to shared memory, so their latency hides behind that tile's MMAs.
+    constexpr int NST = DX_STAGERS * 32;
+    constexpr int UPT = (OG * BNPOS + NST - 1) / NST;
+    float v[UPT][8];
+    auto load_tile = [&](int tile) {
       const int b = tile / tiles_per_img;
       const int tr = tile - b * tiles_per_img;
       const int ty0 = (tr / d.tiles_x) * BR, tx0 = (tr % d.tiles_x) * 8;
-      const uint32_t s = it & 1u;
-      mbar_wait(smem_u32(&dy_empty[s]), ((it >> 1) & 1u) ^ 1u);
-      uint8_t* stage = dy_base + (size_t)s * DYSTAGE;
       const float* dyb = dy + (size_t)b * COUT * HW;
-      for (int u = tid; u < OG * BNPOS; u += DX_STAGERS * 32) {
+#pragma unroll
+      for (int k = 0; k < UPT; ++k) {
+        const int u = tid + k * NST;
         const int og = u / BNPOS, pos = u - og * BNPOS;
         const int py = pos / BP, px = pos - py * BP;
         const int gy = ty0 - 1 + py, gx = tx0 - 1 + px;
-        float v[8];
-        if (gy >= 0 && gy < d.H && gx >= 0 && gx < d.W) {
-          const float* p = dyb + (size_t)(og * 8) * HW + (size_t)gy * d.W + gx;
+        const bool ok = u < OG * BNPOS && gy >= 0 && gy < d.H && gx >= 0 && gx < d.W;
+        const float* p = dyb + (size_t)(og * 8) * HW + (size_t)gy * d.W + gx;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = __ldg(p + (size_t)e * HW);
-        } else {
+        for (int e = 0; e < 8; ++e) v[k][e] = ok ? __ldg(p + (size_t)e * HW) : 0.f;
+      }
+    };
+    uint32_t it = 0;
+    if (first < d.num_tiles) load_tile(first);
+    for (int tile = first; tile < d.num_tiles; tile += step, ++it) {
+      const uint32_t s = it & 1u;
+      mbar_wait(smem_u32(&dy_empty[s]), ((it >> 1) & 1u) ^ 1u);
+      uint8_t* stage = dy_base + (size_t)s * DYSTAGE;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      for (int k = 0; k < UPT; ++k) {
+        const int u = tid + k * NST;
+        if (u < OG * BNPOS) {
+          const int og = u / BNPOS, pos = u - og * BNPOS;
+          *reinterpret_cast<uint4*>(stage + (size_t)og * BPLANE + (size_t)pos * 16) = pack8_bf16(v[k]);
         }
-        *reinterpret_cast<uint4*>(stage + (size_t)og * BPLANE + (size_t)pos * 16) = pack8_bf16(v);
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&dy_full[s]));
+      if (tile + step < d.num_tiles) load_tile(tile + step);
     }
   } else if (warp == DX_WARP_MMA) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
+      {  // one-shot weight load: this channel block's transposed weights stay resident for the CTA's whole life
+        const uint32_t bar = smem_u32(w_full);
+        mbar_expect_tx(bar, WBYTES);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(w2pack) + (size_t)cb * WBYTES;
+#pragma unroll 1
+        for (int t = 0; t < 9; ++t) bulk_g2s(smem_u32(w_base + (size_t)t * KS * WBLK), src + (size_t)t * KS * WBLK, KS * WBLK, bar);
+      }
       mbar_wait(smem_u32(w_full), 0);
       uint32_t it = 0;
       const uint32_t w0 = smem_u32(w_base);
@@ -223,15 +243,6 @@ __global__ void __launch_bounds__(DX_THREADS, 1) kan_bwd_dx_tc_kernel(const floa
         umma_commit(smem_u32(&dy_empty[s]));
         umma_commit(smem_u32(&acc_full[s]));
       }
-    }
-  } else if (warp == DX_WARP_LOAD) {
-    // ===================================================================== one-shot weight load (stays resident)
-    if (lane == 0) {
-      const uint32_t bar = smem_u32(w_full);
-      mbar_expect_tx(bar, WBYTES);
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(w2pack) + (size_t)cb * WBYTES;
-#pragma unroll 1
-      for (int t = 0; t < 9; ++t) bulk_g2s(smem_u32(w_base + (size_t)t * KS * WBLK), src + (size_t)t * KS * WBLK, KS * WBLK, bar);
     }
   } else {
     // ===================================================================== epilogue: dPhi (TMEM) x Phi'(x) -> dX
@@ -339,23 +350,44 @@ __global__ void __launch_bounds__(DW_THREADS, 1) kan_bwd_dw_tc_kernel(const floa
 
   if (warp < DW_PRODUCERS) {
     // ===================================================================== Phi producers (channels cb*CH .. +CH)
-    uint32_t it = 0;
-    for (int tile = split; tile < d.num_tiles; tile += step, ++it) {
+    // x of the NEXT tile is fetched into registers while the current one is evaluated (latency behind the math).
+    constexpr int NPR = DW_PRODUCERS * 32;
+    constexpr int UPT = (CH * BNPOS + NPR - 1) / NPR;
+    float xr[UPT];
+    auto load_tile = [&](int tile) {
       const int b = tile / tiles_per_img;
       const int tr = tile - b * tiles_per_img;
       const int ty0 = (tr / d.tiles_x) * BR, tx0 = (tr % d.tiles_x) * 8;
-      const int st = it % DW_STAGES;
-      mbar_wait(smem_u32(&empty[st]), ((it / DW_STAGES) & 1u) ^ 1u);
-      uint8_t* stage = smem + (size_t)st * C::STAGE;
       const float* xb = x + ((size_t)b * d.Cin + cb * CH) * HW;
-      for (int u = tid; u < CH * BNPOS; u += DW_PRODUCERS * 32) {
+#pragma unroll
+      for (int k = 0; k < UPT; ++k) {
+        const int u = tid + k * NPR;
         const int cl = u / BNPOS, pos = u - cl * BNPOS;
         const int py = pos / BP, px = pos - py * BP;
         const int gy = ty0 - 1 + py, gx = tx0 - 1 + px;
-        const float xv = (gy >= 0 && gy < d.H && gx >= 0 && gx < d.W) ? __ldg(xb + (size_t)cl * HW + (size_t)gy * d.W + gx) : 0.f;
-        *reinterpret_cast<uint4*>(stage + (size_t)cl * BPLANE + (size_t)pos * 16) = spline_group(xv, d.t0, d.inv_h);
-        *reinterpret_cast<__nv_bfloat16*>(stage + (size_t)(CH + (cl >> 3)) * BPLANE + (size_t)pos * 16 + (cl & 7) * 2) =
-            __float2bfloat16_rn(silu_fast(xv));
+        const bool ok = u < CH * BNPOS && gy >= 0 && gy < d.H && gx >= 0 && gx < d.W;
+        xr[k] = ok ? __ldg(xb + (size_t)cl * HW + (size_t)gy * d.W + gx) : 0.f;
+      }
+    };
+    uint32_t it = 0;
+    if (split < d.num_tiles) load_tile(split);
+    for (int tile = split; tile < d.num_tiles; tile += step, ++it) {
+      float xc[UPT];
+#pragma unroll
+      for (int k = 0; k < UPT; ++k) xc[k] = xr[k];
+      if (tile + step < d.num_tiles) load_tile(tile + step);
+      const int st = it % DW_STAGES;
+      mbar_wait(smem_u32(&empty[st]), ((it / DW_STAGES) & 1u) ^ 1u);
+      uint8_t* stage = smem + (size_t)st * C::STAGE;
+#pragma unroll
+      for (int k = 0; k < UPT; ++k) {
+        const int u = tid + k * NPR;
+        if (u < CH * BNPOS) {
+          const int cl = u / BNPOS, pos = u - cl * BNPOS;
+          *reinterpret_cast<uint4*>(stage + (size_t)cl * BPLANE + (size_t)pos * 16) = spline_group(xc[k], d.t0, d.inv_h);
+          *reinterpret_cast<__nv_bfloat16*>(stage + (size_t)(CH + (cl >> 3)) * BPLANE + (size_t)pos * 16 + (cl & 7) * 2) =
+              __float2bfloat16_rn(silu_fast(xc[k]));
+        }
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -363,33 +395,45 @@ __global__ void __launch_bounds__(DW_THREADS, 1) kan_bwd_dw_tc_kernel(const floa
     }
   } else if (warp < DW_PRODUCERS + DW_STAGERS) {
     // ===================================================================== dY stagers: fp32 NCHW -> bf16 [row][og][8 px][8 o]
+    constexpr int NST = DW_STAGERS * 32;
+    constexpr int UNITS = BR * C::OG * 8;
+    constexpr int UPT = (UNITS + NST - 1) / NST;
     const int stid = tid - DW_PRODUCERS * 32;
-    uint32_t it = 0;
-    for (int tile = split; tile < d.num_tiles; tile += step, ++it) {
+    float v[UPT][8];
+    auto load_tile = [&](int tile) {
       const int b = tile / tiles_per_img;
       const int tr = tile - b * tiles_per_img;
       const int ty0 = (tr / d.tiles_x) * BR, tx0 = (tr % d.tiles_x) * 8;
+      const float* dyb = dy + (size_t)b * COUT * HW;
+#pragma unroll
+      for (int k = 0; k < UPT; ++k) {
+        const int u = stid + k * NST;
+        const int cx = u & 7, r = (u >> 3) % BR, og = u / (8 * BR);
+        const int gy = ty0 + r, gx = tx0 + cx;
+        const bool ok = u < UNITS && gy < d.H && gx < d.W;
+        const float* p = dyb + (size_t)(og * 8) * HW + (size_t)gy * d.W + gx;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[k][e] = ok ? __ldg(p + (size_t)e * HW) : 0.f;
+      }
+    };
+    uint32_t it = 0;
+    if (split < d.num_tiles) load_tile(split);
+    for (int tile = split; tile < d.num_tiles; tile += step, ++it) {
       const int st = it % DW_STAGES;
       mbar_wait(smem_u32(&empty[st]), ((it / DW_STAGES) & 1u) ^ 1u);
       uint8_t* stage = smem + (size_t)st * C::STAGE + C::PHI_STAGE;
-      const float* dyb = dy + (size_t)b * COUT * HW;
-      for (int u = stid; u < BR * C::OG * 8; u += DW_STAGERS * 32) {
-        const int cx = u & 7, r = (u >> 3) % BR, og = u / (8 * BR);
-        const int gy = ty0 + r, gx = tx0 + cx;
-        float v[8];
-        if (gy < d.H && gx < d.W) {
-          const float* p = dyb + (size_t)(og * 8) * HW + (size_t)gy * d.W + gx;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = __ldg(p + (size_t)e * HW);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      for (int k = 0; k < UPT; ++k) {
+        const int u = stid + k * NST;
+        if (u < UNITS) {
+          const int cx = u & 7, r = (u >> 3) % BR, og = u / (8 * BR);
+          *reinterpret_cast<uint4*>(stage + (size_t)(r + 2) * C::DY_ROWB + (size_t)og * 128 + (size_t)cx * 16) = pack8_bf16(v[k]);
         }
-        *reinterpret_cast<uint4*>(stage + (size_t)(r + 2) * C::DY_ROWB + (size_t)og * 128 + (size_t)cx * 16) = pack8_bf16(v);
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&full[st]));
+      if (tile + step < d.num_tiles) load_tile(tile + step);
     }
   } else {
     // ===================================================================== MMA issuer
