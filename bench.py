@@ -184,7 +184,6 @@ def run_ours(args):
     x_host = torch.randn(B, CIN, S, S, generator=g).pin_memory()
     gout = torch.randn(B, COUT, S, S, generator=g).to(dev)
     x_dev = x_host.to(dev).requires_grad_(True)
-    x_e2e = torch.empty_like(x_dev).requires_grad_(True)
     grads_host = [torch.empty(p.shape, dtype=p.dtype).pin_memory() for p in params]
 
     def barrier():
@@ -208,19 +207,43 @@ def run_ours(args):
         if reducer is not None:
             reducer.finish()
 
+    # e2e: the batch lives in pinned host memory; every step copies it host->device (on a copy stream, double buffered so
+    # step i+1's copy overlaps step i's kernels -- the loop a user of the module API writes) and reads the step's result
+    # (the weight gradients) back to the host before the step counts as done.
+    copy_stream = torch.cuda.Stream(device=dev)
+    x_bufs = [torch.empty_like(x_dev) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    state = {"i": 0, "primed": False}
+
+    def prefetch(slot):
+        with torch.cuda.stream(copy_stream), torch.no_grad():
+            copy_stream.wait_event(consumed[slot])
+            x_bufs[slot].copy_(x_host, non_blocking=True)        # H2D from pinned memory, every step
+            ready[slot].record(copy_stream)
+
     def step_e2e():
+        slot = state["i"] & 1
+        if not state["primed"]:
+            for e in consumed:
+                e.record()
+            prefetch(slot)
+            state["primed"] = True
+        prefetch(slot ^ 1)                                       # next step's input, overlapped with this step's kernels
+        torch.cuda.current_stream().wait_event(ready[slot])
         for p in params:
             p.grad = None
-        x_e2e.grad = None
-        with torch.no_grad():
-            x_e2e.copy_(x_host, non_blocking=True)        # H2D from pinned memory, every step
-        y = layer(x_e2e)
+        xin = x_bufs[slot].requires_grad_(True)
+        xin.grad = None
+        y = layer(xin)
         y.backward(gout)
+        consumed[slot].record()
         if reducer is not None:
             reducer.finish()
         for h, p in zip(grads_host, params):
             h.copy_(p.grad, non_blocking=True)            # D2H of the step's result (the weight gradients)
         torch.cuda.current_stream().synchronize()         # the host must hold the result before the next step
+        state["i"] += 1
 
     def timed(step, steps, warmup):
         for _ in range(warmup):
@@ -247,9 +270,13 @@ def run_ours(args):
     e2e_ms = timed(step_e2e, args.steps, args.warmup)
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
 
-    # per-family device time (CUDA events on the launching stream): forward alone, backward alone
+    # per-kernel-family device time: CUDA events on the launching (current) stream around each family's launches.
+    # backward-input alone = parameters frozen (the C call gets d_base_weight = NULL), backward-weights alone = detached input.
     def time_family(which):
         ts = []
+        xin = x_dev if which != "dw" else x_dev.detach()
+        for p in params:
+            p.requires_grad_(which != "dx")
         for i in range(args.warmup + args.steps):
             for p in params:
                 p.grad = None
@@ -257,27 +284,33 @@ def run_ours(args):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             if which == "fwd":
                 a.record()
-                y = layer(x_dev)
+                y = layer(xin)
                 b.record()
             else:
-                y = layer(x_dev)
+                y = layer(xin)
                 a.record()
                 y.backward(gout)
                 b.record()
             torch.cuda.synchronize()
             if i >= args.warmup:
                 ts.append(a.elapsed_time(b))
+        for p in params:
+            p.requires_grad_(True)
         return sum(ts) / len(ts)
 
-    fwd_ms = time_family("fwd")
-    bwd_ms = time_family("bwd")
+    fam_ms = {"kanconv2d_fwd": time_family("fwd"), "kanconv2d_bwd_dx": time_family("dx"), "kanconv2d_bwd_dw": time_family("dw")}
     peaks = load_peaks()
     peak_tf = peaks["bf16_tflops"]
-    fam = {"kanconv2d_fwd": (flops_fwd(B), fwd_ms), "kanconv2d_bwd": (2 * flops_fwd(B), bwd_ms)}
+    fam = {k: (flops_fwd(B), ms) for k, ms in fam_ms.items()}        # each family is one 2*M*Cout*Cin*81 GEMM
     dom = max(fam, key=lambda k: fam[k][1])
     roof_all = {k: {"ms": ms, "achieved": fl / ms / 1e9, "frac": fl / ms / 1e9 / peak_tf} for k, (fl, ms) in fam.items()}
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath) and args.precision == "bf16" and B == 32:
+        with open(tpath) as f:
+            traffic = json.load(f).get(dom)
     roofline = {"kernel": dom, "bound": "tensor", "achieved": roof_all[dom]["achieved"], "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": roof_all[dom]["frac"], "traffic": None, "peak_source": peaks["source"] + " bf16 burst",
+                "frac": roof_all[dom]["frac"], "traffic": traffic, "peak_source": peaks["source"] + " bf16 burst",
                 "algorithmic_flops_per_launch": fam[dom][0], "families": roof_all}
 
     cpu = None
@@ -315,7 +348,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
-    ap.add_argument("--precision", default=os.environ.get("KMU_KAN_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("KMU_KAN_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
