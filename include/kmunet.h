@@ -219,6 +219,82 @@ int kmu_dysample_sample_bwd(const kmu_dysample_desc* d, const float* x, const fl
                             float* dx /* zero-initialised, accumulated */, float* doffset /* overwritten */,
                             kmu_stream stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * G: DAGEM attention-gated fusion        DAGEM_md.py:62-92 (edge / vertex gating), :104-110 (final aggregation)
+ *   s = x . sum_k a_k nb_k + a_b ; agg = ReLU(BN0(s)) ; ue_k = We [x; x . nb_k] + e_b ; uvp = Wv [x; agg] + v_b ;
+ *   r = sum_k r_k ReLU(BN1(ue_k)) + r_b ; z = Wf [deformed; ReLU(BN2(uvp)) . ReLU(BN3(r))] ; out = ReLU(BN4(z))
+ *   nb_k = circular neighbours x[h-1], x[h+1], x[w-1], x[w+1] (:64-67).  `deformed` = deform_conv(x, offset_conv(x)) + x
+ *   (:95-104) is the caller's tensor.  BatchNorm order bn[0..4] = edge_aggregation_func.1, edge_update_func.1,
+ *   vertex_update_func.1, update_edge_reduce_func.1, final_aggregation_layer.1.  training != 0: batch statistics
+ *   (biased variance) and running-stat update with `momentum` (unbiased variance), as torch.nn.BatchNorm does.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t B, C, H, W; /* C = input_channels in {8,16,32,64} */
+  int32_t training;
+  float momentum, eps;
+} kmu_dagem_desc;
+
+typedef struct {
+  const float* weight;  /* gamma */
+  const float* bias;    /* beta */
+  float* running_mean;  /* updated in place when training; read when not */
+  float* running_var;
+} kmu_dagem_bn;
+
+typedef struct {
+  kmu_dagem_desc d;
+  const float* x;        /* (B,C,H,W) */
+  const float* deformed; /* (B,C,H,W) */
+  const float* ea_w;     /* edge_aggregation_func.0.weight (1,4) */
+  const float* ea_b;     /* (1) */
+  const float* vu_w;     /* vertex_update_func.0.weight (C/2, 2C) */
+  const float* vu_b;     /* (C/2) */
+  const float* eu_w;     /* edge_update_func.0.weight (C/2, 2C) */
+  const float* eu_b;     /* (C/2) */
+  const float* er_w;     /* update_edge_reduce_func.0.weight (1,4) */
+  const float* er_b;     /* (1) */
+  const float* wf;       /* final_aggregation_layer.0.weight (C, C + C/2) */
+  kmu_dagem_bn bn[5];
+  float* out;            /* (B,C,H,W) */
+  float* saved;          /* kmu_dagem_saved_bytes(): pre-BN activations + BN statistics, input of the backward call */
+  void* workspace;
+  size_t workspace_bytes;
+} kmu_dagem_fwd_args;
+
+typedef struct {
+  kmu_dagem_desc d;
+  const float* x;
+  const float* deformed;
+  const float* dout; /* (B,C,H,W) */
+  const float* saved;
+  const float* ea_w;
+  const float* vu_w;
+  const float* eu_w;
+  const float* er_w;
+  const float* wf;
+  float* dx;         /* gradient through the gating path only (the caller adds the deform/residual path) */
+  float* d_deformed; /* (B,C,H,W) */
+  float* d_ea_w;
+  float* d_ea_b;
+  float* d_vu_w;
+  float* d_vu_b;
+  float* d_eu_w;
+  float* d_eu_b;
+  float* d_er_w;
+  float* d_er_b;
+  float* d_wf;
+  float* d_bn_weight[5];
+  float* d_bn_bias[5];
+  void* workspace;
+  size_t workspace_bytes;
+} kmu_dagem_bwd_args;
+
+size_t kmu_dagem_saved_bytes(const kmu_dagem_desc* d);
+size_t kmu_dagem_fwd_workspace_bytes(const kmu_dagem_desc* d);
+size_t kmu_dagem_bwd_workspace_bytes(const kmu_dagem_desc* d);
+int kmu_dagem_fwd(const kmu_dagem_fwd_args* a, kmu_stream stream);
+int kmu_dagem_bwd(const kmu_dagem_bwd_args* a, kmu_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,6 +64,27 @@ class DysBwdArgs(C.Structure):
                [("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
+class DagemDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B", "C", "H", "W", "training")] + [("momentum", C.c_float), ("eps", C.c_float)]
+
+
+class DagemBn(C.Structure):
+    _fields_ = [(n, _f32p) for n in ("weight", "bias", "running_mean", "running_var")]
+
+
+class DagemFwdArgs(C.Structure):
+    _fields_ = [("d", DagemDesc)] + [(n, _f32p) for n in ("x", "deformed", "ea_w", "ea_b", "vu_w", "vu_b", "eu_w", "eu_b",
+                                                          "er_w", "er_b", "wf")] + \
+               [("bn", DagemBn * 5), ("out", _f32p), ("saved", _f32p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+class DagemBwdArgs(C.Structure):
+    _fields_ = [("d", DagemDesc)] + [(n, _f32p) for n in ("x", "deformed", "dout", "saved", "ea_w", "vu_w", "eu_w", "er_w", "wf",
+                                                          "dx", "d_deformed", "d_ea_w", "d_ea_b", "d_vu_w", "d_vu_b", "d_eu_w",
+                                                          "d_eu_b", "d_er_w", "d_er_b", "d_wf")] + \
+               [("d_bn_weight", _f32p * 5), ("d_bn_bias", _f32p * 5), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
 # every symbol include/kmunet.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "kmu_version": (C.c_int, []),
@@ -89,6 +110,11 @@ SYMBOLS = {
     "kmu_dysample_bwd": (C.c_int, [C.POINTER(DysBwdArgs), C.c_void_p]),
     "kmu_dysample_sample_fwd": (C.c_int, [C.POINTER(DysDesc), _f32p, _f32p, _f32p, C.c_void_p]),
     "kmu_dysample_sample_bwd": (C.c_int, [C.POINTER(DysDesc), _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
+    "kmu_dagem_saved_bytes": (C.c_size_t, [C.POINTER(DagemDesc)]),
+    "kmu_dagem_fwd_workspace_bytes": (C.c_size_t, [C.POINTER(DagemDesc)]),
+    "kmu_dagem_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(DagemDesc)]),
+    "kmu_dagem_fwd": (C.c_int, [C.POINTER(DagemFwdArgs), C.c_void_p]),
+    "kmu_dagem_bwd": (C.c_int, [C.POINTER(DagemBwdArgs), C.c_void_p]),
 }
 
 _lib = None

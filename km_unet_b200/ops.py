@@ -9,10 +9,10 @@ import torch
 from torch.amp import custom_bwd, custom_fwd
 
 from . import _lib
-from ._lib import (DysBwdArgs, DysDesc, DysFwdArgs, HsmBwdArgs, HsmDesc, HsmFwdArgs, KanBwdArgs, KanDesc, KanFwdArgs,
+from ._lib import (DagemBn, DagemBwdArgs, DagemDesc, DagemFwdArgs, DysBwdArgs, DysDesc, DysFwdArgs, HsmBwdArgs, HsmDesc, HsmFwdArgs, KanBwdArgs, KanDesc, KanFwdArgs,
                    KMU_PREC_BF16, KMU_PREC_FP32, check, ptr, stream_ptr)
 
-__all__ = ["kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dysample_sample", "KMU_PREC_FP32", "KMU_PREC_BF16"]
+__all__ = ["kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dysample_sample", "dagem_gate", "KMU_PREC_FP32", "KMU_PREC_BF16"]
 
 
 def _workspace(nbytes, device):
@@ -282,3 +282,74 @@ def dysample_sample(x, offset, scale=2, groups=4):
     if not x.is_cuda:
         raise RuntimeError("km_unet_b200.dysample_sample: CUDA tensors only (no CPU fallback)")
     return _DySampleSampleFn.apply(x, offset, int(scale), int(groups))
+
+
+# ------------------------------------------------------------------------------------------------------ DAGEM
+class _DagemGateFn(torch.autograd.Function):
+    """inputs: x, deformed, 9 Linear/conv tensors, 5 x (bn weight, bn bias); non-differentiable: running stats, flags."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, deformed, ea_w, ea_b, vu_w, vu_b, eu_w, eu_b, er_w, er_b, wf, bn_w0, bn_b0, bn_w1, bn_b1, bn_w2, bn_b2,
+                bn_w3, bn_b3, bn_w4, bn_b4, running, training, momentum, eps):
+        lib = _lib.lib()
+        x, deformed = x.contiguous(), deformed.contiguous()
+        B, Cc, H, W = x.shape
+        desc = DagemDesc(B, Cc, H, W, 1 if training else 0, float(momentum), float(eps))
+        nsaved = lib.kmu_dagem_saved_bytes(C.byref(desc))
+        if nsaved == 0:
+            raise RuntimeError("dagem: " + _lib.last_error())
+        lin = [t.contiguous() for t in (ea_w, ea_b, vu_w, vu_b, eu_w, eu_b, er_w, er_b, wf)]
+        bnw = [t.contiguous() for t in (bn_w0, bn_w1, bn_w2, bn_w3, bn_w4)]
+        bnb = [t.contiguous() for t in (bn_b0, bn_b1, bn_b2, bn_b3, bn_b4)]
+        saved = torch.empty(nsaved // 4, dtype=torch.float32, device=x.device)
+        out = torch.empty_like(x)
+        ws = _workspace(lib.kmu_dagem_fwd_workspace_bytes(C.byref(desc)), x.device)
+        bns = (DagemBn * 5)()
+        for i in range(5):
+            rm, rv = running[i]
+            bns[i] = DagemBn(ptr(bnw[i]), ptr(bnb[i]), ptr(rm), ptr(rv))
+        args = DagemFwdArgs(desc, ptr(x), ptr(deformed), *[ptr(t) for t in lin], bns, ptr(out), ptr(saved), ws.data_ptr(),
+                            ws.numel())
+        check(lib.kmu_dagem_fwd(C.byref(args), stream_ptr()), "kmu_dagem_fwd")
+        ctx.save_for_backward(x, deformed, saved, *lin, *bnw)
+        ctx.desc = desc
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dout):
+        lib = _lib.lib()
+        x, deformed, saved = ctx.saved_tensors[:3]
+        ea_w, ea_b, vu_w, vu_b, eu_w, eu_b, er_w, er_b, wf = ctx.saved_tensors[3:12]
+        bnw = ctx.saved_tensors[12:17]
+        desc = ctx.desc
+        dout = dout.to(torch.float32).contiguous()
+        dx, dd = torch.empty_like(x), torch.empty_like(x)
+        dlin = [torch.empty_like(t) for t in (ea_w, ea_b, vu_w, vu_b, eu_w, eu_b, er_w, er_b, wf)]
+        dbw = [torch.empty_like(t) for t in bnw]
+        dbb = [torch.empty_like(t) for t in bnw]
+        ws = _workspace(lib.kmu_dagem_bwd_workspace_bytes(C.byref(desc)), x.device)
+        d_ea_w, d_ea_b, d_vu_w, d_vu_b, d_eu_w, d_eu_b, d_er_w, d_er_b, d_wf = dlin
+        args = DagemBwdArgs(desc, ptr(x), ptr(deformed), ptr(dout), ptr(saved), ptr(ea_w), ptr(vu_w), ptr(eu_w), ptr(er_w), ptr(wf),
+                            ptr(dx), ptr(dd), ptr(d_ea_w), ptr(d_ea_b), ptr(d_vu_w), ptr(d_vu_b), ptr(d_eu_w), ptr(d_eu_b),
+                            ptr(d_er_w), ptr(d_er_b), ptr(d_wf), (_lib._f32p * 5)(*[ptr(t) for t in dbw]),
+                            (_lib._f32p * 5)(*[ptr(t) for t in dbb]), ws.data_ptr(), ws.numel())
+        check(lib.kmu_dagem_bwd(C.byref(args), stream_ptr()), "kmu_dagem_bwd")
+        bn_grads = []
+        for i in range(5):
+            bn_grads += [dbw[i], dbb[i]]
+        return (dx, dd, *dlin, *bn_grads, None, None, None, None)
+
+
+def dagem_gate(x, deformed, linears, bns, training, momentum=0.1, eps=1e-5):
+    """The gating + final-aggregation part of DAGEM.forward (DAGEM_md.py:62-92,104-110).
+    linears = (ea_w, ea_b, vu_w, vu_b, eu_w, eu_b, er_w, er_b, wf); bns = 5 x (weight, bias, running_mean, running_var) in
+    the order edge_aggregation, edge_update, vertex_update, update_edge_reduce, final_aggregation."""
+    if not x.is_cuda:
+        raise RuntimeError("km_unet_b200.dagem_gate: CUDA tensors only (no CPU fallback)")
+    flat = []
+    for w, b, _, _ in bns:
+        flat += [w, b]
+    running = [(rm, rv) for _, _, rm, rv in bns]
+    return _DagemGateFn.apply(x, deformed, *linears, *flat, running, bool(training), momentum, eps)
