@@ -26,7 +26,8 @@ constexpr int N = 64;         // states
 constexpr int N3 = 192;       // projected channels
 constexpr int TH = 8, TW = 32, HW_ = TW + 2, HH_ = TH + 2, NHALO = HW_ * HH_;  // spatial tile + 1-pixel halo (340)
 constexpr int SUB = 256;      // positions per sub-tile in the over-L sweeps
-constexpr int SUBS_PER_CTA = 4;
+constexpr int SUBS_PER_CTA = 2;
+constexpr int GT = 512;      // threads of the per-batch (C,64) gate kernels
 
 struct Dims {
   int B, C, L, H;
@@ -44,37 +45,49 @@ static Dims make_dims(const kmu_hsmssd_desc& s) {
 }
 
 // ================================================================================================ forward
-// ---- P = dw3x3(Wp x).  grid (tiles, B, 192/NCH), 256 threads = 8x32 interior positions.
-template <int NCH>
+// ---- P = dw3x3(Wp x).  grid (tiles, B), 256 threads = 8x32 interior positions.  The x halo tile is staged once in
+//      shared memory; the CTA then walks the 192 projected channels in passes of PCH: projection on the halo (zero outside
+//      the image = the depthwise conv's zero padding), depthwise 3x3 from shared memory, coalesced store of P.
+constexpr int PCH = 16;
+template <int C>
 __global__ void __launch_bounds__(256) hsm_proj_dw_kernel(const float* __restrict__ x, const float* __restrict__ wp,
                                                           const float* __restrict__ wd, float* __restrict__ P, Dims d) {
   extern __shared__ __align__(16) float smem[];
-  float* q_s = smem;                    // [NCH][NHALO]
-  float* wp_s = q_s + NCH * NHALO;      // [C][NCH]
-  float* wd_s = wp_s + d.C * NCH;       // [NCH][9]
+  float* x_s = smem;                    // [C][NHALO]
+  float* q_s = x_s + C * NHALO;         // [PCH][NHALO]
+  float* wp_s = q_s + PCH * NHALO;      // [C][PCH]
+  float* wd_s = wp_s + C * PCH;         // [PCH][12]
   const int tid = threadIdx.x;
   const int ty0 = (blockIdx.x / d.tiles_x) * TH, tx0 = (blockIdx.x % d.tiles_x) * TW;
-  const int b = blockIdx.y, n0 = blockIdx.z * NCH;
-  for (int i = tid; i < d.C * NCH; i += 256) {
-    int c = i / NCH, nn = i - c * NCH;
-    wp_s[i] = wp[(size_t)(n0 + nn) * d.C + c];
-  }
-  for (int i = tid; i < NCH * 9; i += 256) wd_s[i] = wd[(size_t)n0 * 9 + i];
-  __syncthreads();
-  const float* xb = x + (size_t)b * d.C * d.L;
-  for (int pos = tid; pos < NHALO; pos += 256) {
+  const int b = blockIdx.y;
+  const float* xb = x + (size_t)b * C * d.L;
+  for (int i = tid; i < C * NHALO; i += 256) {
+    int c = i / NHALO, pos = i - c * NHALO;
     int hy = pos / HW_, hx = pos - hy * HW_;
     int gy = ty0 + hy - 1, gx = tx0 + hx - 1;
-    float q[NCH];
+    x_s[i] = (gy >= 0 && gy < d.H && gx >= 0 && gx < d.H) ? __ldg(xb + (size_t)c * d.L + (size_t)gy * d.H + gx) : 0.f;
+  }
+  const int ly = tid >> 5, lx = tid & 31;
+  const int gy = ty0 + ly, gx = tx0 + lx;
+  const bool inside = gy < d.H && gx < d.H;
+  for (int n0 = 0; n0 < N3; n0 += PCH) {
+    __syncthreads();
+    for (int i = tid; i < C * PCH; i += 256) {
+      int c = i / PCH, nn = i - c * PCH;
+      wp_s[i] = wp[(size_t)(n0 + nn) * C + c];
+    }
+    for (int i = tid; i < PCH * 9; i += 256) wd_s[(i / 9) * 12 + (i % 9)] = wd[(size_t)n0 * 9 + i];
+    __syncthreads();
+    for (int pos = tid; pos < NHALO; pos += 256) {
+      float q[PCH];
 #pragma unroll
-    for (int i = 0; i < NCH; ++i) q[i] = 0.f;
-    if (gy >= 0 && gy < d.H && gx >= 0 && gx < d.H) {
-      const float* xp = xb + (size_t)gy * d.H + gx;
-      for (int c = 0; c < d.C; ++c) {
-        float xv = __ldg(xp + (size_t)c * d.L);
-        const float4* w4 = reinterpret_cast<const float4*>(wp_s + c * NCH);
+      for (int i = 0; i < PCH; ++i) q[i] = 0.f;
+#pragma unroll 8
+      for (int c = 0; c < C; ++c) {
+        float xv = x_s[c * NHALO + pos];
+        const float4* w4 = reinterpret_cast<const float4*>(wp_s + c * PCH);
 #pragma unroll
-        for (int i = 0; i < NCH / 4; ++i) {
+        for (int i = 0; i < PCH / 4; ++i) {
           float4 w = w4[i];
           q[4 * i + 0] = fmaf(xv, w.x, q[4 * i + 0]);
           q[4 * i + 1] = fmaf(xv, w.y, q[4 * i + 1]);
@@ -82,23 +95,23 @@ __global__ void __launch_bounds__(256) hsm_proj_dw_kernel(const float* __restric
           q[4 * i + 3] = fmaf(xv, w.w, q[4 * i + 3]);
         }
       }
-    }
 #pragma unroll
-    for (int i = 0; i < NCH; ++i) q_s[i * NHALO + pos] = q[i];
-  }
-  __syncthreads();
-  const int ly = tid >> 5, lx = tid & 31;
-  const int gy = ty0 + ly, gx = tx0 + lx;
-  if (gy < d.H && gx < d.H) {
-    float* pp = P + ((size_t)b * N3 + n0) * d.L + (size_t)gy * d.H + gx;
+      for (int i = 0; i < PCH; ++i) q_s[i * NHALO + pos] = q[i];
+    }
+    __syncthreads();
+    if (inside) {
+      float* pp = P + ((size_t)b * N3 + n0) * d.L + (size_t)gy * d.H + gx;
 #pragma unroll 4
-    for (int nn = 0; nn < NCH; ++nn) {
-      const float* qr = q_s + nn * NHALO + ly * HW_ + lx;
-      const float* w = wd_s + nn * 9;
-      float s = qr[0] * w[0] + qr[1] * w[1] + qr[2] * w[2];
-      s += qr[HW_] * w[3] + qr[HW_ + 1] * w[4] + qr[HW_ + 2] * w[5];
-      s += qr[2 * HW_] * w[6] + qr[2 * HW_ + 1] * w[7] + qr[2 * HW_ + 2] * w[8];
-      pp[(size_t)nn * d.L] = s;
+      for (int nn = 0; nn < PCH; ++nn) {
+        const float* qr = q_s + nn * NHALO + ly * HW_ + lx;
+        const float4 wa = *reinterpret_cast<const float4*>(wd_s + nn * 12);
+        const float4 wb = *reinterpret_cast<const float4*>(wd_s + nn * 12 + 4);
+        const float w8 = wd_s[nn * 12 + 8];
+        float sacc = qr[0] * wa.x + qr[1] * wa.y + qr[2] * wa.z;
+        sacc += qr[HW_] * wa.w + qr[HW_ + 1] * wb.x + qr[HW_ + 2] * wb.y;
+        sacc += qr[2 * HW_] * wb.z + qr[2 * HW_ + 1] * wb.w + qr[2 * HW_ + 2] * w8;
+        pp[(size_t)nn * d.L] = sacc;
+      }
     }
   }
 }
@@ -194,49 +207,61 @@ __global__ void __launch_bounds__(256) hsm_softmax_hs_kernel(const float* __rest
   }
 }
 
-// ---- combine the T partials of one batch element, then the (C,64)-sized gate.  grid B, 256 threads.
-__global__ void __launch_bounds__(256) hsm_combine_gate_kernel(const float* __restrict__ part_m, const float* __restrict__ part_s,
-                                                               const float* __restrict__ part_hs, const float* __restrict__ whz,
-                                                               const float* __restrict__ wo, const float* __restrict__ Dp,
-                                                               float* __restrict__ stats, float* __restrict__ hs_out,
-                                                               float* __restrict__ hz_out, float* __restrict__ ho_out, Dims d) {
+// ---- combine the T partials of one batch element, then the (C,64)-sized gate.  grid B, GT threads; weights in smem.
+__global__ void __launch_bounds__(GT) hsm_combine_gate_kernel(const float* __restrict__ part_m, const float* __restrict__ part_s,
+                                                              const float* __restrict__ part_hs, const float* __restrict__ whz,
+                                                              const float* __restrict__ wo, const float* __restrict__ Dp,
+                                                              float* __restrict__ stats, float* __restrict__ hs_out,
+                                                              float* __restrict__ hz_out, float* __restrict__ ho_out, Dims d) {
   extern __shared__ __align__(16) float smem[];
+  const int C = d.C;
+  constexpr int CG = GT / 64;
   float* hs_s = smem;                  // [C][64]
-  float* hz_s = hs_s + d.C * 64;       // [2C][64]
-  float* v_s = hz_s + 2 * d.C * 64;    // [C][64]
-  const int tid = threadIdx.x, n = tid & 63, cg = tid >> 6, b = blockIdx.x, C = d.C;
+  float* hz_s = hs_s + C * 64;         // [2C][64]
+  float* v_s = hz_s + 2 * C * 64;      // [C][64]
+  float* whz_s = v_s + C * 64;         // [2C][C]
+  float* wo_s = whz_s + 2 * C * C;     // [C][C]
+  float* sc_s = wo_s + C * C;          // [T][64] exp(m_t - m)
+  const int tid = threadIdx.x, n = tid & 63, cg = tid >> 6, b = blockIdx.x;
+  for (int i = tid; i < 2 * C * C; i += GT) whz_s[i] = whz[i];
+  for (int i = tid; i < C * C; i += GT) wo_s[i] = wo[i];
   const float* pm = part_m + (size_t)b * d.T * 64 + n;
   const float* ps = part_s + (size_t)b * d.T * 64 + n;
   float m = -INFINITY;
   for (int t = 0; t < d.T; ++t) m = fmaxf(m, pm[t * 64]);
-  float s = 0.f;
-  for (int t = 0; t < d.T; ++t) s += ps[t * 64] * expf(pm[t * 64] - m);
-  const float inv_s = 1.0f / s;
-  if (cg == 0 && stats) { stats[(size_t)b * 128 + n] = m; stats[(size_t)b * 128 + 64 + n] = s; }
-  for (int c = cg; c < C; c += 4) {
+  float ssum = 0.f;
+  for (int t = 0; t < d.T; ++t) {
+    float e = expf(pm[t * 64] - m);
+    ssum += ps[t * 64] * e;
+    if (cg == 0) sc_s[t * 64 + n] = e;
+  }
+  const float inv_s = 1.0f / ssum;
+  if (cg == 0 && stats) { stats[(size_t)b * 128 + n] = m; stats[(size_t)b * 128 + 64 + n] = ssum; }
+  __syncthreads();
+  for (int c = cg; c < C; c += CG) {
     float a = 0.f;
-    for (int t = 0; t < d.T; ++t) a = fmaf(part_hs[(((size_t)b * d.T + t) * C + c) * 64 + n], expf(pm[t * 64] - m), a);
+    for (int t = 0; t < d.T; ++t) a = fmaf(part_hs[(((size_t)b * d.T + t) * C + c) * 64 + n], sc_s[t * 64 + n], a);
     a *= inv_s;
     hs_s[c * 64 + n] = a;
     if (hs_out) hs_out[((size_t)b * C + c) * 64 + n] = a;
   }
   __syncthreads();
-  for (int dd = cg; dd < 2 * C; dd += 4) {
+  for (int dd = cg; dd < 2 * C; dd += CG) {
     float a = 0.f;
-    for (int c = 0; c < C; ++c) a = fmaf(__ldg(whz + (size_t)dd * C + c), hs_s[c * 64 + n], a);
+    for (int c = 0; c < C; ++c) a = fmaf(whz_s[dd * C + c], hs_s[c * 64 + n], a);
     hz_s[dd * 64 + n] = a;
     if (hz_out) hz_out[((size_t)b * 2 * C + dd) * 64 + n] = a;
   }
   __syncthreads();
   const float Dv = Dp[0];
-  for (int c = cg; c < C; c += 4) {
+  for (int c = cg; c < C; c += CG) {
     float hh = hz_s[c * 64 + n], z = hz_s[(C + c) * 64 + n];
     v_s[c * 64 + n] = hh * siluf_(z) + hh * Dv;
   }
   __syncthreads();
-  for (int dd = cg; dd < C; dd += 4) {
+  for (int dd = cg; dd < C; dd += CG) {
     float a = 0.f;
-    for (int c = 0; c < C; ++c) a = fmaf(__ldg(wo + (size_t)dd * C + c), v_s[c * 64 + n], a);
+    for (int c = 0; c < C; ++c) a = fmaf(wo_s[dd * C + c], v_s[c * 64 + n], a);
     ho_out[((size_t)b * C + dd) * 64 + n] = a;
   }
 }
@@ -313,24 +338,29 @@ __global__ void __launch_bounds__(256) hsm_contract_kernel(const float* __restri
   }
 }
 
-// ---- gate backward on (C,64) tiles.  grid B, 256 threads.  Per-batch weight-gradient partials -> wpart[b][...]
-//      layout of wpart[b]: dWo (C*C) | dWhz (2C*C) | dD (1)
-__global__ void __launch_bounds__(256) hsm_gate_bwd_kernel(const float* __restrict__ part_dho, const float* __restrict__ dh,
-                                                           const float* __restrict__ hs,
-                                                           const float* __restrict__ hz, const float* __restrict__ whz,
-                                                           const float* __restrict__ wo, const float* __restrict__ Dp,
-                                                           float* __restrict__ dhs_out, float* __restrict__ r_out,
-                                                           float* __restrict__ wpart, Dims d) {
+// ---- gate backward on (C,64) tiles.  grid B, GT threads; weights in smem.  Per-batch weight-gradient partials ->
+//      wpart[b][...], layout of wpart[b]: dWo (C*C) | dWhz (2C*C) | dD (1)
+__global__ void __launch_bounds__(GT) hsm_gate_bwd_kernel(const float* __restrict__ part_dho, const float* __restrict__ dh,
+                                                          const float* __restrict__ hs,
+                                                          const float* __restrict__ hz, const float* __restrict__ whz,
+                                                          const float* __restrict__ wo, const float* __restrict__ Dp,
+                                                          float* __restrict__ dhs_out, float* __restrict__ r_out,
+                                                          float* __restrict__ wpart, Dims d) {
   extern __shared__ __align__(16) float smem[];
   const int C = d.C;
+  constexpr int CG = GT / 64;
   float* dho_s = smem;               // [C][64]
   float* v_s = dho_s + C * 64;       // [C][64]
   float* hs_s = v_s + C * 64;        // [C][64]
   float* dhz_s = hs_s + C * 64;      // [2C][64]
-  float* red_s = dhz_s + 2 * C * 64; // [256]
+  float* whz_s = dhz_s + 2 * C * 64; // [2C][C]
+  float* wo_s = whz_s + 2 * C * C;   // [C][C]
+  float* red_s = wo_s + C * C;       // [GT]
   const int tid = threadIdx.x, n = tid & 63, cg = tid >> 6, b = blockIdx.x;
   const float Dv = Dp[0];
-  for (int c = cg; c < C; c += 4) {
+  for (int i = tid; i < 2 * C * C; i += GT) whz_s[i] = whz[i];
+  for (int i = tid; i < C * C; i += GT) wo_s[i] = wo[i];
+  for (int c = cg; c < C; c += CG) {
     float a = 0.f;
     for (int t = 0; t < d.T; ++t) a += part_dho[(((size_t)b * d.T + t) * C + c) * 64 + n];
     if (dh) a += dh[((size_t)b * C + c) * 64 + n];
@@ -341,9 +371,9 @@ __global__ void __launch_bounds__(256) hsm_gate_bwd_kernel(const float* __restri
   }
   __syncthreads();
   float dD_local = 0.f;
-  for (int c = cg; c < C; c += 4) {
+  for (int c = cg; c < C; c += CG) {
     float dv = 0.f;
-    for (int dd = 0; dd < C; ++dd) dv = fmaf(__ldg(wo + (size_t)dd * C + c), dho_s[dd * 64 + n], dv);
+    for (int dd = 0; dd < C; ++dd) dv = fmaf(wo_s[dd * C + c], dho_s[dd * 64 + n], dv);
     float hh = hz[((size_t)b * 2 * C + c) * 64 + n], z = hz[((size_t)b * 2 * C + C + c) * 64 + n];
     dhz_s[c * 64 + n] = dv * (siluf_(z) + Dv);
     dhz_s[(C + c) * 64 + n] = dv * hh * silu_gradf_(z);
@@ -352,26 +382,30 @@ __global__ void __launch_bounds__(256) hsm_gate_bwd_kernel(const float* __restri
   red_s[tid] = dD_local;
   __syncthreads();
   float rn = 0.f;
-  for (int c = cg; c < C; c += 4) {
+  for (int c = cg; c < C; c += CG) {
     float a = 0.f;
-    for (int dd = 0; dd < 2 * C; ++dd) a = fmaf(__ldg(whz + (size_t)dd * C + c), dhz_s[dd * 64 + n], a);
+    for (int dd = 0; dd < 2 * C; ++dd) a = fmaf(whz_s[dd * C + c], dhz_s[dd * 64 + n], a);
     dhs_out[((size_t)b * C + c) * 64 + n] = a;
     rn = fmaf(a, hs_s[c * 64 + n], rn);
   }
-  // r[n] = sum_c dhs[c][n] hs[c][n]: four channel groups hold partial sums for the same n
-  __syncthreads();
+  // r[n] = sum_c dhs[c][n] hs[c][n]: the CG channel groups hold partial sums for the same n
   float dD_tot = 0.f;
   if (tid == 0) {
-    for (int i = 0; i < 256; ++i) dD_tot += red_s[i];
+    for (int i = 0; i < GT; ++i) dD_tot += red_s[i];
   }
   __syncthreads();
   red_s[tid] = rn;
   __syncthreads();
-  if (cg == 0) r_out[(size_t)b * 64 + n] = (red_s[n] + red_s[64 + n]) + (red_s[128 + n] + red_s[192 + n]);
+  if (cg == 0) {
+    float a = 0.f;
+#pragma unroll
+    for (int g = 0; g < CG; ++g) a += red_s[g * 64 + n];
+    r_out[(size_t)b * 64 + n] = a;
+  }
   float* wb = wpart + (size_t)b * (3 * C * C + 1);
   if (tid == 0) wb[3 * C * C] = dD_tot;
   // dWo[dd][c] = sum_n dho[dd][n] v[c][n] ; dWhz[dd][c] = sum_n dhz[dd][n] hs[c][n]
-  for (int i = tid; i < 3 * C * C; i += 256) {
+  for (int i = tid; i < 3 * C * C; i += GT) {
     const float *ar, *br;
     if (i < C * C) { ar = dho_s + (i / C) * 64; br = v_s + (i % C) * 64; }
     else { int k = i - C * C; ar = dhz_s + (k / C) * 64; br = hs_s + (k % C) * 64; }
@@ -385,13 +419,13 @@ __global__ void __launch_bounds__(256) hsm_gate_bwd_kernel(const float* __restri
 }
 
 // ---- dP = [dBm; dCm; ddt] and the direct part of dx.  thread = position.  grid (ceil(L/256), B).
-__global__ void __launch_bounds__(256) hsm_dp_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+template <int C>
+__global__ void __launch_bounds__(256, 2) hsm_dp_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                      const float* __restrict__ P, const float* __restrict__ stats,
                                                      const float* __restrict__ dhs, const float* __restrict__ ho,
                                                      const float* __restrict__ r, float* __restrict__ dP, float* __restrict__ dx,
                                                      Dims d) {
   extern __shared__ __align__(16) float smem[];
-  const int C = d.C;
   float* dhs_s = smem;            // [C][64]
   float* ho_s = dhs_s + C * 64;   // [C][64]
   float* m_s = ho_s + C * 64;     // [64] max, [64] 1/sum, [64] r
@@ -416,6 +450,7 @@ __global__ void __launch_bounds__(256) hsm_dp_kernel(const float* __restrict__ x
 #pragma unroll
   for (int nn = 0; nn < 64; ++nn) t[nn] = 0.f;
   // dG[n] = sum_c dhs[c][n] x[c]
+#pragma unroll 4
   for (int c = 0; c < C; ++c) {
     float xv = __ldg(xb + (size_t)c * d.L);
     const float4* g4 = reinterpret_cast<const float4*>(dhs_s + c * 64);
@@ -440,6 +475,7 @@ __global__ void __launch_bounds__(256) hsm_dp_kernel(const float* __restrict__ x
   }
   // direct dx[c] = sum_n dhs[c][n] A[n] Bm[n]
   float* dxb = dx + (size_t)b * C * d.L + l;
+#pragma unroll 4
   for (int c = 0; c < C; ++c) {
     const float4* g4 = reinterpret_cast<const float4*>(dhs_s + c * 64);
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -456,6 +492,7 @@ __global__ void __launch_bounds__(256) hsm_dp_kernel(const float* __restrict__ x
   // dCm[n] = sum_c ho[c][n] dy[c]
 #pragma unroll
   for (int nn = 0; nn < 64; ++nn) t[nn] = 0.f;
+#pragma unroll 4
   for (int c = 0; c < C; ++c) {
     float gv = __ldg(dyb + (size_t)c * d.L);
     const float4* h4 = reinterpret_cast<const float4*>(ho_s + c * 64);
@@ -473,21 +510,25 @@ __global__ void __launch_bounds__(256) hsm_dp_kernel(const float* __restrict__ x
 }
 
 // ---- projection / depthwise backward on a spatial tile.  grid (tiles, B), 256 threads = 8x32 interior positions.
-//      dQ = dw3x3^T(dP) ; dx += Wp^T dQ ; per-CTA partials of dWp[n][c] = sum dQ x and dWd[n][tap] = sum Q(l+tap) dP(l).
-//      partial layout per CTA: dWp (192*C) | dWd (192*9)
-constexpr int BN = 16;  // projected channels per pass
+//      dQ = dw3x3^T(dP) ; dx += Wp^T dQ ; per-CTA partials of dWp[n][c] = sum dQ x and dWd[n][tap] = sum Q(q) dP(q - tap)
+//      (Q only at the CTA's own pixels: every pixel q belongs to exactly one tile and dP is zero outside the image).
+//      partial layout per CTA: dWp (192*C) | dWd (192*9).  The x tile is staged once; the 192 channels go in passes of BN.
+constexpr int BN = 16;   // projected channels per pass
+constexpr int QP = 260;  // row pitch of the [channel][256 pixel] tiles
+template <int C>
 __global__ void __launch_bounds__(256) hsm_proj_dw_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wp,
                                                               const float* __restrict__ wd, const float* __restrict__ dP,
                                                               float* __restrict__ dx, float* __restrict__ partial, Dims d) {
+  constexpr int NSL = 256 / C;  // pixel slices of the dWp contraction (C blocks of 4x4 outputs x NSL slices = 256 threads)
+  constexpr int SL = C;         // pixels per slice
   extern __shared__ __align__(16) float smem[];
-  const int C = d.C;
   float* dp_s = smem;                 // [BN][NHALO]
-  float* q_s = dp_s + BN * NHALO;     // [BN][NHALO]
-  float* dq_s = q_s + BN * NHALO;     // [256][BN+1]
-  float* x_s = dq_s + 256 * (BN + 1); // [C][256]
-  float* wp_s = x_s + C * 256;        // [C][BN]  (c-major for the Q recompute)
+  float* q_s = dp_s + BN * NHALO;     // [BN][QP]
+  float* dq_s = q_s + BN * QP;        // [BN][QP]
+  float* x_s = dq_s + BN * QP;        // [C][QP]
+  float* wp_s = x_s + C * QP;         // [C][BN]  (c-major for the Q recompute)
   float* wpt_s = wp_s + C * BN;       // [BN][C]  (n-major for dx)
-  float* wd_s = wpt_s + BN * C;       // [BN][9]
+  float* wd_s = wpt_s + BN * C;       // [BN][12]
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int ty0 = (blockIdx.x / d.tiles_x) * TH, tx0 = (blockIdx.x % d.tiles_x) * TW;
   const int b = blockIdx.y;
@@ -495,11 +536,12 @@ __global__ void __launch_bounds__(256) hsm_proj_dw_bwd_kernel(const float* __res
   const int gy = ty0 + ly, gx = tx0 + lx;
   const bool inside = gy < d.H && gx < d.H;
   const float* xb = x + (size_t)b * C * d.L;
-  for (int c = 0; c < C; ++c) x_s[c * 256 + tid] = inside ? __ldg(xb + (size_t)c * d.L + (size_t)gy * d.H + gx) : 0.f;
+#pragma unroll 4
+  for (int c = 0; c < C; ++c) x_s[c * QP + tid] = inside ? __ldg(xb + (size_t)c * d.L + (size_t)gy * d.H + gx) : 0.f;
   float* pb = partial + ((size_t)b * gridDim.x + blockIdx.x) * (size_t)(N3 * C + N3 * 9);
-  float dxa[64];
+  float dxa[C];
 #pragma unroll
-  for (int c = 0; c < 64; ++c) dxa[c] = 0.f;
+  for (int c = 0; c < C; ++c) dxa[c] = 0.f;
 
   for (int n0 = 0; n0 < N3; n0 += BN) {
     __syncthreads();
@@ -509,7 +551,7 @@ __global__ void __launch_bounds__(256) hsm_proj_dw_bwd_kernel(const float* __res
       wp_s[i] = w;
       wpt_s[nn * C + c] = w;
     }
-    for (int i = tid; i < BN * 9; i += 256) wd_s[i] = wd[(size_t)n0 * 9 + i];
+    for (int i = tid; i < BN * 9; i += 256) wd_s[(i / 9) * 12 + (i % 9)] = wd[(size_t)n0 * 9 + i];
     // dP tile with halo (zero outside the image)
     for (int i = tid; i < BN * NHALO; i += 256) {
       int nn = i / NHALO, pos = i - nn * NHALO;
@@ -519,90 +561,118 @@ __global__ void __launch_bounds__(256) hsm_proj_dw_bwd_kernel(const float* __res
                     ? __ldg(dP + ((size_t)b * N3 + n0 + nn) * d.L + (size_t)yy * d.H + xx) : 0.f;
     }
     __syncthreads();
-    // Q on the halo (recomputed projection)
-    for (int pos = tid; pos < NHALO; pos += 256) {
-      int hy = pos / HW_, hx = pos - hy * HW_;
-      int yy = ty0 + hy - 1, xx = tx0 + hx - 1;
+    {
+      // Q at the thread's own pixel (0 outside the image because x_s is 0 there)
       float q[BN];
 #pragma unroll
       for (int i = 0; i < BN; ++i) q[i] = 0.f;
-      if (yy >= 0 && yy < d.H && xx >= 0 && xx < d.H) {
-        const float* xp = xb + (size_t)yy * d.H + xx;
-        for (int c = 0; c < C; ++c) {
-          float xv = __ldg(xp + (size_t)c * d.L);
-          const float4* w4 = reinterpret_cast<const float4*>(wp_s + c * BN);
+#pragma unroll 8
+      for (int c = 0; c < C; ++c) {
+        float xv = x_s[c * QP + tid];
+        const float4* w4 = reinterpret_cast<const float4*>(wp_s + c * BN);
 #pragma unroll
-          for (int i = 0; i < BN / 4; ++i) {
-            float4 w = w4[i];
-            q[4 * i + 0] = fmaf(xv, w.x, q[4 * i + 0]);
-            q[4 * i + 1] = fmaf(xv, w.y, q[4 * i + 1]);
-            q[4 * i + 2] = fmaf(xv, w.z, q[4 * i + 2]);
-            q[4 * i + 3] = fmaf(xv, w.w, q[4 * i + 3]);
-          }
+        for (int i = 0; i < BN / 4; ++i) {
+          float4 w = w4[i];
+          q[4 * i + 0] = fmaf(xv, w.x, q[4 * i + 0]);
+          q[4 * i + 1] = fmaf(xv, w.y, q[4 * i + 1]);
+          q[4 * i + 2] = fmaf(xv, w.z, q[4 * i + 2]);
+          q[4 * i + 3] = fmaf(xv, w.w, q[4 * i + 3]);
         }
       }
 #pragma unroll
-      for (int i = 0; i < BN; ++i) q_s[i * NHALO + pos] = q[i];
-    }
-    // dQ at the interior position (transposed depthwise conv) and dx accumulation
-    {
-      float dq[BN];
+      for (int nn = 0; nn < BN; ++nn) q_s[nn * QP + tid] = q[nn];
+      // dQ at the thread's pixel (transposed depthwise conv) and the dx accumulation
 #pragma unroll
       for (int nn = 0; nn < BN; ++nn) {
-        const float* w = wd_s + nn * 9;
+        const float4 wa = *reinterpret_cast<const float4*>(wd_s + nn * 12);
+        const float4 wb = *reinterpret_cast<const float4*>(wd_s + nn * 12 + 4);
+        const float w8 = wd_s[nn * 12 + 8];
         const float* g = dp_s + nn * NHALO + (ly + 2) * HW_ + (lx + 2);
-        float s = w[0] * g[0] + w[1] * g[-1] + w[2] * g[-2];
-        s += w[3] * g[-HW_] + w[4] * g[-HW_ - 1] + w[5] * g[-HW_ - 2];
-        s += w[6] * g[-2 * HW_] + w[7] * g[-2 * HW_ - 1] + w[8] * g[-2 * HW_ - 2];
-        dq[nn] = inside ? s : 0.f;
-        dq_s[tid * (BN + 1) + nn] = dq[nn];
-      }
+        float sacc = wa.x * g[0] + wa.y * g[-1] + wa.z * g[-2];
+        sacc += wa.w * g[-HW_] + wb.x * g[-HW_ - 1] + wb.y * g[-HW_ - 2];
+        sacc += wb.z * g[-2 * HW_] + wb.w * g[-2 * HW_ - 1] + w8 * g[-2 * HW_ - 2];
+        const float dq = inside ? sacc : 0.f;
+        dq_s[nn * QP + tid] = dq;
+        const float4* wr = reinterpret_cast<const float4*>(wpt_s + nn * C);
 #pragma unroll
-      for (int nn = 0; nn < BN; ++nn) {
-        const float* wr = wpt_s + nn * C;
-#pragma unroll
-        for (int c = 0; c < 64; ++c)
-          if (c < C) dxa[c] = fmaf(wr[c], dq[nn], dxa[c]);
+        for (int c4 = 0; c4 < C / 4; ++c4) {
+          float4 w = wr[c4];
+          dxa[4 * c4 + 0] = fmaf(w.x, dq, dxa[4 * c4 + 0]);
+          dxa[4 * c4 + 1] = fmaf(w.y, dq, dxa[4 * c4 + 1]);
+          dxa[4 * c4 + 2] = fmaf(w.z, dq, dxa[4 * c4 + 2]);
+          dxa[4 * c4 + 3] = fmaf(w.w, dq, dxa[4 * c4 + 3]);
+        }
       }
     }
     __syncthreads();
-    // dWp partial: thread owns projected channel nn = tid % BN, input channels c = tid / BN + 16 k
+    // dWp partial: thread = (4x4 block of (n,c) outputs, pixel slice); slices of one block sit in adjacent lanes
     {
-      const int nn = tid % BN, c0 = tid / BN;  // c0 in [0,16)
-      for (int c = c0; c < C; c += 256 / BN) {
-        float a = 0.f;
-        const float* xr = x_s + c * 256;
-        for (int p = 0; p < 256; ++p) a = fmaf(dq_s[p * (BN + 1) + nn], xr[p], a);
-        pb[(size_t)(n0 + nn) * C + c] = a;
+      const int sl = tid % NSL, blk = tid / NSL;
+      const int i4 = (blk & 3) * 4, j4 = (blk >> 2) * 4;
+      float acc[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) acc[r][t] = 0.f;
+#pragma unroll 2
+      for (int k = 0; k < SL; k += 4) {
+        const int px = sl * SL + k;
+        float4 av[4], bv[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          av[r] = *reinterpret_cast<const float4*>(dq_s + (i4 + r) * QP + px);
+          bv[r] = *reinterpret_cast<const float4*>(x_s + (j4 + r) * QP + px);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            acc[r][t] = fmaf(av[r].x, bv[t].x, fmaf(av[r].y, bv[t].y, fmaf(av[r].z, bv[t].z, fmaf(av[r].w, bv[t].w, acc[r][t]))));
       }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float v = acc[r][t];
+#pragma unroll
+          for (int o = NSL / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (sl == 0) pb[(size_t)(n0 + i4 + r) * C + j4 + t] = v;
+        }
     }
-    // dWd partial: warp handles channels nn = wid*2, wid*2+1; lanes stride the 256 interior positions
+    // dWd partial: warp handles channels 2*wid, 2*wid+1; lane = tile column, sliding 3x3 window of dP down the 8 rows
     for (int j = 0; j < BN / 8; ++j) {
       const int nn = wid * (BN / 8) + j;
       float a[9];
 #pragma unroll
       for (int tp = 0; tp < 9; ++tp) a[tp] = 0.f;
-      for (int p = lane; p < 256; p += 32) {
-        int py = p >> 5, px = p & 31;
-        float g = dp_s[nn * NHALO + (py + 1) * HW_ + (px + 1)];
-        const float* qr = q_s + nn * NHALO + py * HW_ + px;
+      // window rows r0 (halo row qy), r1 (qy+1), r2 (qy+2); columns lane, lane+1, lane+2
+      const float* gp = dp_s + nn * NHALO + lane;
+      float r0[3], r1[3], r2[3];
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
+      for (int cc = 0; cc < 3; ++cc) { r0[cc] = gp[cc]; r1[cc] = gp[HW_ + cc]; }
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) a[ky * 3 + kx] = fmaf(qr[ky * HW_ + kx], g, a[ky * 3 + kx]);
+      for (int qy = 0; qy < TH; ++qy) {
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) r2[cc] = gp[(qy + 2) * HW_ + cc];
+        const float qv = q_s[nn * QP + qy * 32 + lane];
+        // tap (ky,kx) pairs with dP at halo (qy + 2 - ky, lane + 2 - kx)
+        a[0] = fmaf(qv, r2[2], a[0]); a[1] = fmaf(qv, r2[1], a[1]); a[2] = fmaf(qv, r2[0], a[2]);
+        a[3] = fmaf(qv, r1[2], a[3]); a[4] = fmaf(qv, r1[1], a[4]); a[5] = fmaf(qv, r1[0], a[5]);
+        a[6] = fmaf(qv, r0[2], a[6]); a[7] = fmaf(qv, r0[1], a[7]); a[8] = fmaf(qv, r0[0], a[8]);
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) { r0[cc] = r1[cc]; r1[cc] = r2[cc]; }
       }
 #pragma unroll
       for (int tp = 0; tp < 9; ++tp) {
-        float s = warp_sum(a[tp]);
-        if (lane == 0) pb[(size_t)N3 * C + (size_t)(n0 + nn) * 9 + tp] = s;
+        float sacc = warp_sum(a[tp]);
+        if (lane == 0) pb[(size_t)N3 * C + (size_t)(n0 + nn) * 9 + tp] = sacc;
       }
     }
   }
   if (inside) {
     float* dxb = dx + (size_t)b * C * d.L + (size_t)gy * d.H + gx;
 #pragma unroll
-    for (int c = 0; c < 64; ++c)
-      if (c < C) dxb[(size_t)c * d.L] += dxa[c];
+    for (int c = 0; c < C; ++c) dxb[(size_t)c * d.L] += dxa[c];
   }
 }
 
@@ -698,7 +768,8 @@ static int check(const kmu_hsmssd_desc* d, const char* who) {
   KMU_REQUIRE(d->H * d->H == d->L, KMU_ERR_BAD_ARG, "%s: L=%d is not H*H with H=%d (the reference requires square maps)", who,
               d->L, d->H);
   KMU_REQUIRE(d->N == N, KMU_ERR_UNSUPPORTED, "%s: state_dim %d != 64", who, d->N);
-  KMU_REQUIRE(d->C <= 64 && d->C % 4 == 0, KMU_ERR_UNSUPPORTED, "%s: C=%d must be a multiple of 4 and <= 64", who, d->C);
+  KMU_REQUIRE(d->C == 16 || d->C == 32 || d->C == 64, KMU_ERR_UNSUPPORTED, "%s: C=%d not in {16,32,64} (the widths KM-UNet uses)", who,
+              d->C);
   KMU_REQUIRE(d->B <= 65535, KMU_ERR_UNSUPPORTED, "%s: B=%d > 65535", who, d->B);
   return KMU_OK;
 }
@@ -765,10 +836,19 @@ int kmu_hsmssd_fwd(const kmu_hsmssd_fwd_args* a, kmu_stream stream) {
   float* part_s = (float*)(ws + w.part_s);
   float* part_hs = (float*)(ws + w.part_hs);
   {
-    constexpr int NCH = 32;
-    size_t smem = ((size_t)NCH * NHALO + (size_t)d.C * NCH + NCH * 9) * 4;
-    opt_in_smem(hsm_proj_dw_kernel<NCH>, smem);
-    hsm_proj_dw_kernel<NCH><<<dim3(d.tiles_x * d.tiles_y, d.B, N3 / NCH), 256, smem, st>>>(a->x, a->w_bcdt, a->w_dw, a->P, d);
+    size_t smem = ((size_t)d.C * NHALO + (size_t)PCH * NHALO + (size_t)d.C * PCH + PCH * 12) * 4;
+    dim3 grid(d.tiles_x * d.tiles_y, d.B);
+#define KMU_HSM_PROJ(CC)                                                                     \
+  do {                                                                                       \
+    opt_in_smem(hsm_proj_dw_kernel<CC>, smem);                                               \
+    hsm_proj_dw_kernel<CC><<<grid, 256, smem, st>>>(a->x, a->w_bcdt, a->w_dw, a->P, d);      \
+  } while (0)
+    switch (d.C) {
+      case 16: KMU_HSM_PROJ(16); break;
+      case 32: KMU_HSM_PROJ(32); break;
+      default: KMU_HSM_PROJ(64); break;
+    }
+#undef KMU_HSM_PROJ
     KMU_LAUNCH_CHECK("hsm_proj_dw");
   }
   {
@@ -787,9 +867,10 @@ int kmu_hsmssd_fwd(const kmu_hsmssd_fwd_args* a, kmu_stream stream) {
     KMU_LAUNCH_CHECK("hsm_softmax_hs");
   }
   {
-    size_t smem = (size_t)4 * d.C * 64 * 4;
+    size_t smem = ((size_t)4 * d.C * 64 + (size_t)3 * d.C * d.C + (size_t)d.T * 64) * 4;
+    KMU_REQUIRE(smem <= 220 * 1024, KMU_ERR_UNSUPPORTED, "hsmssd_fwd: L=%d too long for the per-batch combine (T=%d)", d.L, d.T);
     opt_in_smem(hsm_combine_gate_kernel, smem);
-    hsm_combine_gate_kernel<<<d.B, 256, smem, st>>>(part_m, part_s, part_hs, a->w_hz, a->w_out, a->D, a->stats, a->hs, a->hz,
+    hsm_combine_gate_kernel<<<d.B, GT, smem, st>>>(part_m, part_s, part_hs, a->w_hz, a->w_out, a->D, a->stats, a->hs, a->hz,
                                                     a->h, d);
     KMU_LAUNCH_CHECK("hsm_combine_gate");
   }
@@ -838,9 +919,9 @@ int kmu_hsmssd_bwd(const kmu_hsmssd_bwd_args* a, kmu_stream stream) {
     KMU_LAUNCH_CHECK("hsm_contract");
   }
   {
-    size_t smem = ((size_t)5 * C * 64 + 256) * 4;
+    size_t smem = ((size_t)5 * C * 64 + (size_t)3 * C * C + GT) * 4;
     opt_in_smem(hsm_gate_bwd_kernel, smem);
-    hsm_gate_bwd_kernel<<<d.B, 256, smem, st>>>(part_dho, a->dh, a->hs, a->hz, a->w_hz, a->w_out, a->D, dhs, r, wpart, d);
+    hsm_gate_bwd_kernel<<<d.B, GT, smem, st>>>(part_dho, a->dh, a->hs, a->hz, a->w_hz, a->w_out, a->D, dhs, r, wpart, d);
     KMU_LAUNCH_CHECK("hsm_gate_bwd");
     int n = 3 * C * C + 1;
     hsm_wgrad_reduce_kernel<<<cdiv(n, 128), 128, 0, st>>>(wpart, d.B, n, a->d_w_out, C * C, a->d_w_hz, 2 * C * C, a->d_D, 1);
@@ -848,15 +929,35 @@ int kmu_hsmssd_bwd(const kmu_hsmssd_bwd_args* a, kmu_stream stream) {
   }
   {
     size_t smem = ((size_t)2 * C * 64 + 192) * 4;
-    opt_in_smem(hsm_dp_kernel, smem);
-    hsm_dp_kernel<<<dim3(cdiv(d.L, 256), d.B), 256, smem, st>>>(a->x, a->dy, a->P, a->stats, dhs, a->h, r, dP, a->dx, d);
+    dim3 grid(cdiv(d.L, 256), d.B);
+#define KMU_HSM_DP(CC)                                                                                              \
+  do {                                                                                                              \
+    opt_in_smem(hsm_dp_kernel<CC>, smem);                                                                           \
+    hsm_dp_kernel<CC><<<grid, 256, smem, st>>>(a->x, a->dy, a->P, a->stats, dhs, a->h, r, dP, a->dx, d);             \
+  } while (0)
+    switch (C) {
+      case 16: KMU_HSM_DP(16); break;
+      case 32: KMU_HSM_DP(32); break;
+      default: KMU_HSM_DP(64); break;
+    }
+#undef KMU_HSM_DP
     KMU_LAUNCH_CHECK("hsm_dp");
   }
   {
-    size_t smem = ((size_t)2 * BN * NHALO + 256 * (BN + 1) + (size_t)C * 256 + 2 * (size_t)C * BN + BN * 9) * 4;
-    opt_in_smem(hsm_proj_dw_bwd_kernel, smem);
+    size_t smem = ((size_t)BN * NHALO + 2 * (size_t)BN * QP + (size_t)C * QP + 2 * (size_t)C * BN + BN * 12) * 4;
     int tiles = d.tiles_x * d.tiles_y;
-    hsm_proj_dw_bwd_kernel<<<dim3(tiles, d.B), 256, smem, st>>>(a->x, a->w_bcdt, a->w_dw, dP, a->dx, tpart, d);
+    dim3 grid(tiles, d.B);
+#define KMU_HSM_PBWD(CC)                                                                                            \
+  do {                                                                                                              \
+    opt_in_smem(hsm_proj_dw_bwd_kernel<CC>, smem);                                                                  \
+    hsm_proj_dw_bwd_kernel<CC><<<grid, 256, smem, st>>>(a->x, a->w_bcdt, a->w_dw, dP, a->dx, tpart, d);              \
+  } while (0)
+    switch (C) {
+      case 16: KMU_HSM_PBWD(16); break;
+      case 32: KMU_HSM_PBWD(32); break;
+      default: KMU_HSM_PBWD(64); break;
+    }
+#undef KMU_HSM_PBWD
     KMU_LAUNCH_CHECK("hsm_proj_dw_bwd");
     int per = N3 * C + N3 * 9;
     hsm_wgrad_reduce_kernel<<<cdiv(per, 128), 128, 0, st>>>(tpart, tiles * d.B, per, a->d_w_bcdt, N3 * C, a->d_w_dw, N3 * 9,
