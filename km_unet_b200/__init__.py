@@ -24,7 +24,11 @@ def enable_dropin():
 
 def __getattr__(name):
     if name in ("KANConv2d", "KANLinear", "KAN_Convolutional_Layer", "EfficientViMBlock", "HSMSSD", "LayerNorm1D", "DySample",
-                "DAGEM"):
+                "DAGEM", "KM_UNetV3", "KM_UNetV3_SH", "KM_UNetV3_LAPS", "StableHybridKANConv", "EnhancedViMBlock",
+                "IntelligentWaveletPoolingModule", "modules"):
+        if name == "modules":
+            import importlib
+            return importlib.import_module(".modules", __name__)
         from . import modules
         return getattr(modules, name)
     raise AttributeError(name)

@@ -1,0 +1,262 @@
+"""Host-side mirror of the callers of the hot path: KM_UNetV3 (SH and LAPS variants) and the glue blocks around the
+CUDA-backed operators, with the reference's module tree so a reference state_dict loads unchanged.
+
+Reference: KM_UNetV3_SH.py:21-94 (StableHybridKANConv), :97-151 (EnhancedViMBlock), :154-212 (DirectionViM), :215-263
+(DirectionAttention), :266-284 (TripleNorm), :287-332 (MultiScaleFusion / ChannelAttention), :336-368
+(LocalContrastAttention), :371-517 (KM_UNetV3); KM_UNetV3_LAPS.py:411-437,483 (plain bilinear upsampling, no bridge);
+WPL/iwp.py:9-132 (Haar wavelet pooling).  This file exists because the reference tree cannot travel to the GPU box: the
+benchmark of the full training step (BASELINE configs[2..4]) needs the caller.  With the reference tree present,
+`km_unet_b200.enable_dropin()` + the reference's own KM_UNetV3_SH.py gives the same network.
+
+Differences that are deliberate: no self-imposed fp16 autocast (the reference decorates forward with
+torch.cuda.amp.autocast; here the KAN convolutions pick their precision from km_unet_b200.config and the rest runs in
+fp32), the dead parameters of the reference (StableHybridKANConv.branches / .attn, DirectionViM.dt_proj,
+IWP.high_freq_conv) are kept for checkpoint compatibility but never executed, and the wavelet pooling does not rebuild
+numpy matrices and upload them on every call.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .dagem import DAGEM
+from .dysample import DySample
+from .kan import KANConv2d
+from .vim import EfficientViMBlock
+
+
+class DropPath(nn.Module):
+    """timm 0.9.16 DropPath: per-sample bernoulli(keep) / keep in training, identity otherwise."""
+
+    def __init__(self, drop_prob=0.0, scale_by_keep=True):
+        super().__init__()
+        self.drop_prob, self.scale_by_keep = drop_prob, scale_by_keep
+
+    def forward(self, x):
+        if self.drop_prob == 0.0 or not self.training:
+            return x
+        keep = 1.0 - self.drop_prob
+        mask = x.new_empty((x.shape[0],) + (1,) * (x.ndim - 1)).bernoulli_(keep)
+        if keep > 0.0 and self.scale_by_keep:
+            mask.div_(keep)
+        return x * mask
+
+
+class StableHybridKANConv(nn.Module):
+    """ReLU(residual(GN4(x)) + KANConv2d(GN4(x)))."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=1):
+        super().__init__()
+        self.branches = nn.ModuleDict({'plain': KANConv2d(in_channels, out_channels, kernel_size, padding=padding)})  # dead
+        self.kanconv2d = nn.Sequential(KANConv2d(in_channels, out_channels, kernel_size, padding=padding))
+        self.attn = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Conv2d(in_channels, 1, 1), nn.Softmax(dim=1))          # dead
+        self.pre_norm = nn.GroupNorm(4, in_channels)
+        self.post_act = nn.ReLU(inplace=True)
+        self.residual = nn.Conv2d(in_channels, out_channels, 1) if in_channels != out_channels else nn.Identity()
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode='fan_out')
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+
+    def forward(self, x):
+        x = self.pre_norm(x)
+        return self.post_act(self.residual(x) + self.kanconv2d(x))
+
+
+class DirectionAttention(nn.Module):
+    """dwconv3x3(sigmoid(q k) v) scaled by a squeeze-excite weight of the globally pooled input."""
+
+    def __init__(self, dim, mode):
+        super().__init__()
+        self.mode = mode
+        self.qkv = nn.Conv2d(dim, dim * 3, 1)
+        self.conv = nn.Conv2d(dim, dim, 3, padding=1, groups=dim)
+        self.fc = nn.Sequential(nn.Linear(dim, dim // 4), nn.GELU(), nn.Linear(dim // 4, dim), nn.Sigmoid())
+
+    def forward(self, x):
+        # the three pooling modes of the reference (mean over W then H, over H then W, or both) are the same global mean
+        weight = self.fc(x.mean(dim=(2, 3)))
+        q, k, v = self.qkv(x).chunk(3, dim=1)
+        return self.conv(torch.sigmoid(q * k) * v) * weight[:, :, None, None]
+
+
+class DirectionViM(nn.Module):
+    def __init__(self, dim, mode='height', state_dim=64):
+        super().__init__()
+        self.mode, self.state_dim = mode, state_dim
+        self.dt_proj = nn.Linear(dim, state_dim)                                                                     # dead
+        self.vit_mamba = EfficientViMBlock(dim=dim, mlp_ratio=4, ssd_expand=1, state_dim=64)
+        if mode == 'height':
+            self.proj = nn.Conv2d(dim, dim, (3, 1), padding=(1, 0))
+        elif mode == 'width':
+            self.proj = nn.Conv2d(dim, dim, (1, 3), padding=(0, 1))
+        else:
+            self.proj = nn.Conv2d(dim, dim, 1)
+        self.attn = DirectionAttention(dim, mode)
+
+    def forward(self, x):
+        return self.attn(self.vit_mamba(self.proj(x)))
+
+
+class TripleNorm(nn.Module):
+    """(GN1(x; h) + GN1(x; w) + LayerNorm_C(x)) / 3 -- GroupNorm(1) statistics do not see the H/W permutation."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.norm_h = nn.GroupNorm(num_groups=1, num_channels=dim)
+        self.norm_w = nn.GroupNorm(num_groups=1, num_channels=dim)
+        self.norm_c = nn.LayerNorm(dim)
+
+    def forward(self, x):
+        c = self.norm_c(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+        return (self.norm_h(x) + self.norm_w(x) + c) / 3
+
+
+class EnhancedViMBlock(nn.Module):
+    def __init__(self, dim, expansion=4, state_dim=64, drop_path=0.1):
+        super().__init__()
+        self.dim, self.state_dim = dim, state_dim
+        self.height_block = DirectionViM(dim, mode='height', state_dim=state_dim)
+        self.width_block = DirectionViM(dim, mode='width', state_dim=state_dim)
+        self.channel_block = DirectionViM(dim, mode='channel', state_dim=state_dim)
+        self.fusion_gate = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Conv2d(dim * 3, dim // 4, 1), nn.GELU(),
+                                         nn.Conv2d(dim // 4, 3, 1), nn.Softmax(dim=1))
+        self.ffn = nn.Sequential(nn.Conv2d(dim, dim * expansion, 1), nn.GELU(), nn.Conv2d(dim * expansion, dim, 1))
+        self.norm = TripleNorm(dim)
+        self.drop_path = DropPath(drop_path) if drop_path > 0 else nn.Identity()
+
+    def forward(self, x):
+        feats = [self.height_block(x), self.width_block(x), self.channel_block(x)]
+        g = self.fusion_gate(torch.cat(feats, dim=1))
+        x = x + self.drop_path(g[:, 0:1] * feats[0] + g[:, 1:2] * feats[1] + g[:, 2:3] * feats[2])
+        return x + self.drop_path(self.ffn(self.norm(x)))
+
+
+class ChannelAttention(nn.Module):
+    def __init__(self, channel, reduction=8):
+        super().__init__()
+        self.gap = nn.AdaptiveAvgPool2d(1)
+        self.fc = nn.Sequential(nn.Linear(channel, channel // reduction), nn.SiLU(), nn.Linear(channel // reduction, channel),
+                                nn.Sigmoid())
+
+    def forward(self, x):
+        return x * self.fc(x.mean(dim=(2, 3)))[:, :, None, None]
+
+
+class MultiScaleFusion(nn.Module):
+    def __init__(self, channels, reduction=4):
+        super().__init__()
+        out = channels[-1]
+        self.blocks = nn.ModuleList([nn.Sequential(nn.Conv2d(c, out, s, padding=s // 2, stride=1), nn.GroupNorm(1, out), nn.SiLU())
+                                     for c, s in zip(channels, [3, 5, 7])])
+        self.fusion = nn.Sequential(nn.Conv2d(out * 3, out, 1), nn.Conv2d(out, out, 3, padding=1), ChannelAttention(out, reduction))
+
+    def forward(self, features):
+        return self.fusion(torch.cat([blk(f) for blk, f in zip(self.blocks, features)], dim=1))
+
+
+class LocalContrastAttention(nn.Module):
+    def __init__(self, in_channels, reduction_ratio=4):
+        super().__init__()
+        self.reduction_ratio = reduction_ratio
+        self.fc = nn.Sequential(nn.Linear(in_channels // reduction_ratio, 64), nn.ReLU(), nn.Linear(64, in_channels), nn.Sigmoid())
+
+    def forward(self, x):
+        avg = x.mean(dim=(2, 3))
+        g = self.fc(avg.view(avg.size(0), -1, self.reduction_ratio).mean(-1))[:, :, None, None]
+        return x * (1 - g) + g
+
+
+class _NoParams(nn.Module):
+    """Placeholder for the reference's parameter-free DWT_2D child (keeps the module tree / state_dict identical)."""
+
+
+class IntelligentWaveletPoolingModule(nn.Module):
+    """Haar 2x2 analysis + 1x1 fusion (WPL/iwp.py:116-132).  With s = 1/sqrt(2) taps the four sub-bands of a 2x2 block
+    [[a,b],[c,d]] are LL=(a+b+c+d)/2, LH=(a-b+c-d)/2, HL=(a+b-c-d)/2, HH=(a-b-c+d)/2; the reference's get_matrix leaves
+    the LAST high-pass row and column zero (:79-82) and its Softmax2d over a one-channel map is identically 1, so the output
+    is fusion_conv(cat[LL, mean_c(LH, HL, HH)])."""
+
+    def __init__(self, in_channels, wavename='haar'):
+        super().__init__()
+        if wavename != 'haar':
+            raise NotImplementedError("only the Haar wavelet (the one KM-UNet uses) is implemented")
+        self.dwt = _NoParams()
+        self.high_freq_conv = nn.Conv2d(3 * in_channels, 1, kernel_size=(1, 1))                                      # inert
+        self.softmax = nn.Softmax2d()
+        self.fusion_conv = nn.Conv2d(in_channels + 1, in_channels, kernel_size=(1, 1))
+
+    def forward(self, x):
+        B, C, H, W = x.shape
+        if H != W or H % 2:
+            raise RuntimeError("IntelligentWaveletPoolingModule: square, even-sized maps only (as in KM-UNet)")
+        a, b = x[:, :, 0::2, 0::2], x[:, :, 0::2, 1::2]
+        c, d = x[:, :, 1::2, 0::2], x[:, :, 1::2, 1::2]
+        ll = (a + b + c + d) * 0.5
+        lh = (a - b + c - d) * 0.5
+        hl = (a + b - c - d) * 0.5
+        hh = (a - b - c + d) * 0.5
+        row = torch.ones(H // 2, 1, device=x.device, dtype=x.dtype)
+        row[-1] = 0
+        col = torch.ones(1, W // 2, device=x.device, dtype=x.dtype)
+        col[:, -1] = 0
+        high = (lh * col + hl * row + hh * (row * col)).sum(dim=1, keepdim=True) / (3 * C)
+        return self.fusion_conv(torch.cat([ll, high], dim=1))
+
+
+class KM_UNetV3(nn.Module):
+    """variant='SH': DAGEM bridge + DySample decoders (KM_UNetV3_SH.py:371-517); variant='LAPS': no bridge, bilinear
+    align_corners upsampling (KM_UNetV3_LAPS.py:411-437,483)."""
+
+    def __init__(self, num_classes=3, embed_dims=(16, 32, 64), variant='SH'):
+        super().__init__()
+        if variant not in ('SH', 'LAPS'):
+            raise ValueError(variant)
+        self.variant = variant
+        e0, e1, e2 = embed_dims
+        self.conv_f = nn.Conv2d(5, 16, kernel_size=3, padding=1, stride=1)
+        self.lca1, self.lca2, self.lca3 = (LocalContrastAttention(e) for e in (e0, e1, e2))
+        self.enc1 = nn.Sequential(StableHybridKANConv(16, e0), EnhancedViMBlock(e0, state_dim=16), IntelligentWaveletPoolingModule(e0))
+        self.enc2 = nn.Sequential(StableHybridKANConv(e0, e1), EnhancedViMBlock(e1, state_dim=16), IntelligentWaveletPoolingModule(e1))
+        self.enc3 = nn.Sequential(StableHybridKANConv(e1, e2), EnhancedViMBlock(e2, state_dim=16), IntelligentWaveletPoolingModule(e2))
+
+        def up():
+            return DySample(e2, scale=2, style='lp') if variant == 'SH' else nn.Upsample(scale_factor=2, mode='bilinear',
+                                                                                         align_corners=True)
+        if variant == 'SH':
+            self.bridge_attention = DAGEM(sync_bn=False, input_channels=e2)
+        self.dec1 = nn.Sequential(up(), StableHybridKANConv(e2, e1))
+        self.attention1 = nn.Sequential(MultiScaleFusion([e0, e1, e1]))
+        self.attention2 = nn.Sequential(MultiScaleFusion([e0, e1, e1]))
+        self.dec2 = nn.Sequential(up(), nn.Conv2d(e1 * 2, e1, kernel_size=3, padding=1, stride=1), EnhancedViMBlock(e1, state_dim=16))
+        self.dec3 = nn.Sequential(up(), nn.Conv2d(e1 * 2, e0, 3, padding=1), EnhancedViMBlock(e0),
+                                  nn.Conv2d(e0, num_classes, 3, padding=1))
+        self.output_norm = nn.GroupNorm(1, num_classes)
+        self.activation = nn.Sigmoid()
+
+    @staticmethod
+    def _skips(e1, e2, size):
+        r1 = F.interpolate(e1, size=size, mode='bilinear', align_corners=True)
+        r2 = F.interpolate(e2, size=size, mode='bilinear', align_corners=True)
+        return [r1, r2, r2]            # the reference feeds e2 twice (KM_UNetV3_SH.py:495)
+
+    def forward(self, x):
+        x = self.conv_f(x)
+        e1 = self.lca1(self.enc1(x))
+        e2 = self.lca2(self.enc2(e1))
+        e3 = self.lca3(self.enc3(e2))
+        if self.variant == 'SH':
+            e3 = self.bridge_attention(e3)
+        d1 = self.dec1(e3)
+        d1 = torch.cat([d1, self.attention1(self._skips(e1, e2, d1.shape[2:]))], dim=1)
+        d2 = self.dec2(d1)
+        d2 = torch.cat([d2, self.attention2(self._skips(e1, e2, d2.shape[2:]))], dim=1)
+        return self.activation(self.output_norm(self.dec3(d2)))
+
+
+def KM_UNetV3_SH(num_classes=3, embed_dims=(16, 32, 64)):
+    return KM_UNetV3(num_classes, embed_dims, 'SH')
+
+
+def KM_UNetV3_LAPS(num_classes=3, embed_dims=(16, 32, 64)):
+    return KM_UNetV3(num_classes, embed_dims, 'LAPS')

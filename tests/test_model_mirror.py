@@ -1,0 +1,82 @@
+"""CPU checks of the host-side model mirror (km_unet_b200/modules/km_unet.py): the module tree must carry exactly the
+reference's state_dict (keys + shapes, pinned by the golden full-model fixture generated from the unmodified reference),
+and the torch-only glue blocks must match the reference modules when the reference tree is present."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, Golden, rel_err
+
+
+def test_state_dict_layout_matches_reference_fixture():
+    from km_unet_b200 import KM_UNetV3_SH
+    g = Golden("km_unetv3_sh_eval_32")
+    want = g.sd()
+    m = KM_UNetV3_SH(num_classes=4)
+    have = m.state_dict()
+    assert set(have.keys()) == set(want.keys())
+    for k, v in want.items():
+        assert tuple(have[k].shape) == tuple(v.shape), k
+    m.load_state_dict(want)       # strict
+
+
+def test_laps_variant_has_no_bridge_and_no_dysample():
+    from km_unet_b200 import KM_UNetV3_LAPS
+    m = KM_UNetV3_LAPS(num_classes=3)
+    keys = m.state_dict().keys()
+    assert not any(k.startswith("bridge_attention") for k in keys)
+    assert not any(k.startswith("dec1.0.") or k.startswith("dec2.0.") or k.startswith("dec3.0.") for k in keys)
+
+
+@pytest.mark.parametrize("C,S", [(4, 8), (16, 6)])
+def test_wavelet_pooling_matches_matrix_form(C, S):
+    """Strided 2x2 form vs the banded-matrix definition of WPL/iwp.py:58-103 restated with numpy (last high-pass row /
+    column zero), through the same fusion conv."""
+    from km_unet_b200.modules.km_unet import IntelligentWaveletPoolingModule
+    torch.manual_seed(C)
+    m = IntelligentWaveletPoolingModule(C)
+    x = torch.randn(2, C, S, S)
+    s = 2 ** -0.5
+    lo = np.zeros((S // 2, S))
+    hi = np.zeros((S // 2, S))
+    for i in range(S // 2):
+        lo[i, 2 * i], lo[i, 2 * i + 1] = s, s
+        if i < S // 2 - 1:
+            hi[i, 2 * i], hi[i, 2 * i + 1] = s, -s
+    lo, hi = torch.tensor(lo, dtype=torch.float32), torch.tensor(hi, dtype=torch.float32)
+    L, Hh = lo @ x, hi @ x
+    LL, LH, HL, HH = L @ lo.t(), L @ hi.t(), Hh @ lo.t(), Hh @ hi.t()
+    high = torch.cat([LH, HL, HH], dim=1).mean(dim=1, keepdim=True)
+    want = m.fusion_conv(torch.cat([LL, high], dim=1))
+    assert rel_err(m(x), want) < 1e-6
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not present")
+@pytest.mark.parametrize("name", ["StableHybridKANConv_noKAN", "TripleNorm", "DirectionAttention", "LocalContrastAttention",
+                                  "MultiScaleFusion", "IntelligentWaveletPoolingModule"])
+def test_glue_blocks_match_live_reference(name):
+    from oracle import ref_loader
+    R = ref_loader.load(with_models=True)
+    import km_unet_b200.modules.km_unet as M
+    torch.manual_seed(11)
+    sh = R.sh_module
+    if name == "TripleNorm":
+        ref, ours, x = sh.TripleNorm(16), M.TripleNorm(16), torch.randn(2, 16, 8, 8)
+    elif name == "DirectionAttention":
+        ref, ours, x = sh.DirectionAttention(16, "height"), M.DirectionAttention(16, "height"), torch.randn(2, 16, 8, 8)
+    elif name == "LocalContrastAttention":
+        ref, ours, x = sh.LocalContrastAttention(16), M.LocalContrastAttention(16), torch.randn(2, 16, 8, 8)
+    elif name == "MultiScaleFusion":
+        ref, ours = sh.MultiScaleFusion([16, 32, 32]), M.MultiScaleFusion([16, 32, 32])
+        x = [torch.randn(2, 16, 8, 8), torch.randn(2, 32, 8, 8), torch.randn(2, 32, 8, 8)]
+    elif name == "IntelligentWaveletPoolingModule":
+        ref, ours, x = sh.IntelligentWaveletPoolingModule(16), M.IntelligentWaveletPoolingModule(16), torch.randn(2, 16, 8, 8)
+    else:
+        pytest.skip("KAN path needs CUDA")
+    with torch.no_grad():
+        for p in ref.parameters():
+            p.add_(torch.randn_like(p) * 0.1)
+    ours.load_state_dict(ref.state_dict())
+    assert rel_err(ours(x), ref(x)) < 1e-5
