@@ -1,19 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- headline measurement of the KM-UNet hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--precision fp32|bf16]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload model|laps|infer|kan]
+                    [--batch B] [--precision fp32|bf16]
 
-Workload (BASELINE.json configs[1], the configuration the "KANConv2D % tensor-core peak" metric is quoted on):
-one KANConv2d(64 -> 64, 3x3, padding 1, grid 5, cubic) forward+backward on B x 64 x 128 x 128 fp32 inputs
-(synthetic randn, seeded), B = 32 per GPU.  A "step" = forward + backward (dX, dWbase, dWspline, dWscaler) of one batch.
-With N > 1 (torchrun, one rank per GPU) every rank processes its own batch shard (weak scaling) and the weight
-gradients are averaged with a bucketed NCCL all-reduce launched from grad-ready hooks.
+Default workload = BASELINE.json configs[2], the configuration the headline metric "KM_UNetV3_SH train samples/sec at
+1/2/4/8 B200" is quoted on: KM_UNetV3_SH(num_classes=20), 5 -> 20 frames of 128x128, B = 32 per GPU, synthetic U[0,1)
+frames, random-init weights, train mode.  A "step" = forward + HybridLoss + backward + gradient all-reduce (N > 1) +
+AdamW update of one batch.  With N > 1 (torchrun, one rank per GPU) every rank processes its own batch shard (weak
+scaling); the only collective is the bucketed NCCL all-reduce of the 5.1 MB of live gradients, launched from grad-ready
+hooks so it overlaps the rest of backward.  `--workload laps` = configs[3] (KM_UNetV3_LAPS, 5 -> 3 frames of 256x256),
+`--workload infer` = configs[4] (SH eval, 256x256, B = 64), `--workload kan` = configs[1] alone (the KANConv2d 64->64
+microbench the "KANConv2D % tensor-core peak" half of the metric is quoted on; it is also attached to every default
+line as `kan_microbench`).
 
-One JSON line on stdout (rank 0).  `value` = whole-job samples/s with inputs resident in HBM; `e2e` = same metric
-through the public module API with the batch in pinned host memory (H2D of x and D2H of the weight gradients inside
-the timed region); `roofline` = the dominant kernel family vs the measured bf16 tensor peak; `cpu_baseline` = the
-oracle port of the same layer on the box's host cores (bounded sample).
-`--impl reference` times that CPU oracle port alone (the reference is pure PyTorch: its own CPU path is the same
+One JSON line on stdout (rank 0).  `value` = whole-job samples/s with the batch resident in HBM; `e2e` = the same
+metric through the public module API with the batch in pinned host memory (H2D of the 25-frame batch and D2H of the
+loss inside the timed region); `roofline` = the C-ABI entry point with the largest share of the step (CUDA events on
+the launching stream around every libkmunet call during a profiling pass of the same workload) against the roofline
+that bounds it; `cpu_baseline` = the full-model CPU oracle (oracle/model.py) on the box's host cores, bounded sample.
+`--impl reference` times that CPU oracle alone (the reference is pure PyTorch: its own CPU path is the same
 arithmetic; the reference tree itself cannot travel to the GPU box).
 """
 import argparse
@@ -28,13 +34,17 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CIN, COUT, KS, S = 64, 64, 3, 128
-METRIC = "train samples/sec (KANConv2d 64->64 3x3 128x128 fwd+bwd)"
 UNIT = "samples/s"
-
-
-def flops_fwd(batch):
-    return 2.0 * batch * S * S * COUT * CIN * KS * KS * 9      # 2*M*Cout*Cin*81
+WORKLOADS = {
+    # name: (metric, description, variant, classes, frames_in, size, default batch, train)
+    "model": ("KM_UNetV3_SH train samples/sec", "BASELINE configs[2]: KM_UNetV3_SH(num_classes=20) full training step "
+              "(fwd + HybridLoss + bwd + AdamW), 5->20 frames 128x128", "SH", 20, 5, 128, 32, True),
+    "laps": ("KM_UNetV3_LAPS train samples/sec", "BASELINE configs[3]: KM_UNetV3_LAPS(num_classes=3) full training step, "
+             "5->3 frames 256x256", "LAPS", 3, 5, 256, 32, True),
+    "infer": ("KM_UNetV3_SH inference samples/sec", "BASELINE configs[4]: KM_UNetV3_SH(num_classes=20) eval forward, "
+              "256x256", "SH", 20, 5, 256, 64, False),
+}
+KAN = dict(CIN=64, COUT=64, KS=3, S=128)
 
 
 def load_peaks():
@@ -96,12 +106,63 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ----------------------------------------------------------------------------------------------------- algorithmic work
+def op_work(name, key):
+    """(bound, algorithmic units per call, unit) of one C-ABI entry point -- SURVEY section 8d / DESIGN section 4."""
+    if name.startswith("kmu_kanconv2d"):
+        B, Cin, H, W, Cout = key
+        f = 2.0 * B * H * W * Cout * Cin * 81
+        return ("tensor", f if name.endswith("fwd") else 2 * f, "flop")
+    if name.startswith("kmu_hsmssd"):
+        B, C, L = key
+        return ("hbm", (8.0 if name.endswith("fwd") else 16.0) * B * C * L, "byte")
+    if name.startswith("kmu_layernorm1d"):
+        B, C, L = key
+        return ("hbm", (8.0 if name.endswith("fwd") else 12.0) * B * C * L, "byte")
+    if name.startswith("kmu_dysample"):
+        B, C, H, W = key
+        return ("hbm", (20.0 if name.endswith("fwd") else 24.0) * B * C * H * W, "byte")
+    if name.startswith("kmu_dagem"):
+        B, C, H, W = key
+        return ("hbm", (12.0 if name.endswith("fwd") else 20.0) * B * C * H * W, "byte")
+    return ("hbm", 0.0, "byte")
+
+
 # ----------------------------------------------------------------------------------------------------- CPU oracle arm
-def cpu_oracle_step_factory(batch):
-    """The oracle port (oracle/kan.py, torch CPU fp32, autograd backward) of the same layer: the checker, timed here as
-    the CPU baseline only."""
+def cpu_oracle_model_step_factory(workload, batch):
+    """Full-model CPU oracle (oracle/model.py: the model mirror's torch glue + the op restatements of oracle/), the same
+    training step as the GPU arm.  The checker, timed here as the CPU baseline only."""
+    import torch
+    import km_unet_b200 as K
+    from km_unet_b200.loss import HybridLoss
+    from oracle import model as OM
+    _, _, variant, classes, fin, size, _, train = WORKLOADS[workload]
+    torch.manual_seed(1234)
+    model = K.KM_UNetV3(num_classes=classes, variant=variant)
+    model.train(train)
+    g = torch.Generator().manual_seed(20240518)
+    data = torch.rand(batch, fin + classes, size, size, generator=g)
+    x, target = data[:, :fin].contiguous(), data[:, fin:].contiguous()
+    crit = HybridLoss()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.05)
+
+    def step():
+        with OM.cpu_ops():
+            if not train:
+                with torch.no_grad():
+                    return float(model(x).mean())
+            opt.zero_grad(set_to_none=True)
+            loss = crit(model(x), target)
+            loss.backward()
+            opt.step()
+            return float(loss.detach())
+    return step
+
+
+def cpu_oracle_kan_step_factory(batch):
     import torch
     from oracle import kan as OK
+    CIN, COUT, KS, S = KAN["CIN"], KAN["COUT"], KAN["KS"], KAN["S"]
     torch.manual_seed(1234)
     grid = OK.make_grid(CIN * KS * KS)
     bw = (torch.rand(COUT, CIN * KS * KS) - 0.5) * 0.083
@@ -121,10 +182,10 @@ def cpu_oracle_step_factory(batch):
     return step
 
 
-def time_cpu_oracle(batch, steps, warmup):
+def time_cpu_oracle(workload, batch, steps, warmup):
     import torch
     torch.set_num_threads(os.cpu_count() or 1)
-    step = cpu_oracle_step_factory(batch)
+    step = cpu_oracle_kan_step_factory(batch) if workload == "kan" else cpu_oracle_model_step_factory(workload, batch)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
@@ -134,20 +195,33 @@ def time_cpu_oracle(batch, steps, warmup):
     return batch * steps / dt, dt / steps * 1e3, torch.get_num_threads()
 
 
+def cpu_sample_batch(workload):
+    return 1 if workload in ("kan", "laps", "infer") else 2
+
+
+def metric_of(workload):
+    return "train samples/sec (KANConv2d 64->64 3x3 128x128 fwd+bwd)" if workload == "kan" else WORKLOADS[workload][0]
+
+
+def describe(workload):
+    return ("BASELINE configs[1]: KANConv2d 64->64 3x3 grid5 order3, 128x128, fwd+bwd" if workload == "kan"
+            else WORKLOADS[workload][1])
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sample_b = 1
-    value, ms, cores = time_cpu_oracle(sample_b, args.steps, args.warmup)
+    sb = cpu_sample_batch(args.workload)
+    steps, warmup = min(args.steps, 3), min(args.warmup, 1)
+    value, ms, cores = time_cpu_oracle(args.workload, sb, steps, warmup)
+    sample = f"{steps} steps x {sb} sample(s) of the workload after {warmup} warm-up, oracle/model.py on torch CPU fp32"
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": metric_of(args.workload), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: KANConv2d 64->64 3x3 grid5 order3, 128x128, fwd+bwd; CPU sample of "
-                               f"{sample_b} image per step", "batch_per_step": sample_b},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps x {sample_b} image(s) of the workload, oracle/kan.py on torch CPU fp32"},
+        "config": {"workload": describe(args.workload) + f"; CPU sample of {sb} sample(s) per step", "batch_per_step": sb},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -156,99 +230,39 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------------- our arm
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device: km_unet_b200 has no CPU fallback")
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    import km_unet_b200 as K
-    from km_unet_b200 import _lib
-    from km_unet_b200.ddp import BucketedGradAllReduce, broadcast_parameters
-    K.config.kan_precision = args.precision
-    _lib.lib()                                            # fail loudly if the extension is missing
+class Harness:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        if not torch.cuda.is_available():
+            raise RuntimeError("bench.py needs a CUDA device: km_unet_b200 has no CPU fallback")
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.args = args
 
-    B = args.batch
-    torch.manual_seed(1234)
-    layer = K.KANConv2d(CIN, COUT, KS, padding=1).to(dev)
-    broadcast_parameters(layer)
-    params = list(layer.parameters())
-    reducer = BucketedGradAllReduce(params, bucket_bytes=1 << 20) if world > 1 else None
-    g = torch.Generator().manual_seed(20240518 + rank)
-    x_host = torch.randn(B, CIN, S, S, generator=g).pin_memory()
-    gout = torch.randn(B, COUT, S, S, generator=g).to(dev)
-    x_dev = x_host.to(dev).requires_grad_(True)
-    grads_host = [torch.empty(p.shape, dtype=p.dtype).pin_memory() for p in params]
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world == 1:
+    def max_over_ranks(self, ms):
+        if self.world == 1:
             return ms
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([ms], device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    def step_resident():
-        for p in params:
-            p.grad = None
-        x_dev.grad = None
-        y = layer(x_dev)
-        y.backward(gout)
-        if reducer is not None:
-            reducer.finish()
-
-    # e2e: the batch lives in pinned host memory; every step copies it host->device (on a copy stream, double buffered so
-    # step i+1's copy overlaps step i's kernels -- the loop a user of the module API writes) and reads the step's result
-    # (the weight gradients) back to the host before the step counts as done.
-    copy_stream = torch.cuda.Stream(device=dev)
-    x_bufs = [torch.empty_like(x_dev) for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
-    state = {"i": 0, "primed": False}
-
-    def prefetch(slot):
-        with torch.cuda.stream(copy_stream), torch.no_grad():
-            copy_stream.wait_event(consumed[slot])
-            x_bufs[slot].copy_(x_host, non_blocking=True)        # H2D from pinned memory, every step
-            ready[slot].record(copy_stream)
-
-    def step_e2e():
-        slot = state["i"] & 1
-        if not state["primed"]:
-            for e in consumed:
-                e.record()
-            prefetch(slot)
-            state["primed"] = True
-        prefetch(slot ^ 1)                                       # next step's input, overlapped with this step's kernels
-        torch.cuda.current_stream().wait_event(ready[slot])
-        for p in params:
-            p.grad = None
-        xin = x_bufs[slot].requires_grad_(True)
-        xin.grad = None
-        y = layer(xin)
-        y.backward(gout)
-        consumed[slot].record()
-        if reducer is not None:
-            reducer.finish()
-        for h, p in zip(grads_host, params):
-            h.copy_(p.grad, non_blocking=True)            # D2H of the step's result (the weight gradients)
-        torch.cuda.current_stream().synchronize()         # the host must hold the result before the next step
-        state["i"] += 1
-
-    def timed(step, steps, warmup):
+    def timed(self, step, steps, warmup):
+        torch = self.torch
         for _ in range(warmup):
             step()
-        barrier()
+        self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
@@ -256,28 +270,32 @@ def run_ours(args):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        barrier()
-        return max_over_ranks(ms)
+        self.barrier()
+        return self.max_over_ranks(ms)
 
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    launches0 = _lib.launch_count()
-    total_ms = timed(step_resident, args.steps, args.warmup)
-    launches = (_lib.launch_count() - launches0) * args.steps // (args.steps + args.warmup)
-    clocks = sampler.stop() if sampler else None
-    value = world * B * args.steps / (total_ms / 1e3)
-    e2e_ms = timed(step_e2e, args.steps, args.warmup)
-    e2e_value = world * B * args.steps / (e2e_ms / 1e3)
 
-    # per-kernel-family device time: CUDA events on the launching (current) stream around each family's launches.
-    # backward-input alone = parameters frozen (the C call gets d_base_weight = NULL), backward-weights alone = detached input.
+def kan_microbench(h, B, steps, warmup, precision, with_total=False):
+    """BASELINE configs[1]: per-kernel-family device time of one KANConv2d(64->64, 3x3) at B x 64 x 128 x 128 and the
+    fraction of the measured bf16 tensor peak (dense FLOP count 2*M*Cout*Cin*81 per GEMM family)."""
+    torch = h.torch
+    import km_unet_b200 as K
+    CIN, COUT, KS, S = KAN["CIN"], KAN["COUT"], KAN["KS"], KAN["S"]
+    old = K.config.kan_precision
+    K.config.kan_precision = precision
+    torch.manual_seed(1234)
+    layer = K.KANConv2d(CIN, COUT, KS, padding=1).to(h.dev)
+    params = list(layer.parameters())
+    g = torch.Generator().manual_seed(20240518 + h.rank)
+    x_dev = torch.randn(B, CIN, S, S, generator=g).to(h.dev).requires_grad_(True)
+    gout = torch.randn(B, COUT, S, S, generator=g).to(h.dev)
+    flops = 2.0 * B * S * S * COUT * CIN * KS * KS * 9
+
     def time_family(which):
         ts = []
         xin = x_dev if which != "dw" else x_dev.detach()
         for p in params:
             p.requires_grad_(which != "dx")
-        for i in range(args.warmup + args.steps):
+        for i in range(warmup + steps):
             for p in params:
                 p.grad = None
             x_dev.grad = None
@@ -292,7 +310,7 @@ def run_ours(args):
                 y.backward(gout)
                 b.record()
             torch.cuda.synchronize()
-            if i >= args.warmup:
+            if i >= warmup:
                 ts.append(a.elapsed_time(b))
         for p in params:
             p.requires_grad_(True)
@@ -300,45 +318,196 @@ def run_ours(args):
 
     fam_ms = {"kanconv2d_fwd": time_family("fwd"), "kanconv2d_bwd_dx": time_family("dx"), "kanconv2d_bwd_dw": time_family("dw")}
     peaks = load_peaks()
-    peak_tf = peaks["bf16_tflops"]
-    fam = {k: (flops_fwd(B), ms) for k, ms in fam_ms.items()}        # each family is one 2*M*Cout*Cin*81 GEMM
-    dom = max(fam, key=lambda k: fam[k][1])
-    roof_all = {k: {"ms": ms, "achieved": fl / ms / 1e9, "frac": fl / ms / 1e9 / peak_tf} for k, (fl, ms) in fam.items()}
+    fam = {k: {"ms": ms, "achieved": flops / ms / 1e9, "frac": flops / ms / 1e9 / peaks["bf16_tflops"]} for k, ms in fam_ms.items()}
+    out = {"workload": describe("kan"), "batch": B, "precision": precision, "flops_per_family": flops, "unit": "TFLOP/s",
+           "peak": peaks["bf16_tflops"], "peak_source": peaks["source"] + " bf16 burst", "families": fam}
+    if with_total:
+        def step():
+            for p in params:
+                p.grad = None
+            x_dev.grad = None
+            layer(x_dev).backward(gout)
+        ms = h.timed(step, steps, warmup) / steps
+        out["fwd_bwd_ms"] = ms
+        out["tflops_fwd_bwd"] = 3 * flops / ms / 1e9
+    K.config.kan_precision = old
+    return out
+
+
+def run_kan(h, args):
+    from km_unet_b200 import _lib
+    B = args.batch or 32
+    launches0 = _lib.launch_count()
+    mb = kan_microbench(h, B, args.steps, args.warmup, args.precision, with_total=True)
+    launches = _lib.launch_count() - launches0
+    if h.rank != 0:
+        return
+    fam = mb["families"]
+    dom = max(fam, key=lambda k: fam[k]["ms"])
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tpath) and args.precision == "bf16" and B == 32:
         with open(tpath) as f:
             traffic = json.load(f).get(dom)
-    roofline = {"kernel": dom, "bound": "tensor", "achieved": roof_all[dom]["achieved"], "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": roof_all[dom]["frac"], "traffic": traffic, "peak_source": peaks["source"] + " bf16 burst",
-                "algorithmic_flops_per_launch": fam[dom][0], "families": roof_all}
-
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, ms, cores = time_cpu_oracle(1, 3, 1)
+    if h.world == 1 and not args.no_cpu_baseline:
+        v, ms, cores = time_cpu_oracle("kan", 1, 3, 1)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "3 steps x 1 image of the workload (B=1, 64x128x128) after 1 warm-up, oracle/kan.py on torch CPU fp32"}
+    value = h.world * B / (mb["fwd_bwd_ms"] / 1e3)
+    line = {"metric": metric_of("kan"), "value": value, "unit": UNIT, "n_gpus": h.world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": mb["fwd_bwd_ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": describe("kan"), "batch_per_gpu": B, "global_batch": B * h.world, "precision": args.precision,
+                       "parallelism": f"dp{h.world}", "l2": "inputs (x, dy: 2 x %.0f MB) exceed the 126 MB L2" % (B * 64 * 128 * 128 * 4 / 1e6)},
+            "e2e": None, "gpu_launches": int(launches // (3 * (args.steps + args.warmup) + args.steps + args.warmup)),
+            "roofline": {"kernel": dom, "bound": "tensor", "achieved": fam[dom]["achieved"], "peak": mb["peak"], "unit": "TFLOP/s",
+                         "frac": fam[dom]["frac"], "traffic": traffic, "peak_source": mb["peak_source"], "families": fam},
+            "cpu_baseline": cpu, "tflops_fwd_bwd": mb["tflops_fwd_bwd"]}
+    print(json.dumps(line), flush=True)
+
+
+def run_model(h, args):
+    torch, dist = h.torch, h.dist
+    import km_unet_b200 as K
+    from km_unet_b200 import _lib, ops
+    from km_unet_b200.ddp import BucketedGradAllReduce, broadcast_parameters
+    from km_unet_b200.loss import HybridLoss
+    K.config.kan_precision = args.precision
+    _lib.lib()                                            # fail loudly if the extension is missing
+    metric, desc, variant, classes, fin, size, default_b, train = WORKLOADS[args.workload]
+    B = args.batch or default_b
+    dev, world, rank = h.dev, h.world, h.rank
+
+    torch.manual_seed(1234)
+    model = K.KM_UNetV3(num_classes=classes, variant=variant).to(dev)
+    model.train(train)
+    broadcast_parameters(model)
+    crit = HybridLoss()
+    g = torch.Generator().manual_seed(20240518 + rank)
+    batch_host = torch.rand(B, fin + classes, size, size, generator=g).pin_memory()
+    batch_dev = batch_host.to(dev)
+    x_dev, t_dev = batch_dev[:, :fin].contiguous(), batch_dev[:, fin:].contiguous()
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    reducer = opt = None
+    if train:
+        # parameters that never receive a gradient (the reference's dead branches) stay out of the optimizer and the all-reduce
+        crit(model(x_dev[:2]), t_dev[:2]).backward()
+        live = [p for p in model.parameters() if p.grad is not None]
+        for p in model.parameters():
+            p.grad = None
+        opt = torch.optim.AdamW(live, lr=1e-3, weight_decay=0.05, fused=True)
+        reducer = BucketedGradAllReduce(live, bucket_bytes=2 << 20) if world > 1 else None
+
+    def train_step(x, t):
+        opt.zero_grad(set_to_none=True)
+        loss = crit(model(x), t)
+        loss.backward()
+        if reducer is not None:
+            reducer.finish()
+        opt.step()
+        return loss
+
+    def infer_step(x):
+        with torch.no_grad():
+            return model(x).mean()
+
+    def step_resident():
+        return train_step(x_dev, t_dev) if train else infer_step(x_dev)
+
+    # e2e: the batch lives in pinned host memory; every step copies it host->device (copy stream, double buffered so step
+    # i+1's copy overlaps step i's kernels) and reads the step's loss back to the host before the step counts as done.
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [torch.empty_like(batch_dev) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    state = {"i": 0, "primed": False}
+
+    def prefetch(slot):
+        with torch.cuda.stream(copy_stream), torch.no_grad():
+            copy_stream.wait_event(consumed[slot])
+            bufs[slot].copy_(batch_host, non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    def step_e2e():
+        slot = state["i"] & 1
+        if not state["primed"]:
+            for e in consumed:
+                e.record()
+            prefetch(slot)
+            state["primed"] = True
+        prefetch(slot ^ 1)
+        torch.cuda.current_stream().wait_event(ready[slot])
+        x, t = bufs[slot][:, :fin].contiguous(), bufs[slot][:, fin:].contiguous()
+        res = train_step(x, t) if train else infer_step(x)
+        consumed[slot].record()
+        loss_host.copy_(res.detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        state["i"] += 1
+
+    sampler = ClockSampler(h.local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    total_ms = h.timed(step_resident, args.steps, args.warmup)
+    launches = (_lib.launch_count() - launches0) // (args.steps + args.warmup)
+    clocks = sampler.stop() if sampler else None
+    value = world * B * args.steps / (total_ms / 1e3)
+    e2e_ms = h.timed(step_e2e, args.steps, args.warmup)
+    e2e_value = world * B * args.steps / (e2e_ms / 1e3)
+
+    # op-level profile of the same step: CUDA events on the launching stream around every libkmunet call
+    prof_steps = 3
+    step_resident()
+    ops.profile_start()
+    for _ in range(prof_steps):
+        step_resident()
+    prof = ops.profile_stop()
+    peaks = load_peaks()
+    table = []
+    for (name, key), e in prof.items():
+        bound, work, unit = op_work(name, key)
+        ms = e["ms"] / e["calls"]
+        peak = peaks["hbm_gbs"] if bound == "hbm" else peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+        ach = work / ms / (1e6 if bound == "hbm" else 1e9)
+        table.append({"op": name, "shape": list(key), "calls_per_step": e["calls"] / prof_steps, "ms_per_call": ms,
+                      "ms_per_step": e["ms"] / prof_steps, "bound": bound, "achieved": ach,
+                      "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": ach / peak})
+    table.sort(key=lambda r: -r["ms_per_step"])
+    ours_ms = sum(r["ms_per_step"] for r in table)
+    dom = table[0]
+    roofline = {"kernel": f"{dom['op']} {tuple(dom['shape'])}", "bound": dom["bound"], "achieved": dom["achieved"],
+                "peak": peaks["hbm_gbs"] if dom["bound"] == "hbm" else (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]),
+                "unit": dom["unit"], "frac": dom["frac"], "traffic": None,
+                "peak_source": peaks["source"] + (" HBM copy" if dom["bound"] == "hbm" else " bf16 sustained"),
+                "share_of_step": dom["ms_per_step"] / (total_ms / args.steps),
+                "libkmunet_ms_per_step": ours_ms, "torch_glue_ms_per_step": total_ms / args.steps - ours_ms, "ops": table[:12]}
+
+    kan = kan_microbench(h, 32, 5, 3, args.precision) if not args.no_kan_microbench else None
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sb = cpu_sample_batch(args.workload)
+        v, ms, cores = time_cpu_oracle(args.workload, sb, 2, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"2 steps x {sb} sample(s) of the workload after 1 warm-up, oracle/model.py on torch CPU fp32"}
 
     if rank == 0:
-        h2d = x_host.numel() * 4
-        d2h = sum(p.numel() * 4 for p in params)
+        nlive = sum(p.numel() for p in opt.param_groups[0]["params"]) if train else 0
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: KANConv2d 64->64 3x3 grid5 order3, 128x128, fwd+bwd",
-                       "batch_per_gpu": B, "global_batch": B * world, "precision": args.precision,
-                       "parallelism": f"dp{world}", "l2": "inputs (x, dy: 2 x %.0f MB) exceed the 126 MB L2" % (B * CIN * S * S * 4 / 1e6),
-                       "grad_allreduce": "bucketed NCCL, hooks" if world > 1 else "none (1 GPU)"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * world, "frames": f"{fin}->{classes}",
+                       "size": size, "precision": f"KANConv2d {args.precision} (tcgen05) / everything else fp32",
+                       "parallelism": f"dp{world}", "optimizer": "AdamW(lr 1e-3, wd 0.05, fused)" if train else None,
+                       "l2": "activations per step (hundreds of %.0f MB tensors) exceed the 126 MB L2" % (B * 16 * size * size * 4 / 1e6),
+                       "grad_allreduce": (f"bucketed NCCL from grad hooks, {nlive * 4 / 1e6:.1f} MB" if world > 1 else "none (1 GPU)")},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": batch_host.numel() * 4, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "tflops_fwd_bwd": 3 * flops_fwd(B) * world / (total_ms / args.steps) / 1e9,
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "kan_microbench": kan,
         }
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
 
 
 def main():
@@ -347,15 +516,23 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
+    ap.add_argument("--workload", default="model", choices=["model", "laps", "infer", "kan"])
+    ap.add_argument("--batch", type=int, default=0, help="samples per GPU per step (0 = the workload's default)")
     ap.add_argument("--precision", default=os.environ.get("KMU_KAN_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kan-microbench", action="store_true")
     args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "ours":
-        args.warmup = max(args.warmup, 1)
+    args.warmup = max(args.warmup, 1)
     if args.impl == "reference":
         return run_reference(args)
-    return run_ours(args)
+    h = Harness(args)
+    if args.workload == "kan":
+        run_kan(h, args)
+    else:
+        run_model(h, args)
+    if h.world > 1:
+        h.dist.destroy_process_group()
+    return 0
 
 
 if __name__ == "__main__":

@@ -15,6 +15,40 @@ from ._lib import (DagemBn, DagemBwdArgs, DagemDesc, DagemFwdArgs, DysBwdArgs, D
 __all__ = ["kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dysample_sample", "dagem_gate", "KMU_PREC_FP32", "KMU_PREC_BF16"]
 
 
+# ------------------------------------------------------------------------------------------------------ op-level timing
+_PROF = None
+
+
+def profile_start():
+    """Record a CUDA-event pair (on the launching stream) around every C-ABI call until profile_stop()."""
+    global _PROF
+    _PROF = []
+
+
+def profile_stop():
+    """-> {(entry point, shape key): {"calls": n, "ms": total device ms}}; synchronises."""
+    global _PROF
+    rec, _PROF = _PROF or [], None
+    torch.cuda.synchronize()
+    out = {}
+    for name, key, a, b in rec:
+        e = out.setdefault((name, key), {"calls": 0, "ms": 0.0})
+        e["calls"] += 1
+        e["ms"] += a.elapsed_time(b)
+    return out
+
+
+def _call(name, key, fn, *args):
+    if _PROF is None:
+        return fn(*args)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    r = fn(*args)
+    b.record()
+    _PROF.append((name, key, a, b))
+    return r
+
+
 def _workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
@@ -46,7 +80,7 @@ class _KanConv2dFn(torch.autograd.Function):
         ws = _workspace(nbytes, x.device)
         y = torch.empty(B, Cout, Ho, Wo, dtype=torch.float32, device=x.device)
         args = KanFwdArgs(desc, ptr(x), ptr(bw), ptr(sw), ptr(sc), ptr(gr), ptr(y), ws.data_ptr(), ws.numel())
-        check(lib.kmu_kanconv2d_fwd(C.byref(args), stream_ptr()), "kmu_kanconv2d_fwd")
+        check(_call("kmu_kanconv2d_fwd", (B, Cin, H, W, Cout), lib.kmu_kanconv2d_fwd, C.byref(args), stream_ptr()), "kmu_kanconv2d_fwd")
         ctx.save_for_backward(x, bw, sw, sc, gr)
         ctx.desc = desc
         return y
@@ -68,7 +102,8 @@ class _KanConv2dFn(torch.autograd.Function):
         ws = _workspace(nbytes, x.device)
         args = KanBwdArgs(desc, ptr(x), ptr(dy), ptr(bw), ptr(sw), ptr(sc), ptr(gr), ptr(dx), ptr(dbw), ptr(dsw), ptr(dsc),
                           ws.data_ptr(), ws.numel())
-        check(lib.kmu_kanconv2d_bwd(C.byref(args), stream_ptr()), "kmu_kanconv2d_bwd")
+        check(_call("kmu_kanconv2d_bwd", (desc.B, desc.Cin, desc.H, desc.W, desc.Cout), lib.kmu_kanconv2d_bwd, C.byref(args), stream_ptr()),
+              "kmu_kanconv2d_bwd")
         return dx, dbw, dsw, dsc, None, None, None, None, None, None, None, None
 
 
@@ -114,8 +149,8 @@ class _LayerNorm1dFn(torch.autograd.Function):
         B, Cc, L = x.shape
         w, b = weight.reshape(-1).contiguous(), bias.reshape(-1).contiguous()
         y = torch.empty_like(x)
-        check(lib.kmu_layernorm1d_fwd(ptr(x), ptr(w), ptr(b), ptr(y), None, B, Cc, L, float(eps), stream_ptr()),
-              "kmu_layernorm1d_fwd")
+        check(_call("kmu_layernorm1d_fwd", (B, Cc, L), lib.kmu_layernorm1d_fwd, ptr(x), ptr(w), ptr(b), ptr(y), None, B, Cc, L, float(eps),
+                    stream_ptr()), "kmu_layernorm1d_fwd")
         ctx.save_for_backward(x, w)
         ctx.eps = float(eps)
         ctx.wshape = weight.shape
@@ -131,8 +166,8 @@ class _LayerNorm1dFn(torch.autograd.Function):
         dx = torch.empty_like(x)
         dw = torch.zeros_like(w)
         db = torch.zeros_like(w)
-        check(lib.kmu_layernorm1d_bwd(ptr(x), ptr(w), ptr(dy), ptr(dx), ptr(dw), ptr(db), B, Cc, L, ctx.eps, stream_ptr()),
-              "kmu_layernorm1d_bwd")
+        check(_call("kmu_layernorm1d_bwd", (B, Cc, L), lib.kmu_layernorm1d_bwd, ptr(x), ptr(w), ptr(dy), ptr(dx), ptr(dw), ptr(db), B, Cc, L,
+                    ctx.eps, stream_ptr()), "kmu_layernorm1d_bwd")
         return dx, dw.reshape(ctx.wshape), db.reshape(ctx.wshape), None
 
 
@@ -169,7 +204,7 @@ class _HsmssdFn(torch.autograd.Function):
         hz = torch.empty(B, 2 * Cc, N, dtype=torch.float32, device=dev)
         args = HsmFwdArgs(desc, ptr(x), ptr(wp), ptr(wd), ptr(whz), ptr(wo), ptr(Ac), ptr(Dc), ptr(y), ptr(h), ptr(P),
                           ptr(stats), ptr(hs), ptr(hz), ws.data_ptr(), ws.numel())
-        check(lib.kmu_hsmssd_fwd(C.byref(args), stream_ptr()), "kmu_hsmssd_fwd")
+        check(_call("kmu_hsmssd_fwd", (B, Cc, L), lib.kmu_hsmssd_fwd, C.byref(args), stream_ptr()), "kmu_hsmssd_fwd")
         ctx.save_for_backward(x, wp, wd, whz, wo, Ac, Dc, P, stats, hs, hz, h)
         ctx.desc = desc
         ctx.shapes = (w_bcdt.shape, w_dw.shape, w_hz.shape, w_out.shape)
@@ -192,7 +227,7 @@ class _HsmssdFn(torch.autograd.Function):
         args = HsmBwdArgs(desc, ptr(x), ptr(dy), ptr(dh), ptr(wp), ptr(wd), ptr(whz), ptr(wo), ptr(Ac), ptr(Dc), ptr(P),
                           ptr(stats), ptr(hs), ptr(hz), ptr(h), ptr(dx), ptr(dwp), ptr(dwd), ptr(dwhz), ptr(dwo), ptr(dA),
                           ptr(dD), ws.data_ptr(), ws.numel())
-        check(lib.kmu_hsmssd_bwd(C.byref(args), stream_ptr()), "kmu_hsmssd_bwd")
+        check(_call("kmu_hsmssd_bwd", (desc.B, desc.C, desc.L), lib.kmu_hsmssd_bwd, C.byref(args), stream_ptr()), "kmu_hsmssd_bwd")
         s = ctx.shapes
         return dx, dwp.reshape(s[0]), dwd.reshape(s[1]), dwhz.reshape(s[2]), dwo.reshape(s[3]), dA, dD, None
 
@@ -220,7 +255,7 @@ class _DySampleFn(torch.autograd.Function):
         offset = torch.empty(B, noff, H, W, dtype=torch.float32, device=x.device)
         out = torch.empty(B, Cc, scale * H, scale * W, dtype=torch.float32, device=x.device)
         args = DysFwdArgs(desc, ptr(x), ptr(w), ptr(b), ptr(ip), ptr(offset), ptr(out))
-        check(lib.kmu_dysample_fwd(C.byref(args), stream_ptr()), "kmu_dysample_fwd")
+        check(_call("kmu_dysample_fwd", (B, Cc, H, W), lib.kmu_dysample_fwd, C.byref(args), stream_ptr()), "kmu_dysample_fwd")
         ctx.save_for_backward(x, w, offset)
         ctx.desc = desc
         ctx.wshape = w_offset.shape
@@ -238,7 +273,7 @@ class _DySampleFn(torch.autograd.Function):
         db = torch.empty(w.shape[0], dtype=torch.float32, device=x.device)
         ws = _workspace(lib.kmu_dysample_bwd_workspace_bytes(C.byref(desc)), x.device)
         args = DysBwdArgs(desc, ptr(x), ptr(w), ptr(offset), ptr(dout), ptr(dx), ptr(dw), ptr(db), ws.data_ptr(), ws.numel())
-        check(lib.kmu_dysample_bwd(C.byref(args), stream_ptr()), "kmu_dysample_bwd")
+        check(_call("kmu_dysample_bwd", (desc.B, desc.C, desc.H, desc.W), lib.kmu_dysample_bwd, C.byref(args), stream_ptr()), "kmu_dysample_bwd")
         return dx, dw.reshape(ctx.wshape), db, None, None, None
 
 
@@ -311,7 +346,7 @@ class _DagemGateFn(torch.autograd.Function):
             bns[i] = DagemBn(ptr(bnw[i]), ptr(bnb[i]), ptr(rm), ptr(rv))
         args = DagemFwdArgs(desc, ptr(x), ptr(deformed), *[ptr(t) for t in lin], bns, ptr(out), ptr(saved), ws.data_ptr(),
                             ws.numel())
-        check(lib.kmu_dagem_fwd(C.byref(args), stream_ptr()), "kmu_dagem_fwd")
+        check(_call("kmu_dagem_fwd", (B, Cc, H, W), lib.kmu_dagem_fwd, C.byref(args), stream_ptr()), "kmu_dagem_fwd")
         ctx.save_for_backward(x, deformed, saved, *lin, *bnw)
         ctx.desc = desc
         return out
@@ -335,7 +370,7 @@ class _DagemGateFn(torch.autograd.Function):
                             ptr(dx), ptr(dd), ptr(d_ea_w), ptr(d_ea_b), ptr(d_vu_w), ptr(d_vu_b), ptr(d_eu_w), ptr(d_eu_b),
                             ptr(d_er_w), ptr(d_er_b), ptr(d_wf), (_lib._f32p * 5)(*[ptr(t) for t in dbw]),
                             (_lib._f32p * 5)(*[ptr(t) for t in dbb]), ws.data_ptr(), ws.numel())
-        check(lib.kmu_dagem_bwd(C.byref(args), stream_ptr()), "kmu_dagem_bwd")
+        check(_call("kmu_dagem_bwd", (desc.B, desc.C, desc.H, desc.W), lib.kmu_dagem_bwd, C.byref(args), stream_ptr()), "kmu_dagem_bwd")
         bn_grads = []
         for i in range(5):
             bn_grads += [dbw[i], dbb[i]]

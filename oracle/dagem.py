@@ -81,3 +81,29 @@ def dagem(x, P, training=True):
     zr = z.permute(0, 2, 3, 1).reshape(-1, C)
     zr = F.relu(bn("final_aggregation_layer.1", zr))
     return zr.reshape(B, H, W, C).permute(0, 3, 1, 2)
+
+
+def dagem_gate(x, deformed, lin, bns, training=True):
+    """The gating + final aggregation alone (DAGEM_md.py:62-92,104-110) with explicit tensors, mirroring the C ABI
+    kmu_dagem_fwd: lin = (ea_w, ea_b, vu_w, vu_b, eu_w, eu_b, er_w, er_b, wf); bns = 5 x (weight, bias, running_mean,
+    running_var) in the order edge_aggregation, edge_update, vertex_update, update_edge_reduce, final.  Running statistics
+    are read (eval) but never updated here."""
+    ea_w, ea_b, vu_w, vu_b, eu_w, eu_b, er_w, er_b, wf = lin
+    B, C, H, W = x.shape
+    Ch = C // 2
+
+    def bn(i, v):
+        w, b, rm, rv = bns[i]
+        return _bn_rows(v, w, b, rm, rv, training)
+
+    nbrs = torch.stack([torch.roll(x, 1, 2), torch.roll(x, -1, 2), torch.roll(x, 1, 3), torch.roll(x, -1, 3)], dim=-1)
+    edge = nbrs * x.unsqueeze(-1)
+    agg = F.relu(bn(0, edge.reshape(-1, 4) @ ea_w.t() + ea_b)).reshape(B, C, H, W)
+    vfeat = torch.cat([x, agg], dim=1).permute(0, 2, 3, 1).reshape(-1, 2 * C)
+    uv = F.relu(bn(2, vfeat @ vu_w.t() + vu_b)).reshape(B, H, W, Ch).permute(0, 3, 1, 2)
+    efeat = torch.cat([x.unsqueeze(-1).expand(B, C, H, W, 4), edge], dim=1).permute(0, 2, 3, 4, 1).reshape(-1, 2 * C)
+    ue = F.relu(bn(1, efeat @ eu_w.t() + eu_b)).reshape(B, H, W, 4, Ch).permute(0, 4, 1, 2, 3).reshape(-1, 4)
+    ur = F.relu(bn(3, ue @ er_w.t() + er_b)).reshape(B, Ch, H, W)
+    z = F.conv2d(torch.cat([deformed, uv * ur], dim=1), wf.reshape(C, C + Ch, 1, 1))
+    zr = F.relu(bn(4, z.permute(0, 2, 3, 1).reshape(-1, C)))
+    return zr.reshape(B, H, W, C).permute(0, 3, 1, 2)

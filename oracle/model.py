@@ -1,0 +1,51 @@
+"""Full-model CPU oracle (TEST INFRASTRUCTURE -- see oracle/__init__.py).
+
+`cpu_ops()` is a context manager that swaps the CUDA entry points of km_unet_b200.ops for the oracle restatements of
+this package, so the host-side model mirror (km_unet_b200/modules/km_unet.py, whose glue is plain torch) runs end to end
+on the CPU with the reference arithmetic.  Used by tests/ (parity of the CUDA model against it), by
+__graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference legs.  Never used by the product path: outside
+this context manager the operators raise on CPU tensors.
+"""
+import contextlib
+
+from . import dagem as _dagem
+from . import dysample as _dysample
+from . import hsmssd as _hsmssd
+from . import kan as _kan
+
+
+def _kanconv2d(x, base_weight, spline_weight, spline_scaler, grid, kernel_size, stride=1, padding=0, grid_size=5,
+               spline_order=3, precision=0, grid_meta=None):
+    return _kan.kanconv2d(x, base_weight, spline_weight, spline_scaler, grid, kernel_size, stride, padding, spline_order)
+
+
+def _kanlinear(x, base_weight, spline_weight, spline_scaler, grid, grid_size=5, spline_order=3, precision=0, grid_meta=None):
+    return _kan.kan_linear(x, base_weight, spline_weight, spline_scaler, grid, spline_order)
+
+
+def _hsm(x, w_bcdt, w_dw, w_hz, w_out, A, D, state_dim=64):
+    y, h = _hsmssd.hsmssd(x, w_bcdt, w_dw, w_hz, w_out, A, D, state_dim)
+    B, C, L = x.shape
+    H = int(round(L ** 0.5))
+    return y.reshape(B, C, H, H), h
+
+
+def _dys(x, w_offset, b_offset, init_pos, scale=2, groups=4):
+    return _dysample.dysample_lp(x, w_offset, b_offset, init_pos)
+
+
+def _gate(x, deformed, linears, bns, training, momentum=0.1, eps=1e-5):
+    return _dagem.dagem_gate(x, deformed, linears, bns, training)
+
+
+@contextlib.contextmanager
+def cpu_ops():
+    from km_unet_b200 import ops
+    saved = {n: getattr(ops, n) for n in ("kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dagem_gate")}
+    ops.kanconv2d, ops.kanlinear, ops.layernorm1d = _kanconv2d, _kanlinear, _hsmssd.layernorm1d
+    ops.hsmssd, ops.dysample, ops.dagem_gate = _hsm, _dys, _gate
+    try:
+        yield
+    finally:
+        for n, f in saved.items():
+            setattr(ops, n, f)

@@ -80,3 +80,38 @@ def test_glue_blocks_match_live_reference(name):
             p.add_(torch.randn_like(p) * 0.1)
     ours.load_state_dict(ref.state_dict())
     assert rel_err(ours(x), ref(x)) < 1e-5
+
+
+def test_full_model_cpu_oracle_matches_reference_golden():
+    """oracle/model.py (model mirror glue + the op restatements of oracle/) against the forward of the unmodified
+    reference model: this pins the full-model oracle used for GPU parity, smoke() and the CPU baseline."""
+    from km_unet_b200 import KM_UNetV3_SH
+    from oracle import model as OM
+    g = Golden("km_unetv3_sh_eval_32")
+    m = KM_UNetV3_SH(num_classes=4)
+    m.load_state_dict(g.sd())
+    m.eval()
+    with OM.cpu_ops(), torch.no_grad():
+        y = m(g.t("in0"))
+    assert rel_err(y, g.t("out0")) < 1e-5
+
+
+def test_product_path_raises_on_cpu_outside_the_oracle_context():
+    from km_unet_b200 import KM_UNetV3_SH
+    m = KM_UNetV3_SH(num_classes=4).eval()
+    with pytest.raises(RuntimeError):
+        m(torch.rand(1, 5, 32, 32))
+
+
+def test_hybrid_loss_ssim_properties():
+    from km_unet_b200.loss import HybridLoss, ssim
+    torch.manual_seed(0)
+    a = torch.rand(2, 3, 32, 32)
+    assert abs(ssim(a, a).item() - 1.0) < 1e-6
+    b = torch.rand(2, 3, 32, 32)
+    assert ssim(a, b).item() < 0.2
+    loss = HybridLoss()
+    assert loss(a, a).item() < 1e-6
+    p = b.clone().requires_grad_(True)
+    loss(p, a).backward()
+    assert torch.isfinite(p.grad).all()
