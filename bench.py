@@ -125,6 +125,12 @@ def op_work(name, key):
     if name.startswith("kmu_dagem"):
         B, C, H, W = key
         return ("hbm", (12.0 if name.endswith("fwd") else 20.0) * B * C * H * W, "byte")
+    if name.startswith("kmu_bnmix"):
+        B, C, HW = key                       # fwd: read x (+res) twice (statistics, apply), write y; bwd: x, dy (+res) twice, dx (+dres)
+        return ("hbm", (12.0 if name.endswith("fwd") else 20.0) * B * C * HW, "byte")
+    if name.startswith("kmu_dwconv3x3"):
+        B, C, H, W = key                     # fwd: read x, write y; bwd: read dy (dx), read x and dy (dw), write dx
+        return ("hbm", (8.0 if name.endswith("fwd") else 16.0) * B * C * H * W, "byte")
     return ("hbm", 0.0, "byte")
 
 

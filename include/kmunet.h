@@ -295,6 +295,68 @@ size_t kmu_dagem_bwd_workspace_bytes(const kmu_dagem_desc* d);
 int kmu_dagem_fwd(const kmu_dagem_fwd_args* a, kmu_stream stream);
 int kmu_dagem_bwd(const kmu_dagem_bwd_args* a, kmu_stream stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * S3: EfficientViMBlock shell       vim_block_init/efficient_vim_init.py:82-96, vim_utils_init.py:83-89,128-130
+ *   kmu_bnmix:     y = BN2d(x) [-> ReLU] [-> (1 - sigmoid(alpha_c)) res + sigmoid(alpha_c) y]   (train or eval statistics)
+ *   kmu_dwconv3x3: depthwise 3x3 convolution, stride 1, zero padding 1, optional bias (ConvLayer2D with groups = dim;
+ *                  DirectionAttention.conv, KM_UNetV3_SH.py:223)
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t B, C, HW;
+  int32_t training; /* batch statistics + running-stat update, else running statistics */
+  int32_t relu;     /* ReLU after the affine normalisation */
+  int32_t mix;      /* layer-scale mix with `res` through sigmoid(alpha) */
+  float momentum, eps;
+} kmu_bnmix_desc;
+
+typedef struct {
+  kmu_bnmix_desc d;
+  const float* x;      /* (B,C,HW) */
+  const float* weight; /* (C) gamma */
+  const float* bias;   /* (C) beta */
+  float* running_mean; /* (C) */
+  float* running_var;  /* (C) */
+  const float* res;    /* (B,C,HW) or NULL */
+  const float* alpha;  /* (C) pre-sigmoid layer scale or NULL */
+  float* y;            /* (B,C,HW) */
+  float* stat;         /* (C,2) mean, rstd: input of the backward call */
+  void* workspace;
+  size_t workspace_bytes;
+} kmu_bnmix_fwd_args;
+
+typedef struct {
+  kmu_bnmix_desc d;
+  const float* x;
+  const float* dy;
+  const float* weight;
+  const float* bias;
+  const float* stat;
+  const float* res;
+  const float* alpha;
+  float* dx;
+  float* d_weight;
+  float* d_bias;
+  float* d_res;   /* (B,C,HW) or NULL when !mix */
+  float* d_alpha; /* (C) or NULL when !mix */
+  void* workspace;
+  size_t workspace_bytes;
+} kmu_bnmix_bwd_args;
+
+size_t kmu_bnmix_workspace_bytes(const kmu_bnmix_desc* d);
+int kmu_bnmix_fwd(const kmu_bnmix_fwd_args* a, kmu_stream stream);
+int kmu_bnmix_bwd(const kmu_bnmix_bwd_args* a, kmu_stream stream);
+
+typedef struct {
+  int32_t B, C, H, W;
+} kmu_dwconv3x3_desc;
+
+size_t kmu_dwconv3x3_bwd_workspace_bytes(const kmu_dwconv3x3_desc* d);
+int kmu_dwconv3x3_fwd(const kmu_dwconv3x3_desc* d, const float* x, const float* w /* (C,9) */, const float* bias /* (C) or NULL */,
+                      float* y, kmu_stream stream);
+/* dx, dw (C,9), dbias (C) are overwritten; dx == NULL skips the input gradient, dw == NULL the weight / bias gradients. */
+int kmu_dwconv3x3_bwd(const kmu_dwconv3x3_desc* d, const float* x, const float* dy, const float* w, float* dx, float* dw,
+                      float* dbias, void* workspace, size_t workspace_bytes, kmu_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

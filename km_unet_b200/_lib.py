@@ -85,6 +85,25 @@ class DagemBwdArgs(C.Structure):
                [("d_bn_weight", _f32p * 5), ("d_bn_bias", _f32p * 5), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
+class BnMixDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B", "C", "HW", "training", "relu", "mix")] + [("momentum", C.c_float), ("eps", C.c_float)]
+
+
+class BnMixFwdArgs(C.Structure):
+    _fields_ = [("d", BnMixDesc)] + [(n, _f32p) for n in ("x", "weight", "bias", "running_mean", "running_var", "res", "alpha", "y",
+                                                          "stat")] + [("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+class BnMixBwdArgs(C.Structure):
+    _fields_ = [("d", BnMixDesc)] + [(n, _f32p) for n in ("x", "dy", "weight", "bias", "stat", "res", "alpha", "dx", "d_weight",
+                                                          "d_bias", "d_res", "d_alpha")] + \
+               [("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+class DwDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B", "C", "H", "W")]
+
+
 # every symbol include/kmunet.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "kmu_version": (C.c_int, []),
@@ -110,6 +129,12 @@ SYMBOLS = {
     "kmu_dysample_bwd": (C.c_int, [C.POINTER(DysBwdArgs), C.c_void_p]),
     "kmu_dysample_sample_fwd": (C.c_int, [C.POINTER(DysDesc), _f32p, _f32p, _f32p, C.c_void_p]),
     "kmu_dysample_sample_bwd": (C.c_int, [C.POINTER(DysDesc), _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
+    "kmu_bnmix_workspace_bytes": (C.c_size_t, [C.POINTER(BnMixDesc)]),
+    "kmu_bnmix_fwd": (C.c_int, [C.POINTER(BnMixFwdArgs), C.c_void_p]),
+    "kmu_bnmix_bwd": (C.c_int, [C.POINTER(BnMixBwdArgs), C.c_void_p]),
+    "kmu_dwconv3x3_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(DwDesc)]),
+    "kmu_dwconv3x3_fwd": (C.c_int, [C.POINTER(DwDesc), _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
+    "kmu_dwconv3x3_bwd": (C.c_int, [C.POINTER(DwDesc), _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kmu_dagem_saved_bytes": (C.c_size_t, [C.POINTER(DagemDesc)]),
     "kmu_dagem_fwd_workspace_bytes": (C.c_size_t, [C.POINTER(DagemDesc)]),
     "kmu_dagem_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(DagemDesc)]),

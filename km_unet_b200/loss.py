@@ -11,22 +11,23 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
-def _gaussian_window(size, sigma, device, dtype):
+def _gaussian_taps(size, sigma, device, dtype):
     d = torch.arange((1 - size) / 2, (1 + size) / 2, 1, device=device, dtype=dtype)
     g = torch.exp(-(d / sigma) ** 2 / 2)
-    g = (g / g.sum()).unsqueeze(0)
-    return g.t() @ g
+    return g / g.sum()
 
 
 def ssim(pred, target, data_range=1.0, size=11, sigma=1.5, k1=0.01, k2=0.03):
     C = pred.shape[1]
     c1, c2 = (k1 * data_range) ** 2, (k2 * data_range) ** 2
     pad = (size - 1) // 2
-    win = _gaussian_window(size, sigma, pred.device, pred.dtype).expand(C, 1, size, size)
+    g = _gaussian_taps(size, sigma, pred.device, pred.dtype)       # the 2-D window is the outer product: filter separably
     p = F.pad(pred, (pad, pad, pad, pad), mode="reflect")
     t = F.pad(target, (pad, pad, pad, pad), mode="reflect")
     stack = torch.cat([p, t, p * p, t * t, p * t])
-    out = F.conv2d(stack, win, groups=C)
+    n, _, hp, wp = stack.shape
+    flat = stack.reshape(n * C, 1, hp, wp)
+    out = F.conv2d(F.conv2d(flat, g.view(1, 1, size, 1)), g.view(1, 1, 1, size)).reshape(n, C, hp - 2 * pad, wp - 2 * pad)
     mu_p, mu_t, pp, tt, pt = out.split(pred.shape[0])
     s_p, s_t, s_pt = pp - mu_p * mu_p, tt - mu_t * mu_t, pt - mu_p * mu_t
     m = ((2 * mu_p * mu_t + c1) * (2 * s_pt + c2)) / ((mu_p * mu_p + mu_t * mu_t + c1) * (s_p + s_t + c2))

@@ -18,6 +18,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import ops
 from .dagem import DAGEM
 from .dysample import DySample
 from .kan import KANConv2d
@@ -77,7 +78,7 @@ class DirectionAttention(nn.Module):
         # the three pooling modes of the reference (mean over W then H, over H then W, or both) are the same global mean
         weight = self.fc(x.mean(dim=(2, 3)))
         q, k, v = self.qkv(x).chunk(3, dim=1)
-        return self.conv(torch.sigmoid(q * k) * v) * weight[:, :, None, None]
+        return ops.dwconv3x3(torch.sigmoid(q * k) * v, self.conv.weight, self.conv.bias) * weight[:, :, None, None]
 
 
 class DirectionViM(nn.Module):

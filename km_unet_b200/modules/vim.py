@@ -1,8 +1,8 @@
 """EfficientViM building blocks with the reference's names, constructor signatures and state_dict layout
 (vim_block_init/vim_utils_init.py:34-130, vim_block_init/efficient_vim_init.py:14-97).
 
-LayerNorm1D and the HSM-SSD mixer run in libkmunet.so.  The depthwise-conv/BatchNorm/FFN shell of the block is still
-composed from torch.nn modules in this round (SURVEY section 8f rank 2 -- next to be fused).
+LayerNorm1D, the HSM-SSD mixer, the depthwise 3x3 convolutions and every BatchNorm of the block (with its ReLU /
+sigmoid-layer-scale epilogue) run in libkmunet.so; the two 1x1 FFN convolutions are cuDNN library GEMMs.
 """
 import torch
 import torch.nn as nn
@@ -69,6 +69,15 @@ class _ConvLayer(nn.Module):
         return x
 
 
+def _bn2d(bn, x, relu=False, res=None, alpha=None):
+    """BatchNorm2d module `bn` applied through the fused CUDA op (keeps the module's parameters, buffers and counters)."""
+    training = bn.training or bn.running_mean is None
+    y = ops.bnmix(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, bn.momentum, bn.eps, relu, res, alpha)
+    if bn.training and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    return y
+
+
 class ConvLayer2D(_ConvLayer):
     def __init__(self, in_dim, out_dim, kernel_size=3, stride=1, padding=0, dilation=1, groups=1, norm=nn.BatchNorm2d,
                  act_layer=nn.ReLU, bn_weight_init=1):
@@ -76,6 +85,26 @@ class ConvLayer2D(_ConvLayer):
         self.conv = nn.Conv2d(in_dim, out_dim, (kernel_size, kernel_size), (stride, stride), (padding, padding),
                               (dilation, dilation), groups, bias=False)
         self._finish(out_dim, norm, act_layer, bn_weight_init)
+        self._dw3 = (kernel_size == 3 and stride == 1 and padding == 1 and dilation == 1 and groups == in_dim == out_dim)
+
+    def conv_out(self, x):
+        return ops.dwconv3x3(x, self.conv.weight) if self._dw3 else self.conv(x)
+
+    def forward(self, x, res=None, alpha=None):
+        """conv -> norm -> act; with res/alpha the block's layer-scale mix is fused into the normalisation."""
+        x = self.conv_out(x)
+        fusable = isinstance(self.norm, nn.BatchNorm2d) and (self.act is None or isinstance(self.act, nn.ReLU)) \
+            and self.norm.affine and self.norm.momentum is not None
+        if fusable:
+            return _bn2d(self.norm, x, relu=self.act is not None, res=res, alpha=alpha)
+        if self.norm:
+            x = self.norm(x)
+        if self.act:
+            x = self.act(x)
+        if res is not None:
+            a = torch.sigmoid(alpha).view(1, -1, 1, 1)
+            x = (1 - a) * res + a * x
+        return x
 
 
 class ConvLayer1D(_ConvLayer):
@@ -92,8 +121,8 @@ class FFN(nn.Module):
         self.fc1 = ConvLayer2D(in_dim, dim, 1)
         self.fc2 = ConvLayer2D(dim, in_dim, 1, act_layer=None, bn_weight_init=0)
 
-    def forward(self, x):
-        return self.fc2(self.fc1(x))
+    def forward(self, x, res=None, alpha=None):
+        return self.fc2(self.fc1(x), res, alpha)
 
 
 class HSMSSD(nn.Module):
@@ -134,10 +163,10 @@ class EfficientViMBlock(nn.Module):
         self.alpha = nn.Parameter(1e-4 * torch.ones(4, dim), requires_grad=True)
 
     def forward(self, x):
-        a = torch.sigmoid(self.alpha).view(4, -1, 1, 1)
-        x = (1 - a[0]) * x + a[0] * self.dwconv1(x)
+        # x <- (1 - sigmoid(alpha_i)) x + sigmoid(alpha_i) f_i(x): the mix of the three conv branches is the epilogue of
+        # their BatchNorm kernel; the mixer's is one lerp
+        x = self.dwconv1(x, res=x, alpha=self.alpha[0])
         mixed, _ = self.mixer(self.norm(x.flatten(2)))
-        x = (1 - a[1]) * x + a[1] * mixed
-        x = (1 - a[2]) * x + a[2] * self.dwconv2(x)
-        x = (1 - a[3]) * x + a[3] * self.ffn(x)
-        return x
+        x = torch.lerp(x, mixed, torch.sigmoid(self.alpha[1]).view(1, -1, 1, 1))
+        x = self.dwconv2(x, res=x, alpha=self.alpha[2])
+        return self.ffn(x, res=x, alpha=self.alpha[3])

@@ -9,10 +9,10 @@ import torch
 from torch.amp import custom_bwd, custom_fwd
 
 from . import _lib
-from ._lib import (DagemBn, DagemBwdArgs, DagemDesc, DagemFwdArgs, DysBwdArgs, DysDesc, DysFwdArgs, HsmBwdArgs, HsmDesc, HsmFwdArgs, KanBwdArgs, KanDesc, KanFwdArgs,
+from ._lib import (BnMixBwdArgs, BnMixDesc, BnMixFwdArgs, DwDesc, DagemBn, DagemBwdArgs, DagemDesc, DagemFwdArgs, DysBwdArgs, DysDesc, DysFwdArgs, HsmBwdArgs, HsmDesc, HsmFwdArgs, KanBwdArgs, KanDesc, KanFwdArgs,
                    KMU_PREC_BF16, KMU_PREC_FP32, check, ptr, stream_ptr)
 
-__all__ = ["kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dysample_sample", "dagem_gate", "KMU_PREC_FP32", "KMU_PREC_BF16"]
+__all__ = ["kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dysample_sample", "dagem_gate", "bnmix", "dwconv3x3", "KMU_PREC_FP32", "KMU_PREC_BF16"]
 
 
 # ------------------------------------------------------------------------------------------------------ op-level timing
@@ -388,3 +388,98 @@ def dagem_gate(x, deformed, linears, bns, training, momentum=0.1, eps=1e-5):
         flat += [w, b]
     running = [(rm, rv) for _, _, rm, rv in bns]
     return _DagemGateFn.apply(x, deformed, *linears, *flat, running, bool(training), momentum, eps)
+
+
+# ------------------------------------------------------------------------------------------------------ EfficientViMBlock shell
+class _BnMixFn(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, weight, bias, res, alpha, running_mean, running_var, training, momentum, eps, relu):
+        lib = _lib.lib()
+        x = x.contiguous()
+        B, Cc = x.shape[0], x.shape[1]
+        HW = x.numel() // (B * Cc)
+        mix = res is not None
+        desc = BnMixDesc(B, Cc, HW, 1 if training else 0, 1 if relu else 0, 1 if mix else 0, float(momentum), float(eps))
+        w, b = weight.contiguous(), bias.contiguous()
+        r = res.contiguous() if mix else None
+        al = alpha.contiguous() if mix else None
+        y = torch.empty_like(x)
+        stat = torch.empty(Cc, 2, dtype=torch.float32, device=x.device)
+        ws = _workspace(lib.kmu_bnmix_workspace_bytes(C.byref(desc)), x.device)
+        args = BnMixFwdArgs(desc, ptr(x), ptr(w), ptr(b), ptr(running_mean), ptr(running_var), ptr(r), ptr(al), ptr(y), ptr(stat),
+                            ws.data_ptr(), ws.numel())
+        check(_call("kmu_bnmix_fwd", (B, Cc, HW), lib.kmu_bnmix_fwd, C.byref(args), stream_ptr()), "kmu_bnmix_fwd")
+        ctx.save_for_backward(x, w, b, stat, r, al)
+        ctx.desc = desc
+        return y
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        lib = _lib.lib()
+        x, w, b, stat, r, al = ctx.saved_tensors
+        desc = ctx.desc
+        dy = dy.to(torch.float32).contiguous()
+        dx = torch.empty_like(x)
+        dw, db = torch.empty_like(w), torch.empty_like(b)
+        dres = torch.empty_like(x) if desc.mix else None
+        dal = torch.empty_like(al) if desc.mix else None
+        ws = _workspace(lib.kmu_bnmix_workspace_bytes(C.byref(desc)), x.device)
+        args = BnMixBwdArgs(desc, ptr(x), ptr(dy), ptr(w), ptr(b), ptr(stat), ptr(r), ptr(al), ptr(dx), ptr(dw), ptr(db), ptr(dres),
+                            ptr(dal), ws.data_ptr(), ws.numel())
+        check(_call("kmu_bnmix_bwd", (desc.B, desc.C, desc.HW), lib.kmu_bnmix_bwd, C.byref(args), stream_ptr()), "kmu_bnmix_bwd")
+        return dx, dw, db, dres, dal, None, None, None, None, None, None
+
+
+def bnmix(x, weight, bias, running_mean, running_var, training, momentum=0.1, eps=1e-5, relu=False, res=None, alpha=None):
+    """BatchNorm2d (batch statistics when `training`, running-stat update in place) with the fused epilogues of the
+    EfficientViMBlock shell: ReLU (ffn.fc1) or the layer-scale mix (1 - sigmoid(alpha)) res + sigmoid(alpha) BN(x)
+    (vim_block_init/efficient_vim_init.py:85,93,96).  alpha is the raw (pre-sigmoid) (C,) row."""
+    if not x.is_cuda:
+        raise RuntimeError("km_unet_b200.bnmix: CUDA tensors only (no CPU fallback)")
+    if (res is None) != (alpha is None):
+        raise ValueError("bnmix: res and alpha go together")
+    return _BnMixFn.apply(x, weight, bias, res, alpha, running_mean, running_var, bool(training), momentum, eps, bool(relu))
+
+
+class _DwConv3x3Fn(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, weight, bias):
+        lib = _lib.lib()
+        x = x.contiguous()
+        B, Cc, H, W = x.shape
+        desc = DwDesc(B, Cc, H, W)
+        w = weight.reshape(Cc, 9).contiguous()
+        b = None if bias is None else bias.contiguous()
+        y = torch.empty_like(x)
+        check(_call("kmu_dwconv3x3_fwd", (B, Cc, H, W), lib.kmu_dwconv3x3_fwd, C.byref(desc), ptr(x), ptr(w), ptr(b), ptr(y),
+                    stream_ptr()), "kmu_dwconv3x3_fwd")
+        ctx.save_for_backward(x, w)
+        ctx.desc, ctx.has_bias, ctx.wshape = desc, bias is not None, weight.shape
+        return y
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        lib = _lib.lib()
+        x, w = ctx.saved_tensors
+        desc = ctx.desc
+        dy = dy.to(torch.float32).contiguous()
+        need_x = ctx.needs_input_grad[0]
+        need_w = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
+        dx = torch.empty_like(x) if need_x else None
+        dw = torch.empty_like(w) if need_w else None
+        db = torch.empty(desc.C, dtype=torch.float32, device=x.device) if (need_w and ctx.has_bias) else None
+        ws = _workspace(lib.kmu_dwconv3x3_bwd_workspace_bytes(C.byref(desc)), x.device)
+        check(_call("kmu_dwconv3x3_bwd", (desc.B, desc.C, desc.H, desc.W), lib.kmu_dwconv3x3_bwd, C.byref(desc), ptr(x), ptr(dy), ptr(w),
+                    ptr(dx), ptr(dw), ptr(db), ws.data_ptr(), ws.numel(), stream_ptr()), "kmu_dwconv3x3_bwd")
+        return dx, None if dw is None else dw.reshape(ctx.wshape), db
+
+
+def dwconv3x3(x, weight, bias=None):
+    """Depthwise 3x3 convolution, stride 1, zero padding 1: weight (C,1,3,3), optional bias (C)."""
+    if not x.is_cuda:
+        raise RuntimeError("km_unet_b200.dwconv3x3: CUDA tensors only (no CPU fallback)")
+    return _DwConv3x3Fn.apply(x, weight, bias)

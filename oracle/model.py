@@ -34,6 +34,24 @@ def _dys(x, w_offset, b_offset, init_pos, scale=2, groups=4):
     return _dysample.dysample_lp(x, w_offset, b_offset, init_pos)
 
 
+def _bnmix(x, weight, bias, running_mean, running_var, training, momentum=0.1, eps=1e-5, relu=False, res=None, alpha=None):
+    """vim_utils_init.py:83-89 (BatchNorm2d inside ConvLayer2D) + efficient_vim_init.py:82-96 (sigmoid layer-scale mix)."""
+    import torch
+    import torch.nn.functional as F
+    y = F.batch_norm(x, running_mean, running_var, weight, bias, training, momentum, eps)
+    if relu:
+        y = F.relu(y)
+    if res is not None:
+        a = torch.sigmoid(alpha).view(1, -1, 1, 1)
+        y = (1 - a) * res + a * y
+    return y
+
+
+def _dwconv3x3(x, weight, bias=None):
+    import torch.nn.functional as F
+    return F.conv2d(x, weight, bias, stride=1, padding=1, groups=x.shape[1])
+
+
 def _gate(x, deformed, linears, bns, training, momentum=0.1, eps=1e-5):
     return _dagem.dagem_gate(x, deformed, linears, bns, training)
 
@@ -41,9 +59,11 @@ def _gate(x, deformed, linears, bns, training, momentum=0.1, eps=1e-5):
 @contextlib.contextmanager
 def cpu_ops():
     from km_unet_b200 import ops
-    saved = {n: getattr(ops, n) for n in ("kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dagem_gate")}
+    saved = {n: getattr(ops, n) for n in ("kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dagem_gate", "bnmix",
+                                          "dwconv3x3")}
     ops.kanconv2d, ops.kanlinear, ops.layernorm1d = _kanconv2d, _kanlinear, _hsmssd.layernorm1d
     ops.hsmssd, ops.dysample, ops.dagem_gate = _hsm, _dys, _gate
+    ops.bnmix, ops.dwconv3x3 = _bnmix, _dwconv3x3
     try:
         yield
     finally:

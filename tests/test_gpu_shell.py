@@ -1,0 +1,84 @@
+"""GPU parity of the EfficientViMBlock shell ops (kmu_bnmix, kmu_dwconv3x3) against torch fp64 autograd of the same
+arithmetic (vim_utils_init.py:83-89 BatchNorm2d inside ConvLayer2D; efficient_vim_init.py:82-96 layer-scale mix)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _ref_bnmix(x, w, b, rm, rv, training, relu, res, alpha):
+    y = F.batch_norm(x, rm, rv, w, b, training, 0.1, 1e-5)
+    if relu:
+        y = F.relu(y)
+    if res is not None:
+        a = torch.sigmoid(alpha).view(1, -1, 1, 1)
+        y = (1 - a) * res + a * y
+    return y
+
+
+@pytest.mark.parametrize("B,C,H,W,training,relu,mix", [
+    (4, 16, 32, 32, True, False, True), (2, 64, 16, 16, True, True, False), (3, 8, 5, 7, True, False, True),
+    (2, 16, 8, 8, False, False, True), (2, 32, 12, 12, False, True, False), (32, 16, 128, 128, True, False, True)])
+def test_bnmix_vs_torch(B, C, H, W, training, relu, mix):
+    from km_unet_b200 import ops
+    torch.manual_seed(C + H)
+    x = torch.randn(B, C, H, W) * 1.7 + 0.4
+    w, b = torch.rand(C) + 0.5, torch.randn(C) * 0.2
+    rm, rv = torch.randn(C) * 0.1, torch.rand(C) + 0.5
+    res = torch.randn(B, C, H, W) if mix else None
+    alpha = torch.randn(C) if mix else None
+    gout = torch.randn(B, C, H, W)
+    dbl = lambda t: None if t is None else t.double().requires_grad_(True)
+    xd, wd, bd, rd, ad = dbl(x), dbl(w), dbl(b), dbl(res), dbl(alpha)
+    rm_ref, rv_ref = rm.double().clone(), rv.double().clone()
+    want = _ref_bnmix(xd, wd, bd, rm_ref, rv_ref, training, relu, rd, ad)
+    want.backward(gout.double())
+    cu = lambda t: None if t is None else t.cuda().requires_grad_(True)
+    xc, wc, bc, rc, ac = cu(x), cu(w), cu(b), cu(res), cu(alpha)
+    rmc, rvc = rm.cuda(), rv.cuda()
+    y = ops.bnmix(xc, wc, bc, rmc, rvc, training, 0.1, 1e-5, relu, rc, ac)
+    assert rel_err(y, want) < TOL
+    y.backward(gout.cuda())
+    assert rel_err(xc.grad, xd.grad) < TOL
+    assert rel_err(wc.grad, wd.grad) < TOL
+    assert rel_err(bc.grad, bd.grad) < TOL
+    if mix:
+        assert rel_err(rc.grad, rd.grad) < TOL
+        assert rel_err(ac.grad, ad.grad) < TOL
+    assert rel_err(rmc, rm_ref) < TOL and rel_err(rvc, rv_ref) < TOL
+
+
+@pytest.mark.parametrize("B,C,H,W,bias", [(2, 16, 32, 32, False), (3, 8, 7, 5, True), (1, 64, 16, 16, True), (4, 16, 128, 128, False),
+                                          (2, 4, 1, 1, True)])
+def test_dwconv3x3_vs_torch(B, C, H, W, bias):
+    from km_unet_b200 import ops
+    torch.manual_seed(H * W + C)
+    x = torch.randn(B, C, H, W)
+    w = torch.randn(C, 1, 3, 3) * 0.4
+    bv = torch.randn(C) if bias else None
+    gout = torch.randn(B, C, H, W)
+    xd, wd = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    bd = bv.double().requires_grad_(True) if bias else None
+    want = F.conv2d(xd, wd, bd, padding=1, groups=C)
+    want.backward(gout.double())
+    xc, wc = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+    bc = bv.cuda().requires_grad_(True) if bias else None
+    y = ops.dwconv3x3(xc, wc, bc)
+    assert rel_err(y, want) < TOL
+    y.backward(gout.cuda())
+    assert rel_err(xc.grad, xd.grad) < TOL
+    assert rel_err(wc.grad, wd.grad) < TOL
+    if bias:
+        assert rel_err(bc.grad, bd.grad) < TOL
+
+
+def test_shell_ops_raise_on_cpu():
+    from km_unet_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.dwconv3x3(torch.randn(1, 4, 4, 4), torch.randn(4, 1, 3, 3))
+    with pytest.raises(RuntimeError):
+        ops.bnmix(torch.randn(1, 4, 4, 4), torch.ones(4), torch.zeros(4), torch.zeros(4), torch.ones(4), True)

@@ -79,7 +79,10 @@ def test_glue_blocks_match_live_reference(name):
         for p in ref.parameters():
             p.add_(torch.randn_like(p) * 0.1)
     ours.load_state_dict(ref.state_dict())
-    assert rel_err(ours(x), ref(x)) < 1e-5
+    from oracle import model as OM
+    with OM.cpu_ops():
+        got = ours(x)
+    assert rel_err(got, ref(x)) < 1e-5
 
 
 def test_full_model_cpu_oracle_matches_reference_golden():
