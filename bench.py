@@ -131,6 +131,9 @@ def op_work(name, key):
     if name.startswith("kmu_dwconv3x3"):
         B, C, H, W = key                     # fwd: read x, write y; bwd: read dy (dx), read x and dy (dw), write dx
         return ("hbm", (8.0 if name.endswith("fwd") else 16.0) * B * C * H * W, "byte")
+    if name.startswith("kmu_pwconv"):
+        B, Cin, Cout, HW = key               # fwd: read x, write y; bwd: read dy (dx) + x and dy (dw), write dx
+        return ("hbm", (4.0 * (Cin + Cout) if name.endswith("fwd") else 4.0 * (2 * Cin + 2 * Cout)) * B * HW, "byte")
     return ("hbm", 0.0, "byte")
 
 
@@ -403,10 +406,18 @@ def run_model(h, args):
         live = [p for p in model.parameters() if p.grad is not None]
         for p in model.parameters():
             p.grad = None
-        opt = torch.optim.AdamW(live, lr=1e-3, weight_decay=0.05, fused=True)
-        reducer = BucketedGradAllReduce(live, bucket_bytes=2 << 20) if world > 1 else None
+        opt = torch.optim.AdamW(live, lr=1e-3, weight_decay=0.05, fused=True, capturable=args.graph)
+        reducer = BucketedGradAllReduce(live, bucket_bytes=2 << 20) if (world > 1 and not args.graph) else None
+    graphed, graphed_launches = None, 0
+    if train and args.graph:
+        from km_unet_b200.train import GraphedTrainStep
+        l0 = _lib.launch_count()
+        graphed = GraphedTrainStep(model, crit, opt, x_dev, t_dev, world=world, warmup=3)
+        graphed_launches = (_lib.launch_count() - l0) // 4          # 3 eager warm-up steps + the captured one
 
     def train_step(x, t):
+        if graphed is not None:
+            return graphed(None if x is x_dev else x, None if t is t_dev else t)
         opt.zero_grad(set_to_none=True)
         loss = crit(model(x), t)
         loss.backward()
@@ -458,6 +469,8 @@ def run_model(h, args):
     launches0 = _lib.launch_count()
     total_ms = h.timed(step_resident, args.steps, args.warmup)
     launches = (_lib.launch_count() - launches0) // (args.steps + args.warmup)
+    if graphed is not None:
+        launches = graphed_launches            # replays do not pass through the host-side counter: count of the captured step
     clocks = sampler.stop() if sampler else None
     value = world * B * args.steps / (total_ms / 1e3)
     e2e_ms = h.timed(step_e2e, args.steps, args.warmup)
@@ -465,10 +478,20 @@ def run_model(h, args):
 
     # op-level profile of the same step: CUDA events on the launching stream around every libkmunet call
     prof_steps = 3
-    step_resident()
+
+    def eager_step():
+        if not train:
+            return infer_step(x_dev)
+        opt.zero_grad(set_to_none=True)
+        loss = crit(model(x_dev), t_dev)
+        loss.backward()
+        opt.step()
+        return loss
+
+    eager_step()
     ops.profile_start()
     for _ in range(prof_steps):
-        step_resident()
+        eager_step()
     prof = ops.profile_stop()
     peaks = load_peaks()
     table = []
@@ -488,7 +511,7 @@ def run_model(h, args):
                 "unit": dom["unit"], "frac": dom["frac"], "traffic": None,
                 "peak_source": peaks["source"] + (" HBM copy" if dom["bound"] == "hbm" else " bf16 sustained"),
                 "share_of_step": dom["ms_per_step"] / (total_ms / args.steps),
-                "libkmunet_ms_per_step": ours_ms, "torch_glue_ms_per_step": total_ms / args.steps - ours_ms, "ops": table[:12]}
+                "libkmunet_ms_per_step": ours_ms, "library_and_glue_ms_per_step": total_ms / args.steps - ours_ms, "ops": table[:12]}
 
     kan = kan_microbench(h, 32, 5, 3, args.precision) if not args.no_kan_microbench else None
     cpu = None
@@ -506,9 +529,9 @@ def run_model(h, args):
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * world, "frames": f"{fin}->{classes}",
                        "size": size, "precision": f"KANConv2d {args.precision} (tcgen05) / everything else fp32",
-                       "parallelism": f"dp{world}", "optimizer": "AdamW(lr 1e-3, wd 0.05, fused)" if train else None,
+                       "parallelism": f"dp{world}", "cuda_graph": bool(graphed is not None), "optimizer": "AdamW(lr 1e-3, wd 0.05, fused)" if train else None,
                        "l2": "activations per step (hundreds of %.0f MB tensors) exceed the 126 MB L2" % (B * 16 * size * size * 4 / 1e6),
-                       "grad_allreduce": (f"bucketed NCCL from grad hooks, {nlive * 4 / 1e6:.1f} MB" if world > 1 else "none (1 GPU)")},
+                       "grad_allreduce": (f"bucketed NCCL, {nlive * 4 / 1e6:.1f} MB" if world > 1 else "none (1 GPU)")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": batch_host.numel() * 4, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "kan_microbench": kan,
@@ -527,6 +550,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("KMU_KAN_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kan-microbench", action="store_true")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="run the training step eagerly instead of as CUDA graphs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 1)
     if args.impl == "reference":

@@ -357,6 +357,21 @@ int kmu_dwconv3x3_fwd(const kmu_dwconv3x3_desc* d, const float* x, const float* 
 int kmu_dwconv3x3_bwd(const kmu_dwconv3x3_desc* d, const float* x, const float* dy, const float* w, float* dx, float* dw,
                       float* dbias, void* workspace, size_t workspace_bytes, kmu_stream stream);
 
+/* Pointwise (1x1) convolution on NCHW: y[b,o,p] = bias[o] + sum_c w[o,c] x[b,c,p]   (vim_utils_init.py:122-130 FFN,
+ * KM_UNetV3_SH.py:59,118-122,178,221).  The weight gradient kernel needs Cin a power of two in [16,1024] and
+ * Cout <= 16*1024/Cin (kmu_pwconv_wgrad_supported); forward and input gradient take any channel counts. */
+typedef struct {
+  int32_t B, Cin, Cout, HW;
+} kmu_pwconv_desc;
+
+int kmu_pwconv_wgrad_supported(const kmu_pwconv_desc* d);
+size_t kmu_pwconv_bwd_workspace_bytes(const kmu_pwconv_desc* d);
+int kmu_pwconv_fwd(const kmu_pwconv_desc* d, const float* x, const float* w /* (Cout,Cin) */, const float* bias /* (Cout) or NULL */,
+                   float* y, kmu_stream stream);
+/* dx, dw (Cout,Cin), dbias (Cout) are overwritten; NULL dx skips the input gradient, NULL dw the weight / bias gradients. */
+int kmu_pwconv_bwd(const kmu_pwconv_desc* d, const float* x, const float* dy, const float* w, float* dx, float* dw, float* dbias,
+                   void* workspace, size_t workspace_bytes, kmu_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

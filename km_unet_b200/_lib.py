@@ -104,6 +104,10 @@ class DwDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("B", "C", "H", "W")]
 
 
+class PwDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B", "Cin", "Cout", "HW")]
+
+
 # every symbol include/kmunet.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "kmu_version": (C.c_int, []),
@@ -135,6 +139,10 @@ SYMBOLS = {
     "kmu_dwconv3x3_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(DwDesc)]),
     "kmu_dwconv3x3_fwd": (C.c_int, [C.POINTER(DwDesc), _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
     "kmu_dwconv3x3_bwd": (C.c_int, [C.POINTER(DwDesc), _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kmu_pwconv_wgrad_supported": (C.c_int, [C.POINTER(PwDesc)]),
+    "kmu_pwconv_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(PwDesc)]),
+    "kmu_pwconv_fwd": (C.c_int, [C.POINTER(PwDesc), _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
+    "kmu_pwconv_bwd": (C.c_int, [C.POINTER(PwDesc), _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kmu_dagem_saved_bytes": (C.c_size_t, [C.POINTER(DagemDesc)]),
     "kmu_dagem_fwd_workspace_bytes": (C.c_size_t, [C.POINTER(DagemDesc)]),
     "kmu_dagem_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(DagemDesc)]),

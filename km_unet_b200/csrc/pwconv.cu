@@ -1,0 +1,241 @@
+// pwconv.cu -- pointwise (1x1) convolution on NCHW tensors, forward / input gradient / weight+bias gradient.
+//
+// The EfficientViMBlock FFN (vim_utils_init.py:122-130: 1x1 C->4C, 1x1 4C->C), DirectionAttention.qkv (KM_UNetV3_SH.py:221),
+// the EnhancedViMBlock FFN (:118-122), DirectionViM.proj in 'channel' mode (:178) and StableHybridKANConv.residual (:59) are
+// all y[b,o,p] = bias[o] + sum_c W[o,c] x[b,c,p] with 16..256 channels on 1k..16k pixels: a few hundred FLOP per byte moved
+// at most, i.e. HBM-bound streaming.  cuDNN runs them as NHWC implicit GEMMs bracketed by two layout-transposing kernels
+// per call; here the NCHW planes are read as they lie (pixel-contiguous, coalesced), the weights sit in shared memory
+// and every thread keeps a 2-pixel x 32-output register tile.  The weight gradient is a pixel reduction: persistent
+// CTAs keep their Cout x Cin partial in registers across all their pixel tiles and a second kernel folds the partials in
+// a fixed order (deterministic, no atomics).  fp32 FMA throughout: matches the reference's fp32 modules to rounding.
+#include "common.cuh"
+
+namespace kmu {
+namespace pw {
+
+constexpr int OT = 32;   // outputs per thread pass
+constexpr int NTH = 128; // threads per CTA (forward / dgrad); each thread owns 2 pixels
+
+// y[b, j0+j, p] = bias[j0+j] + sum_i Wt[i][j] in[b, i, p]; Wt[i][j] = W[j*NI + i] (forward) or W[i*NJ_total + j] (dgrad: in = dy)
+// grid (ceil(HW / (2*NTH)), ceil(NJ/OT), B)
+__global__ void __launch_bounds__(NTH) pw_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                 const float* __restrict__ bias, float* __restrict__ out, int NI, int NJ, int HW,
+                                                 int dgrad) {
+  extern __shared__ __align__(16) float w_s[];  // [NI][OT]
+  const int j0 = blockIdx.y * OT;
+  for (int i = threadIdx.x; i < NI * OT; i += NTH) {
+    int ii = i / OT, j = i - ii * OT;
+    float v = 0.f;
+    if (j0 + j < NJ) v = dgrad ? w[(size_t)ii * NJ + j0 + j] : w[(size_t)(j0 + j) * NI + ii];
+    w_s[i] = v;
+  }
+  __syncthreads();
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * (2 * NTH) + threadIdx.x, p1 = p0 + NTH;
+  const bool ok0 = p0 < HW, ok1 = p1 < HW;
+  const float* ib = in + (size_t)b * NI * HW;
+  float a0[OT], a1[OT];
+#pragma unroll
+  for (int j = 0; j < OT; ++j) {
+    float bv = (bias && j0 + j < NJ) ? __ldg(bias + j0 + j) : 0.f;
+    a0[j] = bv;
+    a1[j] = bv;
+  }
+#pragma unroll 4
+  for (int i = 0; i < NI; ++i) {
+    const float x0 = ok0 ? __ldg(ib + (size_t)i * HW + p0) : 0.f;
+    const float x1 = ok1 ? __ldg(ib + (size_t)i * HW + p1) : 0.f;
+    const float4* w4 = reinterpret_cast<const float4*>(w_s + i * OT);
+#pragma unroll
+    for (int q = 0; q < OT / 4; ++q) {
+      const float4 ww = w4[q];
+      a0[4 * q + 0] = fmaf(ww.x, x0, a0[4 * q + 0]); a1[4 * q + 0] = fmaf(ww.x, x1, a1[4 * q + 0]);
+      a0[4 * q + 1] = fmaf(ww.y, x0, a0[4 * q + 1]); a1[4 * q + 1] = fmaf(ww.y, x1, a1[4 * q + 1]);
+      a0[4 * q + 2] = fmaf(ww.z, x0, a0[4 * q + 2]); a1[4 * q + 2] = fmaf(ww.z, x1, a1[4 * q + 2]);
+      a0[4 * q + 3] = fmaf(ww.w, x0, a0[4 * q + 3]); a1[4 * q + 3] = fmaf(ww.w, x1, a1[4 * q + 3]);
+    }
+  }
+  float* ob = out + (size_t)b * NJ * HW;
+#pragma unroll
+  for (int j = 0; j < OT; ++j) {
+    if (j0 + j < NJ) {
+      if (ok0) ob[(size_t)(j0 + j) * HW + p0] = a0[j];
+      if (ok1) ob[(size_t)(j0 + j) * HW + p1] = a1[j];
+    }
+  }
+}
+
+// ---- weight / bias gradient.  dW[o][c] = sum_{b,p} dy[b,o,p] x[b,c,p], db[o] = sum dy.
+// CTA = 256 threads = TC (= Cin/4) threads along c x TO (= 256/TC) along o; thread tile = NO outputs x 4 inputs, kept in
+// registers across all the CTA's pixel tiles of TP pixels.  partial[cta][Cout*Cin + Cout].
+constexpr int TP = 32;
+template <int NO>
+__global__ void __launch_bounds__(256) pw_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                       float* __restrict__ partial, int Cin, int Cout, int HW, int B, int ntiles) {
+  extern __shared__ __align__(16) float smem[];
+  const int XP = Cin + 4, YP = NO * (1024 / Cin) + 4;   // row pitches ([pixel][channel], padded, 16-byte aligned)
+  float* x_s = smem;            // [TP][XP]
+  float* y_s = x_s + TP * XP;   // [TP][YP]   (channel index = to*NO + k)
+  const int TC = Cin >> 2, tid = threadIdx.x;
+  const int tc = tid % TC, to = tid / TC;
+  const int o0 = to * NO;
+  float acc[NO][4], bacc[NO];
+#pragma unroll
+  for (int k = 0; k < NO; ++k) {
+    bacc[k] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[k][e] = 0.f;
+  }
+  const int tiles_per_img = (HW + TP - 1) / TP;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int b = tile / tiles_per_img, p0 = (tile - b * tiles_per_img) * TP;
+    __syncthreads();
+    for (int i = tid; i < Cin * TP; i += 256) {
+      int c = i / TP, p = i - c * TP;
+      x_s[p * XP + c] = (p0 + p < HW) ? __ldg(x + ((size_t)b * Cin + c) * HW + p0 + p) : 0.f;
+    }
+    const int OC = NO * (1024 / Cin);  // outputs covered by the thread grid (>= Cout)
+    for (int i = tid; i < OC * TP; i += 256) {
+      int o = i / TP, p = i - o * TP;
+      y_s[p * YP + o] = (o < Cout && p0 + p < HW) ? __ldg(dy + ((size_t)b * Cout + o) * HW + p0 + p) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int p = 0; p < TP; ++p) {
+      const float4 xv = *reinterpret_cast<const float4*>(x_s + p * XP + 4 * tc);
+      float g[NO];
+      if (NO >= 4) {
+#pragma unroll
+        for (int q = 0; q < NO / 4; ++q) {
+          const float4 t = *reinterpret_cast<const float4*>(y_s + p * YP + o0 + 4 * q);
+          g[4 * q] = t.x; g[4 * q + 1] = t.y; g[4 * q + 2] = t.z; g[4 * q + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < NO; ++k) g[k] = y_s[p * YP + o0 + k];
+      }
+#pragma unroll
+      for (int k = 0; k < NO; ++k) {
+        acc[k][0] = fmaf(g[k], xv.x, acc[k][0]);
+        acc[k][1] = fmaf(g[k], xv.y, acc[k][1]);
+        acc[k][2] = fmaf(g[k], xv.z, acc[k][2]);
+        acc[k][3] = fmaf(g[k], xv.w, acc[k][3]);
+        bacc[k] += g[k];
+      }
+    }
+  }
+  float* pb = partial + (size_t)blockIdx.x * ((size_t)Cout * Cin + Cout);
+#pragma unroll
+  for (int k = 0; k < NO; ++k) {
+    const int o = o0 + k;
+    if (o < Cout) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) pb[(size_t)o * Cin + 4 * tc + e] = acc[k][e];
+      if (tc == 0) pb[(size_t)Cout * Cin + o] = bacc[k];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) pw_wreduce_kernel(const float* __restrict__ partial, int nparts, int n_w, int n_b,
+                                                         float* __restrict__ dw, float* __restrict__ db) {
+  int idx = blockIdx.x * 128 + threadIdx.x;
+  if (idx >= n_w + n_b) return;
+  float s = 0.f;
+  for (int k = 0; k < nparts; ++k) s += partial[(size_t)k * (n_w + n_b) + idx];
+  if (idx < n_w) dw[idx] = s;
+  else if (db) db[idx - n_w] = s;
+}
+
+static int check(const kmu_pwconv_desc* d, const char* who) {
+  KMU_REQUIRE(d != nullptr, KMU_ERR_BAD_ARG, "%s: null descriptor", who);
+  KMU_REQUIRE(d->B > 0 && d->Cin > 0 && d->Cout > 0 && d->HW > 0, KMU_ERR_BAD_ARG, "%s: non-positive shape", who);
+  KMU_REQUIRE(d->B <= 65535, KMU_ERR_UNSUPPORTED, "%s: B=%d > 65535", who, d->B);
+  KMU_REQUIRE((size_t)(d->Cin > d->Cout ? d->Cin : d->Cout) * OT * 4 <= 200 * 1024, KMU_ERR_UNSUPPORTED, "%s: too many channels", who);
+  return KMU_OK;
+}
+static bool wgrad_ok(const kmu_pwconv_desc& d) {
+  const int c = d.Cin;
+  const bool pow2 = c >= 16 && c <= 1024 && (c & (c - 1)) == 0;
+  return pow2 && d.Cout <= 16 * (1024 / c);
+}
+static int wgrad_no(const kmu_pwconv_desc& d) {
+  int to = 1024 / d.Cin, need = cdiv(d.Cout, to), no = 1;
+  while (no < need) no <<= 1;
+  return no;
+}
+static int wgrad_ctas(const kmu_pwconv_desc& d) {
+  long long tiles = (long long)d.B * cdiv(d.HW, TP);
+  return (int)(tiles < 296 ? tiles : 296);
+}
+
+template <int NO>
+static void launch_wgrad(const kmu_pwconv_desc& d, const float* x, const float* dy, float* partial, cudaStream_t st) {
+  const int XP = d.Cin + 4, YP = NO * (1024 / d.Cin) + 4;
+  size_t smem = (size_t)TP * (XP + YP) * 4;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(pw_wgrad_kernel<NO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int ntiles = d.B * cdiv(d.HW, TP);
+  pw_wgrad_kernel<NO><<<wgrad_ctas(d), 256, smem, st>>>(x, dy, partial, d.Cin, d.Cout, d.HW, d.B, ntiles);
+}
+
+}  // namespace pw
+}  // namespace kmu
+
+using namespace kmu;
+using namespace kmu::pw;
+
+extern "C" {
+
+int kmu_pwconv_wgrad_supported(const kmu_pwconv_desc* d) { return (d && wgrad_ok(*d)) ? 1 : 0; }
+
+size_t kmu_pwconv_bwd_workspace_bytes(const kmu_pwconv_desc* d) {
+  if (check(d, "pwconv_bwd_workspace_bytes") != KMU_OK) return 0;
+  if (!wgrad_ok(*d)) return 256;
+  return align_up((size_t)wgrad_ctas(*d) * ((size_t)d->Cout * d->Cin + d->Cout) * 4, 256);
+}
+
+int kmu_pwconv_fwd(const kmu_pwconv_desc* d, const float* x, const float* w, const float* bias, float* y, kmu_stream stream) {
+  int rc = check(d, "pwconv_fwd");
+  if (rc != KMU_OK) return rc;
+  KMU_REQUIRE(x && w && y, KMU_ERR_BAD_ARG, "pwconv_fwd: null tensor");
+  size_t smem = (size_t)d->Cin * OT * 4;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(pw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  pw_kernel<<<dim3(cdiv(d->HW, 2 * NTH), cdiv(d->Cout, OT), d->B), NTH, smem, (cudaStream_t)stream>>>(x, w, bias, y, d->Cin, d->Cout,
+                                                                                                    d->HW, 0);
+  KMU_LAUNCH_CHECK("pw_fwd");
+  return KMU_OK;
+}
+
+int kmu_pwconv_bwd(const kmu_pwconv_desc* d, const float* x, const float* dy, const float* w, float* dx, float* dw, float* dbias,
+                   void* workspace, size_t workspace_bytes, kmu_stream stream) {
+  int rc = check(d, "pwconv_bwd");
+  if (rc != KMU_OK) return rc;
+  KMU_REQUIRE(dy && w, KMU_ERR_BAD_ARG, "pwconv_bwd: null tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dx) {
+    size_t smem = (size_t)d->Cout * OT * 4;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(pw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    pw_kernel<<<dim3(cdiv(d->HW, 2 * NTH), cdiv(d->Cin, OT), d->B), NTH, smem, st>>>(dy, w, nullptr, dx, d->Cout, d->Cin, d->HW, 1);
+    KMU_LAUNCH_CHECK("pw_dgrad");
+  }
+  if (dw) {
+    KMU_REQUIRE(x != nullptr, KMU_ERR_BAD_ARG, "pwconv_bwd: weight gradient needs x");
+    KMU_REQUIRE(wgrad_ok(*d), KMU_ERR_UNSUPPORTED, "pwconv_bwd: weight gradient needs Cin a power of two in [16,1024] and Cout <= 16*1024/Cin "
+                "(got %d -> %d)", d->Cin, d->Cout);
+    KMU_REQUIRE(workspace && workspace_bytes >= kmu_pwconv_bwd_workspace_bytes(d), KMU_ERR_WORKSPACE, "pwconv_bwd: workspace too small");
+    float* partial = (float*)workspace;
+    switch (wgrad_no(*d)) {
+      case 1: launch_wgrad<1>(*d, x, dy, partial, st); break;
+      case 2: launch_wgrad<2>(*d, x, dy, partial, st); break;
+      case 4: launch_wgrad<4>(*d, x, dy, partial, st); break;
+      case 8: launch_wgrad<8>(*d, x, dy, partial, st); break;
+      default: launch_wgrad<16>(*d, x, dy, partial, st); break;
+    }
+    KMU_LAUNCH_CHECK("pw_wgrad");
+    const int n_w = d->Cout * d->Cin, n_b = d->Cout;
+    pw_wreduce_kernel<<<cdiv(n_w + n_b, 128), 128, 0, st>>>(partial, wgrad_ctas(*d), n_w, n_b, dw, dbias);
+    KMU_LAUNCH_CHECK("pw_wreduce");
+  }
+  return KMU_OK;
+}
+
+}  // extern "C"

@@ -17,21 +17,35 @@ def _gaussian_taps(size, sigma, device, dtype):
     return g / g.sum()
 
 
+_BANDS = {}
+
+
+def _band(n, size, sigma, device, dtype):
+    """(n, n - size + 1) banded matrix whose column j holds the Gaussian taps at rows j .. j + size - 1."""
+    key = (n, size, sigma, str(device), dtype)
+    if key not in _BANDS:
+        g = _gaussian_taps(size, sigma, device, dtype)
+        m = torch.zeros(n, n - size + 1, device=device, dtype=dtype)
+        idx = torch.arange(n - size + 1, device=device)
+        for k in range(size):
+            m[idx + k, idx] = g[k]
+        _BANDS[key] = m
+    return _BANDS[key]
+
+
 def ssim(pred, target, data_range=1.0, size=11, sigma=1.5, k1=0.01, k2=0.03):
-    C = pred.shape[1]
+    """torchmetrics pads by reflection, filters, then crops the padded border again: what survives are exactly the
+    windows that lie inside the image, i.e. a VALID 11x11 Gaussian filter.  The window is separable, so the filter is two
+    small dense products with constant banded matrices (x @ G_w, G_h^T @ .), which run as batched GEMMs."""
     c1, c2 = (k1 * data_range) ** 2, (k2 * data_range) ** 2
-    pad = (size - 1) // 2
-    g = _gaussian_taps(size, sigma, pred.device, pred.dtype)       # the 2-D window is the outer product: filter separably
-    p = F.pad(pred, (pad, pad, pad, pad), mode="reflect")
-    t = F.pad(target, (pad, pad, pad, pad), mode="reflect")
-    stack = torch.cat([p, t, p * p, t * t, p * t])
-    n, _, hp, wp = stack.shape
-    flat = stack.reshape(n * C, 1, hp, wp)
-    out = F.conv2d(F.conv2d(flat, g.view(1, 1, size, 1)), g.view(1, 1, 1, size)).reshape(n, C, hp - 2 * pad, wp - 2 * pad)
-    mu_p, mu_t, pp, tt, pt = out.split(pred.shape[0])
+    H, W = pred.shape[-2:]
+    gw = _band(W, size, sigma, pred.device, pred.dtype)
+    gh = _band(H, size, sigma, pred.device, pred.dtype).t()
+    stack = torch.stack([pred, target, pred * pred, target * target, pred * target])
+    out = torch.matmul(gh, torch.matmul(stack, gw))
+    mu_p, mu_t, pp, tt, pt = out.unbind(0)
     s_p, s_t, s_pt = pp - mu_p * mu_p, tt - mu_t * mu_t, pt - mu_p * mu_t
     m = ((2 * mu_p * mu_t + c1) * (2 * s_pt + c2)) / ((mu_p * mu_p + mu_t * mu_t + c1) * (s_p + s_t + c2))
-    m = m[..., pad:-pad, pad:-pad]
     return m.reshape(m.shape[0], -1).mean(-1).mean()
 
 

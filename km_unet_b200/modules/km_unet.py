@@ -22,7 +22,7 @@ from .. import ops
 from .dagem import DAGEM
 from .dysample import DySample
 from .kan import KANConv2d
-from .vim import EfficientViMBlock
+from .vim import EfficientViMBlock, conv1x1
 
 
 class DropPath(nn.Module):
@@ -61,7 +61,8 @@ class StableHybridKANConv(nn.Module):
 
     def forward(self, x):
         x = self.pre_norm(x)
-        return self.post_act(self.residual(x) + self.kanconv2d(x))
+        identity = x if isinstance(self.residual, nn.Identity) else conv1x1(x, self.residual.weight, self.residual.bias)
+        return self.post_act(identity + self.kanconv2d(x))
 
 
 class DirectionAttention(nn.Module):
@@ -77,7 +78,7 @@ class DirectionAttention(nn.Module):
     def forward(self, x):
         # the three pooling modes of the reference (mean over W then H, over H then W, or both) are the same global mean
         weight = self.fc(x.mean(dim=(2, 3)))
-        q, k, v = self.qkv(x).chunk(3, dim=1)
+        q, k, v = conv1x1(x, self.qkv.weight, self.qkv.bias).chunk(3, dim=1)
         return ops.dwconv3x3(torch.sigmoid(q * k) * v, self.conv.weight, self.conv.bias) * weight[:, :, None, None]
 
 
@@ -96,7 +97,8 @@ class DirectionViM(nn.Module):
         self.attn = DirectionAttention(dim, mode)
 
     def forward(self, x):
-        return self.attn(self.vit_mamba(self.proj(x)))
+        x = conv1x1(x, self.proj.weight, self.proj.bias) if self.mode == 'channel' else self.proj(x)
+        return self.attn(self.vit_mamba(x))
 
 
 class TripleNorm(nn.Module):
@@ -130,7 +132,8 @@ class EnhancedViMBlock(nn.Module):
         feats = [self.height_block(x), self.width_block(x), self.channel_block(x)]
         g = self.fusion_gate(torch.cat(feats, dim=1))
         x = x + self.drop_path(g[:, 0:1] * feats[0] + g[:, 1:2] * feats[1] + g[:, 2:3] * feats[2])
-        return x + self.drop_path(self.ffn(self.norm(x)))
+        h = F.gelu(conv1x1(self.norm(x), self.ffn[0].weight, self.ffn[0].bias))
+        return x + self.drop_path(conv1x1(h, self.ffn[2].weight, self.ffn[2].bias))
 
 
 class ChannelAttention(nn.Module):
@@ -202,7 +205,7 @@ class IntelligentWaveletPoolingModule(nn.Module):
         col = torch.ones(1, W // 2, device=x.device, dtype=x.dtype)
         col[:, -1] = 0
         high = (lh * col + hl * row + hh * (row * col)).sum(dim=1, keepdim=True) / (3 * C)
-        return self.fusion_conv(torch.cat([ll, high], dim=1))
+        return conv1x1(torch.cat([ll, high], dim=1), self.fusion_conv.weight, self.fusion_conv.bias)
 
 
 class KM_UNetV3(nn.Module):

@@ -69,6 +69,14 @@ class _ConvLayer(nn.Module):
         return x
 
 
+def conv1x1(x, weight, bias=None):
+    """Pointwise convolution on NCHW through the streaming CUDA kernel (cuDNN's implicit-GEMM path transposes to NHWC and
+    back around every such call); channel pairs its weight-gradient kernel does not cover stay a library conv2d."""
+    if ops.pwconv_supported(weight.shape[1], weight.shape[0]):
+        return ops.pwconv(x, weight, bias)
+    return torch.nn.functional.conv2d(x, weight.reshape(weight.shape[0], weight.shape[1], 1, 1), bias)
+
+
 def _bn2d(bn, x, relu=False, res=None, alpha=None):
     """BatchNorm2d module `bn` applied through the fused CUDA op (keeps the module's parameters, buffers and counters)."""
     training = bn.training or bn.running_mean is None
@@ -86,9 +94,12 @@ class ConvLayer2D(_ConvLayer):
                               (dilation, dilation), groups, bias=False)
         self._finish(out_dim, norm, act_layer, bn_weight_init)
         self._dw3 = (kernel_size == 3 and stride == 1 and padding == 1 and dilation == 1 and groups == in_dim == out_dim)
+        self._pw = (kernel_size == 1 and stride == 1 and padding == 0 and groups == 1)
 
     def conv_out(self, x):
-        return ops.dwconv3x3(x, self.conv.weight) if self._dw3 else self.conv(x)
+        if self._dw3:
+            return ops.dwconv3x3(x, self.conv.weight)
+        return conv1x1(x, self.conv.weight) if self._pw else self.conv(x)
 
     def forward(self, x, res=None, alpha=None):
         """conv -> norm -> act; with res/alpha the block's layer-scale mix is fused into the normalisation."""

@@ -9,10 +9,10 @@ import torch
 from torch.amp import custom_bwd, custom_fwd
 
 from . import _lib
-from ._lib import (BnMixBwdArgs, BnMixDesc, BnMixFwdArgs, DwDesc, DagemBn, DagemBwdArgs, DagemDesc, DagemFwdArgs, DysBwdArgs, DysDesc, DysFwdArgs, HsmBwdArgs, HsmDesc, HsmFwdArgs, KanBwdArgs, KanDesc, KanFwdArgs,
+from ._lib import (PwDesc, BnMixBwdArgs, BnMixDesc, BnMixFwdArgs, DwDesc, DagemBn, DagemBwdArgs, DagemDesc, DagemFwdArgs, DysBwdArgs, DysDesc, DysFwdArgs, HsmBwdArgs, HsmDesc, HsmFwdArgs, KanBwdArgs, KanDesc, KanFwdArgs,
                    KMU_PREC_BF16, KMU_PREC_FP32, check, ptr, stream_ptr)
 
-__all__ = ["kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dysample_sample", "dagem_gate", "bnmix", "dwconv3x3", "KMU_PREC_FP32", "KMU_PREC_BF16"]
+__all__ = ["kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dysample_sample", "dagem_gate", "bnmix", "dwconv3x3", "pwconv", "pwconv_supported", "KMU_PREC_FP32", "KMU_PREC_BF16"]
 
 
 # ------------------------------------------------------------------------------------------------------ op-level timing
@@ -483,3 +483,53 @@ def dwconv3x3(x, weight, bias=None):
     if not x.is_cuda:
         raise RuntimeError("km_unet_b200.dwconv3x3: CUDA tensors only (no CPU fallback)")
     return _DwConv3x3Fn.apply(x, weight, bias)
+
+
+class _PwConvFn(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, weight, bias):
+        lib = _lib.lib()
+        x = x.contiguous()
+        B, Cin = x.shape[0], x.shape[1]
+        HW = x.numel() // (B * Cin)
+        Cout = weight.shape[0]
+        desc = PwDesc(B, Cin, Cout, HW)
+        w = weight.reshape(Cout, Cin).contiguous()
+        b = None if bias is None else bias.contiguous()
+        y = torch.empty((B, Cout) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
+        check(_call("kmu_pwconv_fwd", (B, Cin, Cout, HW), lib.kmu_pwconv_fwd, C.byref(desc), ptr(x), ptr(w), ptr(b), ptr(y), stream_ptr()),
+              "kmu_pwconv_fwd")
+        ctx.save_for_backward(x, w)
+        ctx.desc, ctx.has_bias, ctx.wshape = desc, bias is not None, weight.shape
+        return y
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        lib = _lib.lib()
+        x, w = ctx.saved_tensors
+        desc = ctx.desc
+        dy = dy.to(torch.float32).contiguous()
+        need_x = ctx.needs_input_grad[0]
+        need_w = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
+        dx = torch.empty_like(x) if need_x else None
+        dw = torch.empty_like(w) if need_w else None
+        db = torch.empty(desc.Cout, dtype=torch.float32, device=x.device) if (need_w and ctx.has_bias) else None
+        ws = _workspace(lib.kmu_pwconv_bwd_workspace_bytes(C.byref(desc)), x.device)
+        check(_call("kmu_pwconv_bwd", (desc.B, desc.Cin, desc.Cout, desc.HW), lib.kmu_pwconv_bwd, C.byref(desc), ptr(x), ptr(dy), ptr(w),
+                    ptr(dx), ptr(dw), ptr(db), ws.data_ptr(), ws.numel(), stream_ptr()), "kmu_pwconv_bwd")
+        return dx, None if dw is None else dw.reshape(ctx.wshape), db
+
+
+def pwconv_supported(cin, cout):
+    """True when the CUDA weight-gradient kernel covers this channel pair (forward / input gradient always do)."""
+    d = PwDesc(1, int(cin), int(cout), 1)
+    return bool(_lib.lib().kmu_pwconv_wgrad_supported(C.byref(d)))
+
+
+def pwconv(x, weight, bias=None):
+    """1x1 convolution on NCHW: weight (Cout,Cin,1,1) or (Cout,Cin), optional bias (Cout)."""
+    if not x.is_cuda:
+        raise RuntimeError("km_unet_b200.pwconv: CUDA tensors only (no CPU fallback)")
+    return _PwConvFn.apply(x, weight, bias)

@@ -52,6 +52,11 @@ def _dwconv3x3(x, weight, bias=None):
     return F.conv2d(x, weight, bias, stride=1, padding=1, groups=x.shape[1])
 
 
+def _pwconv(x, weight, bias=None):
+    import torch.nn.functional as F
+    return F.conv2d(x, weight.reshape(weight.shape[0], weight.shape[1], 1, 1), bias)
+
+
 def _gate(x, deformed, linears, bns, training, momentum=0.1, eps=1e-5):
     return _dagem.dagem_gate(x, deformed, linears, bns, training)
 
@@ -60,10 +65,10 @@ def _gate(x, deformed, linears, bns, training, momentum=0.1, eps=1e-5):
 def cpu_ops():
     from km_unet_b200 import ops
     saved = {n: getattr(ops, n) for n in ("kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dagem_gate", "bnmix",
-                                          "dwconv3x3")}
+                                          "dwconv3x3", "pwconv")}
     ops.kanconv2d, ops.kanlinear, ops.layernorm1d = _kanconv2d, _kanlinear, _hsmssd.layernorm1d
     ops.hsmssd, ops.dysample, ops.dagem_gate = _hsm, _dys, _gate
-    ops.bnmix, ops.dwconv3x3 = _bnmix, _dwconv3x3
+    ops.bnmix, ops.dwconv3x3, ops.pwconv = _bnmix, _dwconv3x3, _pwconv
     try:
         yield
     finally:

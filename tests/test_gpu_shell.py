@@ -82,3 +82,35 @@ def test_shell_ops_raise_on_cpu():
         ops.dwconv3x3(torch.randn(1, 4, 4, 4), torch.randn(4, 1, 3, 3))
     with pytest.raises(RuntimeError):
         ops.bnmix(torch.randn(1, 4, 4, 4), torch.ones(4), torch.zeros(4), torch.zeros(4), torch.ones(4), True)
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W,bias", [(2, 16, 64, 32, 32, True), (3, 64, 16, 7, 9, False), (2, 16, 48, 16, 16, True),
+                                                (1, 256, 64, 8, 8, True), (2, 64, 256, 12, 12, False), (2, 128, 32, 5, 5, True),
+                                                (32, 16, 64, 128, 128, False), (2, 32, 32, 64, 64, True)])
+def test_pwconv_vs_torch(B, Cin, Cout, H, W, bias):
+    from km_unet_b200 import ops
+    assert ops.pwconv_supported(Cin, Cout)
+    torch.manual_seed(Cin + Cout)
+    x = torch.randn(B, Cin, H, W)
+    w = torch.randn(Cout, Cin, 1, 1) / Cin ** 0.5
+    bv = torch.randn(Cout) if bias else None
+    gout = torch.randn(B, Cout, H, W)
+    xd, wd = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    bd = bv.double().requires_grad_(True) if bias else None
+    want = F.conv2d(xd, wd, bd)
+    want.backward(gout.double())
+    xc, wc = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+    bc = bv.cuda().requires_grad_(True) if bias else None
+    y = ops.pwconv(xc, wc, bc)
+    assert rel_err(y, want) < TOL
+    y.backward(gout.cuda())
+    assert rel_err(xc.grad, xd.grad) < TOL
+    assert rel_err(wc.grad, wd.grad) < TOL
+    if bias:
+        assert rel_err(bc.grad, bd.grad) < TOL
+
+
+def test_pwconv_unsupported_pairs_are_reported():
+    from km_unet_b200 import ops
+    assert not ops.pwconv_supported(17, 16)      # IWP fusion conv (C + 1 inputs) stays a library conv
+    assert not ops.pwconv_supported(96, 32)
