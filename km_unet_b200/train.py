@@ -35,6 +35,10 @@ class GraphedTrainStep:
                     cur, cur_bytes = [], 0
             if cur:
                 self.buckets.append((cur, torch.empty(sum(q.numel() for q in cur), dtype=cur[0].dtype, device=cur[0].device)))
+        # the parameters' AccumulateGrad nodes may predate this object (created on the default stream): harmless here, the
+        # capture below runs every node on the capture stream
+        if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
