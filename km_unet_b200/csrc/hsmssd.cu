@@ -45,31 +45,34 @@ static Dims make_dims(const kmu_hsmssd_desc& s) {
 }
 
 // ================================================================================================ forward
-// ---- P = dw3x3(Wp x).  grid (tiles, B), 256 threads = 8x32 interior positions.  The x halo tile is staged once in
-//      shared memory; the CTA then walks the 192 projected channels in passes of PCH: projection on the halo (zero outside
-//      the image = the depthwise conv's zero padding), depthwise 3x3 from shared memory, coalesced store of P.
+// ---- P = dw3x3(Wp x).  grid (tiles, B), 256 threads, tile = 8 rows x 32 columns.  The x halo tile is staged once in
+//      shared memory (10 rows x 36 columns: halo columns -2..33 so that every group of 4 positions is 16-byte aligned); the CTA
+//      then walks the 192 projected channels in passes of PCH:
+//        projection  task = (4 consecutive halo positions, 4 channels): per input channel one LDS.128 of x and one of
+//                    weights feed 16 FMAs (register tile; shared-memory bandwidth was the limiter of the 1x16 version)
+//        depthwise   thread = (tile column, channel): 3x3 window slides down the 8 rows in registers, taps in registers,
+//                    3 LDS + 9 FMA per output, one coalesced 128-byte store per warp and row.
 constexpr int PCH = 16;
+constexpr int HPX = 36, HPR = 10, HPN = HPX * HPR;  // padded halo tile: 360 positions
 template <int C>
 __global__ void __launch_bounds__(256) hsm_proj_dw_kernel(const float* __restrict__ x, const float* __restrict__ wp,
                                                           const float* __restrict__ wd, float* __restrict__ P, Dims d) {
   extern __shared__ __align__(16) float smem[];
-  float* x_s = smem;                    // [C][NHALO]
-  float* q_s = x_s + C * NHALO;         // [PCH][NHALO]
-  float* wp_s = q_s + PCH * NHALO;      // [C][PCH]
+  float* x_s = smem;                    // [C][HPN]
+  float* q_s = x_s + C * HPN;           // [PCH][HPN]
+  float* wp_s = q_s + PCH * HPN;        // [C][PCH]
   float* wd_s = wp_s + C * PCH;         // [PCH][12]
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int ty0 = (blockIdx.x / d.tiles_x) * TH, tx0 = (blockIdx.x % d.tiles_x) * TW;
   const int b = blockIdx.y;
   const float* xb = x + (size_t)b * C * d.L;
-  for (int i = tid; i < C * NHALO; i += 256) {
-    int c = i / NHALO, pos = i - c * NHALO;
-    int hy = pos / HW_, hx = pos - hy * HW_;
-    int gy = ty0 + hy - 1, gx = tx0 + hx - 1;
+  for (int i = tid; i < C * HPN; i += 256) {
+    int c = i / HPN, pos = i - c * HPN;
+    int hy = pos / HPX, hx = pos - hy * HPX;
+    int gy = ty0 + hy - 1, gx = tx0 + hx - 2;
     x_s[i] = (gy >= 0 && gy < d.H && gx >= 0 && gx < d.H) ? __ldg(xb + (size_t)c * d.L + (size_t)gy * d.H + gx) : 0.f;
   }
-  const int ly = tid >> 5, lx = tid & 31;
-  const int gy = ty0 + ly, gx = tx0 + lx;
-  const bool inside = gy < d.H && gx < d.H;
+  const int gx = tx0 + lane;
   for (int n0 = 0; n0 < N3; n0 += PCH) {
     __syncthreads();
     for (int i = tid; i < C * PCH; i += 256) {
@@ -78,39 +81,52 @@ __global__ void __launch_bounds__(256) hsm_proj_dw_kernel(const float* __restric
     }
     for (int i = tid; i < PCH * 9; i += 256) wd_s[(i / 9) * 12 + (i % 9)] = wd[(size_t)n0 * 9 + i];
     __syncthreads();
-    for (int pos = tid; pos < NHALO; pos += 256) {
-      float q[PCH];
+    // projection on the halo: 90 position quads x 4 channel groups = 360 tasks
+    for (int task = tid; task < (HPN / 4) * (PCH / 4); task += 256) {
+      const int quad = task % (HPN / 4), g = task / (HPN / 4);
+      float q[4][4];
 #pragma unroll
-      for (int i = 0; i < PCH; ++i) q[i] = 0.f;
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) q[k][e] = 0.f;
 #pragma unroll 8
       for (int c = 0; c < C; ++c) {
-        float xv = x_s[c * NHALO + pos];
-        const float4* w4 = reinterpret_cast<const float4*>(wp_s + c * PCH);
-#pragma unroll
-        for (int i = 0; i < PCH / 4; ++i) {
-          float4 w = w4[i];
-          q[4 * i + 0] = fmaf(xv, w.x, q[4 * i + 0]);
-          q[4 * i + 1] = fmaf(xv, w.y, q[4 * i + 1]);
-          q[4 * i + 2] = fmaf(xv, w.z, q[4 * i + 2]);
-          q[4 * i + 3] = fmaf(xv, w.w, q[4 * i + 3]);
-        }
+        const float4 xv = *reinterpret_cast<const float4*>(x_s + c * HPN + 4 * quad);
+        const float4 w = *reinterpret_cast<const float4*>(wp_s + c * PCH + 4 * g);
+        q[0][0] = fmaf(w.x, xv.x, q[0][0]); q[0][1] = fmaf(w.x, xv.y, q[0][1]); q[0][2] = fmaf(w.x, xv.z, q[0][2]); q[0][3] = fmaf(w.x, xv.w, q[0][3]);
+        q[1][0] = fmaf(w.y, xv.x, q[1][0]); q[1][1] = fmaf(w.y, xv.y, q[1][1]); q[1][2] = fmaf(w.y, xv.z, q[1][2]); q[1][3] = fmaf(w.y, xv.w, q[1][3]);
+        q[2][0] = fmaf(w.z, xv.x, q[2][0]); q[2][1] = fmaf(w.z, xv.y, q[2][1]); q[2][2] = fmaf(w.z, xv.z, q[2][2]); q[2][3] = fmaf(w.z, xv.w, q[2][3]);
+        q[3][0] = fmaf(w.w, xv.x, q[3][0]); q[3][1] = fmaf(w.w, xv.y, q[3][1]); q[3][2] = fmaf(w.w, xv.z, q[3][2]); q[3][3] = fmaf(w.w, xv.w, q[3][3]);
       }
 #pragma unroll
-      for (int i = 0; i < PCH; ++i) q_s[i * NHALO + pos] = q[i];
+      for (int k = 0; k < 4; ++k)
+        *reinterpret_cast<float4*>(q_s + (4 * g + k) * HPN + 4 * quad) = make_float4(q[k][0], q[k][1], q[k][2], q[k][3]);
     }
     __syncthreads();
-    if (inside) {
-      float* pp = P + ((size_t)b * N3 + n0) * d.L + (size_t)gy * d.H + gx;
-#pragma unroll 4
-      for (int nn = 0; nn < PCH; ++nn) {
-        const float* qr = q_s + nn * NHALO + ly * HW_ + lx;
+    // depthwise 3x3: warp handles channels 2*wid, 2*wid+1; lane = tile column (halo column lane + 2)
+    if (gx < d.H) {
+#pragma unroll
+      for (int j = 0; j < PCH / 8; ++j) {
+        const int nn = wid * (PCH / 8) + j;
         const float4 wa = *reinterpret_cast<const float4*>(wd_s + nn * 12);
         const float4 wb = *reinterpret_cast<const float4*>(wd_s + nn * 12 + 4);
         const float w8 = wd_s[nn * 12 + 8];
-        float sacc = qr[0] * wa.x + qr[1] * wa.y + qr[2] * wa.z;
-        sacc += qr[HW_] * wa.w + qr[HW_ + 1] * wb.x + qr[HW_ + 2] * wb.y;
-        sacc += qr[2 * HW_] * wb.z + qr[2 * HW_ + 1] * wb.w + qr[2 * HW_ + 2] * w8;
-        pp[(size_t)nn * d.L] = sacc;
+        const float* qp = q_s + nn * HPN + lane + 1;   // halo column of tap kx = 0
+        float r0[3], r1[3], r2[3];
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) { r0[cc] = qp[cc]; r1[cc] = qp[HPX + cc]; }
+        float* pp = P + ((size_t)b * N3 + n0 + nn) * d.L + (size_t)ty0 * d.H + gx;
+#pragma unroll
+        for (int ly = 0; ly < TH; ++ly) {
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc) r2[cc] = qp[(ly + 2) * HPX + cc];
+          float sacc = r0[0] * wa.x + r0[1] * wa.y + r0[2] * wa.z;
+          sacc += r1[0] * wa.w + r1[1] * wb.x + r1[2] * wb.y;
+          sacc += r2[0] * wb.z + r2[1] * wb.w + r2[2] * w8;
+          if (ty0 + ly < d.H) pp[(size_t)ly * d.H] = sacc;
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc) { r0[cc] = r1[cc]; r1[cc] = r2[cc]; }
+        }
       }
     }
   }
@@ -509,10 +525,15 @@ __global__ void __launch_bounds__(256, 2) hsm_dp_kernel(const float* __restrict_
   for (int nn = 0; nn < 64; ++nn) dPb[(size_t)(N + nn) * d.L] = t[nn];
 }
 
-// ---- projection / depthwise backward on a spatial tile.  grid (tiles, B), 256 threads = 8x32 interior positions.
+// ---- projection / depthwise backward on a spatial tile.  grid (tiles, B), 256 threads, tile = 8 rows x 32 columns.
 //      dQ = dw3x3^T(dP) ; dx += Wp^T dQ ; per-CTA partials of dWp[n][c] = sum dQ x and dWd[n][tap] = sum Q(q) dP(q - tap)
 //      (Q only at the CTA's own pixels: every pixel q belongs to exactly one tile and dP is zero outside the image).
-//      partial layout per CTA: dWp (192*C) | dWd (192*9).  The x tile is staged once; the 192 channels go in passes of BN.
+//      partial layout per CTA: dWp (192*C) | dWd (192*9).  The x tile is staged once; the 192 channels go in passes of BN:
+//        Q        task = (4 consecutive pixels, 4 channels): LDS.128 x + LDS.128 weights -> 16 FMA
+//        stencil  thread = (tile column, channel): one 3x3 window of dP slides down the rows in registers and feeds BOTH
+//                 dQ (taps in registers) and the dWd partial (9 register accumulators, one warp reduction per channel)
+//        dx       task = (4 consecutive pixels, C/4 input channels), accumulators live in registers across all passes
+//        dWp      4x4 register blocks over interleaved pixel slices (conflict-free LDS.128), shuffle-reduced over slices
 constexpr int BN = 16;   // projected channels per pass
 constexpr int QP = 260;  // row pitch of the [channel][256 pixel] tiles
 template <int C>
@@ -520,7 +541,7 @@ __global__ void __launch_bounds__(256) hsm_proj_dw_bwd_kernel(const float* __res
                                                               const float* __restrict__ wd, const float* __restrict__ dP,
                                                               float* __restrict__ dx, float* __restrict__ partial, Dims d) {
   constexpr int NSL = 256 / C;  // pixel slices of the dWp contraction (C blocks of 4x4 outputs x NSL slices = 256 threads)
-  constexpr int SL = C;         // pixels per slice
+  constexpr int CQ = C / 4;     // input channels per dx task
   extern __shared__ __align__(16) float smem[];
   float* dp_s = smem;                 // [BN][NHALO]
   float* q_s = dp_s + BN * NHALO;     // [BN][QP]
@@ -532,16 +553,21 @@ __global__ void __launch_bounds__(256) hsm_proj_dw_bwd_kernel(const float* __res
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int ty0 = (blockIdx.x / d.tiles_x) * TH, tx0 = (blockIdx.x % d.tiles_x) * TW;
   const int b = blockIdx.y;
-  const int ly = tid >> 5, lx = tid & 31;
-  const int gy = ty0 + ly, gx = tx0 + lx;
-  const bool inside = gy < d.H && gx < d.H;
   const float* xb = x + (size_t)b * C * d.L;
+  {
+    const int gy = ty0 + (tid >> 5), gx = tx0 + (tid & 31);
+    const bool inside = gy < d.H && gx < d.H;
 #pragma unroll 4
-  for (int c = 0; c < C; ++c) x_s[c * QP + tid] = inside ? __ldg(xb + (size_t)c * d.L + (size_t)gy * d.H + gx) : 0.f;
+    for (int c = 0; c < C; ++c) x_s[c * QP + tid] = inside ? __ldg(xb + (size_t)c * d.L + (size_t)gy * d.H + gx) : 0.f;
+  }
   float* pb = partial + ((size_t)b * gridDim.x + blockIdx.x) * (size_t)(N3 * C + N3 * 9);
-  float dxa[C];
+  const int quad = tid & 63, grp = tid >> 6;          // Q / dx task: pixels 4*quad .. 4*quad+3 (one tile row), group 0..3
+  float dxa[CQ][4];
 #pragma unroll
-  for (int c = 0; c < C; ++c) dxa[c] = 0.f;
+  for (int c = 0; c < CQ; ++c)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dxa[c][e] = 0.f;
+  const bool col_in = tx0 + lane < d.H;
 
   for (int n0 = 0; n0 < N3; n0 += BN) {
     __syncthreads();
@@ -562,50 +588,83 @@ __global__ void __launch_bounds__(256) hsm_proj_dw_bwd_kernel(const float* __res
     }
     __syncthreads();
     {
-      // Q at the thread's own pixel (0 outside the image because x_s is 0 there)
-      float q[BN];
+      // Q at the CTA's own pixels (0 outside the image because x_s is 0 there): channels 4*grp .. 4*grp+3
+      float q[4][4];
 #pragma unroll
-      for (int i = 0; i < BN; ++i) q[i] = 0.f;
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) q[k][e] = 0.f;
 #pragma unroll 8
       for (int c = 0; c < C; ++c) {
-        float xv = x_s[c * QP + tid];
-        const float4* w4 = reinterpret_cast<const float4*>(wp_s + c * BN);
-#pragma unroll
-        for (int i = 0; i < BN / 4; ++i) {
-          float4 w = w4[i];
-          q[4 * i + 0] = fmaf(xv, w.x, q[4 * i + 0]);
-          q[4 * i + 1] = fmaf(xv, w.y, q[4 * i + 1]);
-          q[4 * i + 2] = fmaf(xv, w.z, q[4 * i + 2]);
-          q[4 * i + 3] = fmaf(xv, w.w, q[4 * i + 3]);
-        }
+        const float4 xv = *reinterpret_cast<const float4*>(x_s + c * QP + 4 * quad);
+        const float4 w = *reinterpret_cast<const float4*>(wp_s + c * BN + 4 * grp);
+        q[0][0] = fmaf(w.x, xv.x, q[0][0]); q[0][1] = fmaf(w.x, xv.y, q[0][1]); q[0][2] = fmaf(w.x, xv.z, q[0][2]); q[0][3] = fmaf(w.x, xv.w, q[0][3]);
+        q[1][0] = fmaf(w.y, xv.x, q[1][0]); q[1][1] = fmaf(w.y, xv.y, q[1][1]); q[1][2] = fmaf(w.y, xv.z, q[1][2]); q[1][3] = fmaf(w.y, xv.w, q[1][3]);
+        q[2][0] = fmaf(w.z, xv.x, q[2][0]); q[2][1] = fmaf(w.z, xv.y, q[2][1]); q[2][2] = fmaf(w.z, xv.z, q[2][2]); q[2][3] = fmaf(w.z, xv.w, q[2][3]);
+        q[3][0] = fmaf(w.w, xv.x, q[3][0]); q[3][1] = fmaf(w.w, xv.y, q[3][1]); q[3][2] = fmaf(w.w, xv.z, q[3][2]); q[3][3] = fmaf(w.w, xv.w, q[3][3]);
       }
 #pragma unroll
-      for (int nn = 0; nn < BN; ++nn) q_s[nn * QP + tid] = q[nn];
-      // dQ at the thread's pixel (transposed depthwise conv) and the dx accumulation
+      for (int k = 0; k < 4; ++k)
+        *reinterpret_cast<float4*>(q_s + (4 * grp + k) * QP + 4 * quad) = make_float4(q[k][0], q[k][1], q[k][2], q[k][3]);
+    }
+    __syncthreads();
+    // stencil: warp handles channels 2*wid, 2*wid+1; lane = tile column; the dP window (halo rows qy..qy+2, halo columns
+    // lane..lane+2) gives dQ(qy, lane) = sum w[ky][kx] dP(qy+2-ky, lane+2-kx) and dWd[ky][kx] += Q(qy, lane) dP(same)
 #pragma unroll
-      for (int nn = 0; nn < BN; ++nn) {
-        const float4 wa = *reinterpret_cast<const float4*>(wd_s + nn * 12);
-        const float4 wb = *reinterpret_cast<const float4*>(wd_s + nn * 12 + 4);
-        const float w8 = wd_s[nn * 12 + 8];
-        const float* g = dp_s + nn * NHALO + (ly + 2) * HW_ + (lx + 2);
-        float sacc = wa.x * g[0] + wa.y * g[-1] + wa.z * g[-2];
-        sacc += wa.w * g[-HW_] + wb.x * g[-HW_ - 1] + wb.y * g[-HW_ - 2];
-        sacc += wb.z * g[-2 * HW_] + wb.w * g[-2 * HW_ - 1] + w8 * g[-2 * HW_ - 2];
-        const float dq = inside ? sacc : 0.f;
-        dq_s[nn * QP + tid] = dq;
-        const float4* wr = reinterpret_cast<const float4*>(wpt_s + nn * C);
+    for (int j = 0; j < BN / 8; ++j) {
+      const int nn = wid * (BN / 8) + j;
+      const float4 wa = *reinterpret_cast<const float4*>(wd_s + nn * 12);
+      const float4 wb = *reinterpret_cast<const float4*>(wd_s + nn * 12 + 4);
+      const float w8 = wd_s[nn * 12 + 8];
+      float a[9];
 #pragma unroll
-        for (int c4 = 0; c4 < C / 4; ++c4) {
-          float4 w = wr[c4];
-          dxa[4 * c4 + 0] = fmaf(w.x, dq, dxa[4 * c4 + 0]);
-          dxa[4 * c4 + 1] = fmaf(w.y, dq, dxa[4 * c4 + 1]);
-          dxa[4 * c4 + 2] = fmaf(w.z, dq, dxa[4 * c4 + 2]);
-          dxa[4 * c4 + 3] = fmaf(w.w, dq, dxa[4 * c4 + 3]);
-        }
+      for (int tp = 0; tp < 9; ++tp) a[tp] = 0.f;
+      const float* gp = dp_s + nn * NHALO + lane;
+      float r0[3], r1[3], r2[3];
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) { r0[cc] = gp[cc]; r1[cc] = gp[HW_ + cc]; }
+#pragma unroll
+      for (int qy = 0; qy < TH; ++qy) {
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) r2[cc] = gp[(qy + 2) * HW_ + cc];
+        const float qv = q_s[nn * QP + qy * 32 + lane];
+        float dq = wa.x * r2[2] + wa.y * r2[1] + wa.z * r2[0];
+        dq += wa.w * r1[2] + wb.x * r1[1] + wb.y * r1[0];
+        dq += wb.z * r0[2] + wb.w * r0[1] + w8 * r0[0];
+        dq_s[nn * QP + qy * 32 + lane] = (col_in && ty0 + qy < d.H) ? dq : 0.f;
+        a[0] = fmaf(qv, r2[2], a[0]); a[1] = fmaf(qv, r2[1], a[1]); a[2] = fmaf(qv, r2[0], a[2]);
+        a[3] = fmaf(qv, r1[2], a[3]); a[4] = fmaf(qv, r1[1], a[4]); a[5] = fmaf(qv, r1[0], a[5]);
+        a[6] = fmaf(qv, r0[2], a[6]); a[7] = fmaf(qv, r0[1], a[7]); a[8] = fmaf(qv, r0[0], a[8]);
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) { r0[cc] = r1[cc]; r1[cc] = r2[cc]; }
+      }
+#pragma unroll
+      for (int tp = 0; tp < 9; ++tp) {
+        float sacc = warp_sum(a[tp]);
+        if (lane == 0) pb[(size_t)N3 * C + (size_t)(n0 + nn) * 9 + tp] = sacc;
       }
     }
     __syncthreads();
-    // dWp partial: thread = (4x4 block of (n,c) outputs, pixel slice); slices of one block sit in adjacent lanes
+    // dx accumulation: pixels 4*quad.., input channels grp*CQ .. grp*CQ + CQ - 1
+#pragma unroll 4
+    for (int nn = 0; nn < BN; ++nn) {
+      const float4 g = *reinterpret_cast<const float4*>(dq_s + nn * QP + 4 * quad);
+      const float4* wr = reinterpret_cast<const float4*>(wpt_s + nn * C + grp * CQ);
+#pragma unroll
+      for (int c4 = 0; c4 < CQ / 4; ++c4) {
+        const float4 w = wr[c4];
+        dxa[4 * c4 + 0][0] = fmaf(w.x, g.x, dxa[4 * c4 + 0][0]); dxa[4 * c4 + 0][1] = fmaf(w.x, g.y, dxa[4 * c4 + 0][1]);
+        dxa[4 * c4 + 0][2] = fmaf(w.x, g.z, dxa[4 * c4 + 0][2]); dxa[4 * c4 + 0][3] = fmaf(w.x, g.w, dxa[4 * c4 + 0][3]);
+        dxa[4 * c4 + 1][0] = fmaf(w.y, g.x, dxa[4 * c4 + 1][0]); dxa[4 * c4 + 1][1] = fmaf(w.y, g.y, dxa[4 * c4 + 1][1]);
+        dxa[4 * c4 + 1][2] = fmaf(w.y, g.z, dxa[4 * c4 + 1][2]); dxa[4 * c4 + 1][3] = fmaf(w.y, g.w, dxa[4 * c4 + 1][3]);
+        dxa[4 * c4 + 2][0] = fmaf(w.z, g.x, dxa[4 * c4 + 2][0]); dxa[4 * c4 + 2][1] = fmaf(w.z, g.y, dxa[4 * c4 + 2][1]);
+        dxa[4 * c4 + 2][2] = fmaf(w.z, g.z, dxa[4 * c4 + 2][2]); dxa[4 * c4 + 2][3] = fmaf(w.z, g.w, dxa[4 * c4 + 2][3]);
+        dxa[4 * c4 + 3][0] = fmaf(w.w, g.x, dxa[4 * c4 + 3][0]); dxa[4 * c4 + 3][1] = fmaf(w.w, g.y, dxa[4 * c4 + 3][1]);
+        dxa[4 * c4 + 3][2] = fmaf(w.w, g.z, dxa[4 * c4 + 3][2]); dxa[4 * c4 + 3][3] = fmaf(w.w, g.w, dxa[4 * c4 + 3][3]);
+      }
+    }
+    // dWp partial: thread = (4x4 block of (n,c) outputs, pixel slice); slice sl owns the float4 groups sl, sl+NSL, ... so the
+    // lanes of a warp read consecutive 16-byte groups (no bank conflicts)
     {
       const int sl = tid % NSL, blk = tid / NSL;
       const int i4 = (blk & 3) * 4, j4 = (blk >> 2) * 4;
@@ -615,8 +674,8 @@ __global__ void __launch_bounds__(256) hsm_proj_dw_bwd_kernel(const float* __res
 #pragma unroll
         for (int t = 0; t < 4; ++t) acc[r][t] = 0.f;
 #pragma unroll 2
-      for (int k = 0; k < SL; k += 4) {
-        const int px = sl * SL + k;
+      for (int k = 0; k < 64 / NSL; ++k) {
+        const int px = (k * NSL + sl) * 4;
         float4 av[4], bv[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
@@ -639,53 +698,49 @@ __global__ void __launch_bounds__(256) hsm_proj_dw_bwd_kernel(const float* __res
           if (sl == 0) pb[(size_t)(n0 + i4 + r) * C + j4 + t] = v;
         }
     }
-    // dWd partial: warp handles channels 2*wid, 2*wid+1; lane = tile column, sliding 3x3 window of dP down the 8 rows
-    for (int j = 0; j < BN / 8; ++j) {
-      const int nn = wid * (BN / 8) + j;
-      float a[9];
+  }
+  // dx += the accumulated projection-path gradient (the direct part was written by hsm_dp_kernel)
+  {
+    const int gy = ty0 + (quad >> 3), gx0 = tx0 + (quad & 7) * 4;
+    if (gy < d.H) {
 #pragma unroll
-      for (int tp = 0; tp < 9; ++tp) a[tp] = 0.f;
-      // window rows r0 (halo row qy), r1 (qy+1), r2 (qy+2); columns lane, lane+1, lane+2
-      const float* gp = dp_s + nn * NHALO + lane;
-      float r0[3], r1[3], r2[3];
+      for (int c = 0; c < CQ; ++c) {
+        float* dxp = dx + ((size_t)b * C + grp * CQ + c) * d.L + (size_t)gy * d.H + gx0;
+        if ((d.H & 3) == 0 && gx0 + 3 < d.H) {
+          float4 t = *reinterpret_cast<float4*>(dxp);
+          t.x += dxa[c][0]; t.y += dxa[c][1]; t.z += dxa[c][2]; t.w += dxa[c][3];
+          *reinterpret_cast<float4*>(dxp) = t;
+        } else {
 #pragma unroll
-      for (int cc = 0; cc < 3; ++cc) { r0[cc] = gp[cc]; r1[cc] = gp[HW_ + cc]; }
-#pragma unroll
-      for (int qy = 0; qy < TH; ++qy) {
-#pragma unroll
-        for (int cc = 0; cc < 3; ++cc) r2[cc] = gp[(qy + 2) * HW_ + cc];
-        const float qv = q_s[nn * QP + qy * 32 + lane];
-        // tap (ky,kx) pairs with dP at halo (qy + 2 - ky, lane + 2 - kx)
-        a[0] = fmaf(qv, r2[2], a[0]); a[1] = fmaf(qv, r2[1], a[1]); a[2] = fmaf(qv, r2[0], a[2]);
-        a[3] = fmaf(qv, r1[2], a[3]); a[4] = fmaf(qv, r1[1], a[4]); a[5] = fmaf(qv, r1[0], a[5]);
-        a[6] = fmaf(qv, r0[2], a[6]); a[7] = fmaf(qv, r0[1], a[7]); a[8] = fmaf(qv, r0[0], a[8]);
-#pragma unroll
-        for (int cc = 0; cc < 3; ++cc) { r0[cc] = r1[cc]; r1[cc] = r2[cc]; }
-      }
-#pragma unroll
-      for (int tp = 0; tp < 9; ++tp) {
-        float sacc = warp_sum(a[tp]);
-        if (lane == 0) pb[(size_t)N3 * C + (size_t)(n0 + nn) * 9 + tp] = sacc;
+          for (int e = 0; e < 4; ++e)
+            if (gx0 + e < d.H) dxp[e] += dxa[c][e];
+        }
       }
     }
   }
-  if (inside) {
-    float* dxb = dx + (size_t)b * C * d.L + (size_t)gy * d.H + gx;
-#pragma unroll
-    for (int c = 0; c < C; ++c) dxb[(size_t)c * d.L] += dxa[c];
-  }
 }
 
-// ---- fixed-order reductions of the weight-gradient partials
-__global__ void hsm_wgrad_reduce_kernel(const float* __restrict__ partial, int nparts, int per, float* __restrict__ out0, int n0,
-                                        float* __restrict__ out1, int n1, float* __restrict__ out2, int n2) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n0 + n1 + n2) return;
+// ---- fixed-order reductions of the weight-gradient partials: CTA = 32 outputs x 8 interleaved part slices (each thread
+//      sums parts k = slice, slice+8, ...; the 8 slice sums are then added in order), so many loads are in flight per output
+__global__ void __launch_bounds__(256) hsm_wgrad_reduce_kernel(const float* __restrict__ partial, int nparts, int per,
+                                                               float* __restrict__ out0, int n0, float* __restrict__ out1, int n1,
+                                                               float* __restrict__ out2, int n2) {
+  __shared__ float red[8][33];
+  const int o = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 32 + o;
   float s = 0.f;
-  for (int k = 0; k < nparts; ++k) s += partial[(size_t)k * per + idx];
-  if (idx < n0) out0[idx] = s;
-  else if (idx < n0 + n1) out1[idx - n0] = s;
-  else out2[idx - n0 - n1] = s;
+  if (idx < n0 + n1 + n2)
+    for (int k = sl; k < nparts; k += 8) s += partial[(size_t)k * per + idx];
+  red[sl][o] = s;
+  __syncthreads();
+  if (sl == 0 && idx < n0 + n1 + n2) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += red[q][o];
+    if (idx < n0) out0[idx] = t;
+    else if (idx < n0 + n1) out1[idx - n0] = t;
+    else out2[idx - n0 - n1] = t;
+  }
 }
 
 __global__ void fill_kernel(float* __restrict__ p, int n, float v) {
@@ -836,7 +891,7 @@ int kmu_hsmssd_fwd(const kmu_hsmssd_fwd_args* a, kmu_stream stream) {
   float* part_s = (float*)(ws + w.part_s);
   float* part_hs = (float*)(ws + w.part_hs);
   {
-    size_t smem = ((size_t)d.C * NHALO + (size_t)PCH * NHALO + (size_t)d.C * PCH + PCH * 12) * 4;
+    size_t smem = ((size_t)d.C * HPN + (size_t)PCH * HPN + (size_t)d.C * PCH + PCH * 12) * 4;
     dim3 grid(d.tiles_x * d.tiles_y, d.B);
 #define KMU_HSM_PROJ(CC)                                                                     \
   do {                                                                                       \
@@ -924,7 +979,7 @@ int kmu_hsmssd_bwd(const kmu_hsmssd_bwd_args* a, kmu_stream stream) {
     hsm_gate_bwd_kernel<<<d.B, GT, smem, st>>>(part_dho, a->dh, a->hs, a->hz, a->w_hz, a->w_out, a->D, dhs, r, wpart, d);
     KMU_LAUNCH_CHECK("hsm_gate_bwd");
     int n = 3 * C * C + 1;
-    hsm_wgrad_reduce_kernel<<<cdiv(n, 128), 128, 0, st>>>(wpart, d.B, n, a->d_w_out, C * C, a->d_w_hz, 2 * C * C, a->d_D, 1);
+    hsm_wgrad_reduce_kernel<<<cdiv(n, 32), 256, 0, st>>>(wpart, d.B, n, a->d_w_out, C * C, a->d_w_hz, 2 * C * C, a->d_D, 1);
     KMU_LAUNCH_CHECK("hsm_wgrad_reduce(gate)");
   }
   {
@@ -960,7 +1015,7 @@ int kmu_hsmssd_bwd(const kmu_hsmssd_bwd_args* a, kmu_stream stream) {
 #undef KMU_HSM_PBWD
     KMU_LAUNCH_CHECK("hsm_proj_dw_bwd");
     int per = N3 * C + N3 * 9;
-    hsm_wgrad_reduce_kernel<<<cdiv(per, 128), 128, 0, st>>>(tpart, tiles * d.B, per, a->d_w_bcdt, N3 * C, a->d_w_dw, N3 * 9,
+    hsm_wgrad_reduce_kernel<<<cdiv(per, 32), 256, 0, st>>>(tpart, tiles * d.B, per, a->d_w_bcdt, N3 * C, a->d_w_dw, N3 * 9,
                                                             nullptr, 0);
     KMU_LAUNCH_CHECK("hsm_wgrad_reduce(proj)");
   }
