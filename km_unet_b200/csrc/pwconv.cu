@@ -66,19 +66,24 @@ __global__ void __launch_bounds__(NTH) pw_kernel(const float* __restrict__ in, c
 }
 
 // ---- weight / bias gradient.  dW[o][c] = sum_{b,p} dy[b,o,p] x[b,c,p], db[o] = sum dy.
-// CTA = 256 threads = TC (= Cin/4) threads along c x TO (= 256/TC) along o; thread tile = NO outputs x 4 inputs, kept in
-// registers across all the CTA's pixel tiles of TP pixels.  partial[cta][Cout*Cin + Cout].
+// Thread tile = NO outputs x 4 inputs (NO >= 4), kept in registers across all the CTA's pixel tiles of TP pixels.  The
+// (Cin/4) x (Cout/NO) thread grid may be smaller than the CTA: the CTA then holds PG = 256/T copies of it, copy g taking the
+// pixels p = g (mod PG) of every tile and writing its own partial.  partial[cta*PG + g][Cout*Cin + Cout].
 constexpr int TP = 32;
 template <int NO>
 __global__ void __launch_bounds__(256) pw_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                                       float* __restrict__ partial, int Cin, int Cout, int HW, int B, int ntiles) {
+                                                       float* __restrict__ partial, int Cin, int Cout, int HW, int B, int ntiles,
+                                                       int TOn, int PG) {
   extern __shared__ __align__(16) float smem[];
-  const int XP = Cin + 4, YP = NO * (1024 / Cin) + 4;   // row pitches ([pixel][channel], padded, 16-byte aligned)
+  const int OC = TOn * NO;                    // outputs covered by the thread grid (>= Cout, multiple of 4)
+  const int XP = Cin + 4, YP = OC + 4;        // row pitches ([pixel][channel], padded, 16-byte aligned)
   float* x_s = smem;            // [TP][XP]
-  float* y_s = x_s + TP * XP;   // [TP][YP]   (channel index = to*NO + k)
-  const int TC = Cin >> 2, tid = threadIdx.x;
-  const int tc = tid % TC, to = tid / TC;
+  float* y_s = x_s + TP * XP;   // [TP][YP]
+  const int TC = Cin >> 2, T = TC * TOn, tid = threadIdx.x;
+  const int pg = tid / T, r = tid - pg * T;
+  const int tc = r % TC, to = r / TC;
   const int o0 = to * NO;
+  const bool active = pg < PG;
   float acc[NO][4], bacc[NO];
 #pragma unroll
   for (int k = 0; k < NO; ++k) {
@@ -94,56 +99,63 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const float* __restrict__
       int c = i / TP, p = i - c * TP;
       x_s[p * XP + c] = (p0 + p < HW) ? __ldg(x + ((size_t)b * Cin + c) * HW + p0 + p) : 0.f;
     }
-    const int OC = NO * (1024 / Cin);  // outputs covered by the thread grid (>= Cout)
     for (int i = tid; i < OC * TP; i += 256) {
       int o = i / TP, p = i - o * TP;
       y_s[p * YP + o] = (o < Cout && p0 + p < HW) ? __ldg(dy + ((size_t)b * Cout + o) * HW + p0 + p) : 0.f;
     }
     __syncthreads();
-#pragma unroll 4
-    for (int p = 0; p < TP; ++p) {
-      const float4 xv = *reinterpret_cast<const float4*>(x_s + p * XP + 4 * tc);
-      float g[NO];
-      if (NO >= 4) {
+    if (active) {
+      for (int p = pg; p < TP; p += PG) {
+        const float4 xv = *reinterpret_cast<const float4*>(x_s + p * XP + 4 * tc);
+        float g[NO];
 #pragma unroll
         for (int q = 0; q < NO / 4; ++q) {
           const float4 t = *reinterpret_cast<const float4*>(y_s + p * YP + o0 + 4 * q);
           g[4 * q] = t.x; g[4 * q + 1] = t.y; g[4 * q + 2] = t.z; g[4 * q + 3] = t.w;
         }
-      } else {
 #pragma unroll
-        for (int k = 0; k < NO; ++k) g[k] = y_s[p * YP + o0 + k];
-      }
-#pragma unroll
-      for (int k = 0; k < NO; ++k) {
-        acc[k][0] = fmaf(g[k], xv.x, acc[k][0]);
-        acc[k][1] = fmaf(g[k], xv.y, acc[k][1]);
-        acc[k][2] = fmaf(g[k], xv.z, acc[k][2]);
-        acc[k][3] = fmaf(g[k], xv.w, acc[k][3]);
-        bacc[k] += g[k];
+        for (int k = 0; k < NO; ++k) {
+          acc[k][0] = fmaf(g[k], xv.x, acc[k][0]);
+          acc[k][1] = fmaf(g[k], xv.y, acc[k][1]);
+          acc[k][2] = fmaf(g[k], xv.z, acc[k][2]);
+          acc[k][3] = fmaf(g[k], xv.w, acc[k][3]);
+          bacc[k] += g[k];
+        }
       }
     }
   }
-  float* pb = partial + (size_t)blockIdx.x * ((size_t)Cout * Cin + Cout);
+  if (active) {
+    float* pb = partial + ((size_t)blockIdx.x * PG + pg) * ((size_t)Cout * Cin + Cout);
 #pragma unroll
-  for (int k = 0; k < NO; ++k) {
-    const int o = o0 + k;
-    if (o < Cout) {
+    for (int k = 0; k < NO; ++k) {
+      const int o = o0 + k;
+      if (o < Cout) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) pb[(size_t)o * Cin + 4 * tc + e] = acc[k][e];
-      if (tc == 0) pb[(size_t)Cout * Cin + o] = bacc[k];
+        for (int e = 0; e < 4; ++e) pb[(size_t)o * Cin + 4 * tc + e] = acc[k][e];
+        if (tc == 0) pb[(size_t)Cout * Cin + o] = bacc[k];
+      }
     }
   }
 }
 
-__global__ void __launch_bounds__(128) pw_wreduce_kernel(const float* __restrict__ partial, int nparts, int n_w, int n_b,
+// fixed-order sum of the partials: CTA = 32 outputs x 8 interleaved part slices
+__global__ void __launch_bounds__(256) pw_wreduce_kernel(const float* __restrict__ partial, int nparts, int n_w, int n_b,
                                                          float* __restrict__ dw, float* __restrict__ db) {
-  int idx = blockIdx.x * 128 + threadIdx.x;
-  if (idx >= n_w + n_b) return;
+  __shared__ float red[8][33];
+  const int o = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 32 + o;
   float s = 0.f;
-  for (int k = 0; k < nparts; ++k) s += partial[(size_t)k * (n_w + n_b) + idx];
-  if (idx < n_w) dw[idx] = s;
-  else if (db) db[idx - n_w] = s;
+  if (idx < n_w + n_b)
+    for (int k = sl; k < nparts; k += 8) s += partial[(size_t)k * (n_w + n_b) + idx];
+  red[sl][o] = s;
+  __syncthreads();
+  if (sl == 0 && idx < n_w + n_b) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += red[q][o];
+    if (idx < n_w) dw[idx] = t;
+    else if (db) db[idx - n_w] = t;
+  }
 }
 
 static int check(const kmu_pwconv_desc* d, const char* who) {
@@ -153,28 +165,33 @@ static int check(const kmu_pwconv_desc* d, const char* who) {
   KMU_REQUIRE((size_t)(d->Cin > d->Cout ? d->Cin : d->Cout) * OT * 4 <= 200 * 1024, KMU_ERR_UNSUPPORTED, "%s: too many channels", who);
   return KMU_OK;
 }
+struct WgradPlan {
+  int NO, TOn, PG, ctas;
+};
 static bool wgrad_ok(const kmu_pwconv_desc& d) {
   const int c = d.Cin;
   const bool pow2 = c >= 16 && c <= 1024 && (c & (c - 1)) == 0;
-  return pow2 && d.Cout <= 16 * (1024 / c);
+  return pow2 && (long long)d.Cout * c <= 16 * 1024;
 }
-static int wgrad_no(const kmu_pwconv_desc& d) {
-  int to = 1024 / d.Cin, need = cdiv(d.Cout, to), no = 1;
-  while (no < need) no <<= 1;
-  return no;
-}
-static int wgrad_ctas(const kmu_pwconv_desc& d) {
+static WgradPlan wgrad_plan(const kmu_pwconv_desc& d) {
+  WgradPlan p;
+  p.NO = 4;
+  while ((d.Cin / 4) * cdiv(d.Cout, p.NO) > 256) p.NO <<= 1;   // <= 16 by wgrad_ok
+  p.TOn = cdiv(d.Cout, p.NO);
+  p.PG = 256 / ((d.Cin / 4) * p.TOn);
+  if (p.PG > 8) p.PG = 8;
   long long tiles = (long long)d.B * cdiv(d.HW, TP);
-  return (int)(tiles < 296 ? tiles : 296);
+  p.ctas = (int)(tiles < 296 ? tiles : 296);
+  return p;
 }
 
 template <int NO>
-static void launch_wgrad(const kmu_pwconv_desc& d, const float* x, const float* dy, float* partial, cudaStream_t st) {
-  const int XP = d.Cin + 4, YP = NO * (1024 / d.Cin) + 4;
+static void launch_wgrad(const kmu_pwconv_desc& d, const WgradPlan& pl, const float* x, const float* dy, float* partial, cudaStream_t st) {
+  const int XP = d.Cin + 4, YP = pl.TOn * NO + 4;
   size_t smem = (size_t)TP * (XP + YP) * 4;
   if (smem > 48 * 1024) cudaFuncSetAttribute(pw_wgrad_kernel<NO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int ntiles = d.B * cdiv(d.HW, TP);
-  pw_wgrad_kernel<NO><<<wgrad_ctas(d), 256, smem, st>>>(x, dy, partial, d.Cin, d.Cout, d.HW, d.B, ntiles);
+  pw_wgrad_kernel<NO><<<pl.ctas, 256, smem, st>>>(x, dy, partial, d.Cin, d.Cout, d.HW, d.B, ntiles, pl.TOn, pl.PG);
 }
 
 }  // namespace pw
@@ -190,7 +207,8 @@ int kmu_pwconv_wgrad_supported(const kmu_pwconv_desc* d) { return (d && wgrad_ok
 size_t kmu_pwconv_bwd_workspace_bytes(const kmu_pwconv_desc* d) {
   if (check(d, "pwconv_bwd_workspace_bytes") != KMU_OK) return 0;
   if (!wgrad_ok(*d)) return 256;
-  return align_up((size_t)wgrad_ctas(*d) * ((size_t)d->Cout * d->Cin + d->Cout) * 4, 256);
+  WgradPlan pl = wgrad_plan(*d);
+  return align_up((size_t)pl.ctas * pl.PG * ((size_t)d->Cout * d->Cin + d->Cout) * 4, 256);
 }
 
 int kmu_pwconv_fwd(const kmu_pwconv_desc* d, const float* x, const float* w, const float* bias, float* y, kmu_stream stream) {
@@ -219,20 +237,19 @@ int kmu_pwconv_bwd(const kmu_pwconv_desc* d, const float* x, const float* dy, co
   }
   if (dw) {
     KMU_REQUIRE(x != nullptr, KMU_ERR_BAD_ARG, "pwconv_bwd: weight gradient needs x");
-    KMU_REQUIRE(wgrad_ok(*d), KMU_ERR_UNSUPPORTED, "pwconv_bwd: weight gradient needs Cin a power of two in [16,1024] and Cout <= 16*1024/Cin "
+    KMU_REQUIRE(wgrad_ok(*d), KMU_ERR_UNSUPPORTED, "pwconv_bwd: weight gradient needs Cin a power of two in [16,1024] and Cin*Cout <= 16384 "
                 "(got %d -> %d)", d->Cin, d->Cout);
     KMU_REQUIRE(workspace && workspace_bytes >= kmu_pwconv_bwd_workspace_bytes(d), KMU_ERR_WORKSPACE, "pwconv_bwd: workspace too small");
     float* partial = (float*)workspace;
-    switch (wgrad_no(*d)) {
-      case 1: launch_wgrad<1>(*d, x, dy, partial, st); break;
-      case 2: launch_wgrad<2>(*d, x, dy, partial, st); break;
-      case 4: launch_wgrad<4>(*d, x, dy, partial, st); break;
-      case 8: launch_wgrad<8>(*d, x, dy, partial, st); break;
-      default: launch_wgrad<16>(*d, x, dy, partial, st); break;
+    const WgradPlan pl = wgrad_plan(*d);
+    switch (pl.NO) {
+      case 4: launch_wgrad<4>(*d, pl, x, dy, partial, st); break;
+      case 8: launch_wgrad<8>(*d, pl, x, dy, partial, st); break;
+      default: launch_wgrad<16>(*d, pl, x, dy, partial, st); break;
     }
     KMU_LAUNCH_CHECK("pw_wgrad");
     const int n_w = d->Cout * d->Cin, n_b = d->Cout;
-    pw_wreduce_kernel<<<cdiv(n_w + n_b, 128), 128, 0, st>>>(partial, wgrad_ctas(*d), n_w, n_b, dw, dbias);
+    pw_wreduce_kernel<<<cdiv(n_w + n_b, 32), 256, 0, st>>>(partial, pl.ctas * pl.PG, n_w, n_b, dw, dbias);
     KMU_LAUNCH_CHECK("pw_wreduce");
   }
   return KMU_OK;

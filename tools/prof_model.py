@@ -35,7 +35,12 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_sh
     for _ in range(2):
         step()
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
+rows = [(e.key, e.self_device_time_total / 2000.0, e.count // 2) for e in prof.key_averages() if e.self_device_time_total > 0]
+rows.sort(key=lambda r: -r[1])
+tot = sum(r[1] for r in rows)
+print(f"GPU ms per step {tot:.2f}")
+for k, ms, n in rows[:70]:
+    print(f"{ms:8.3f} ms {n:5d}x  {k[:110]}")
 # module-level attribution with hooks
 import collections
 tot = collections.defaultdict(float)
