@@ -13,11 +13,12 @@
 namespace kmu {
 namespace pw {
 
-constexpr int OT = 32;   // outputs per thread pass
-constexpr int NTH = 128; // threads per CTA (forward / dgrad); each thread owns 2 pixels
+constexpr int OTMAX = 32; // outputs per thread pass (16 when the layer has <= 16 outputs)
+constexpr int NTH = 128;  // threads per CTA (forward / dgrad); each thread owns 2 pixels
 
 // y[b, j0+j, p] = bias[j0+j] + sum_i Wt[i][j] in[b, i, p]; Wt[i][j] = W[j*NI + i] (forward) or W[i*NJ_total + j] (dgrad: in = dy)
 // grid (ceil(HW / (2*NTH)), ceil(NJ/OT), B)
+template <int OT>
 __global__ void __launch_bounds__(NTH) pw_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                  const float* __restrict__ bias, float* __restrict__ out, int NI, int NJ, int HW,
                                                  int dgrad) {
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(NTH) pw_kernel(const float* __restrict__ in, c
 // Thread tile = NO outputs x 4 inputs (NO >= 4), kept in registers across all the CTA's pixel tiles of TP pixels.  The
 // (Cin/4) x (Cout/NO) thread grid may be smaller than the CTA: the CTA then holds PG = 256/T copies of it, copy g taking the
 // pixels p = g (mod PG) of every tile and writing its own partial.  partial[cta*PG + g][Cout*Cin + Cout].
-constexpr int TP = 32;
+constexpr int TP = 64;
 template <int NO>
 __global__ void __launch_bounds__(256) pw_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                        float* __restrict__ partial, int Cin, int Cout, int HW, int B, int ntiles,
@@ -95,12 +96,16 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const float* __restrict__
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int b = tile / tiles_per_img, p0 = (tile - b * tiles_per_img) * TP;
     __syncthreads();
+    // transposing stage-in: a warp covers 8 consecutive pixels x 4 channels, so its 32 stores ([pixel][channel] rows whose
+    // pitch is an odd number of 16-byte groups) hit 32 different banks while every global access is a full 32-byte sector
     for (int i = tid; i < Cin * TP; i += 256) {
-      int c = i / TP, p = i - c * TP;
+      const int rest = i >> 5;
+      const int p = (rest % (TP / 8)) * 8 + (i & 7), c = (rest / (TP / 8)) * 4 + ((i >> 3) & 3);
       x_s[p * XP + c] = (p0 + p < HW) ? __ldg(x + ((size_t)b * Cin + c) * HW + p0 + p) : 0.f;
     }
     for (int i = tid; i < OC * TP; i += 256) {
-      int o = i / TP, p = i - o * TP;
+      const int rest = i >> 5;
+      const int p = (rest % (TP / 8)) * 8 + (i & 7), o = (rest / (TP / 8)) * 4 + ((i >> 3) & 3);
       y_s[p * YP + o] = (o < Cout && p0 + p < HW) ? __ldg(dy + ((size_t)b * Cout + o) * HW + p0 + p) : 0.f;
     }
     __syncthreads();
@@ -162,9 +167,22 @@ static int check(const kmu_pwconv_desc* d, const char* who) {
   KMU_REQUIRE(d != nullptr, KMU_ERR_BAD_ARG, "%s: null descriptor", who);
   KMU_REQUIRE(d->B > 0 && d->Cin > 0 && d->Cout > 0 && d->HW > 0, KMU_ERR_BAD_ARG, "%s: non-positive shape", who);
   KMU_REQUIRE(d->B <= 65535, KMU_ERR_UNSUPPORTED, "%s: B=%d > 65535", who, d->B);
-  KMU_REQUIRE((size_t)(d->Cin > d->Cout ? d->Cin : d->Cout) * OT * 4 <= 200 * 1024, KMU_ERR_UNSUPPORTED, "%s: too many channels", who);
+  KMU_REQUIRE((size_t)(d->Cin > d->Cout ? d->Cin : d->Cout) * OTMAX * 4 <= 200 * 1024, KMU_ERR_UNSUPPORTED, "%s: too many channels", who);
   return KMU_OK;
 }
+static void launch_pw(const float* in, const float* w, const float* bias, float* out, int NI, int NJ, int HW, int B, int dgrad,
+                      cudaStream_t st) {
+  if (NJ <= 16) {
+    size_t smem = (size_t)NI * 16 * 4;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(pw_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    pw_kernel<16><<<dim3(cdiv(HW, 2 * NTH), 1, B), NTH, smem, st>>>(in, w, bias, out, NI, NJ, HW, dgrad);
+  } else {
+    size_t smem = (size_t)NI * 32 * 4;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(pw_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    pw_kernel<32><<<dim3(cdiv(HW, 2 * NTH), cdiv(NJ, 32), B), NTH, smem, st>>>(in, w, bias, out, NI, NJ, HW, dgrad);
+  }
+}
+
 struct WgradPlan {
   int NO, TOn, PG, ctas;
 };
@@ -215,10 +233,7 @@ int kmu_pwconv_fwd(const kmu_pwconv_desc* d, const float* x, const float* w, con
   int rc = check(d, "pwconv_fwd");
   if (rc != KMU_OK) return rc;
   KMU_REQUIRE(x && w && y, KMU_ERR_BAD_ARG, "pwconv_fwd: null tensor");
-  size_t smem = (size_t)d->Cin * OT * 4;
-  if (smem > 48 * 1024) cudaFuncSetAttribute(pw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  pw_kernel<<<dim3(cdiv(d->HW, 2 * NTH), cdiv(d->Cout, OT), d->B), NTH, smem, (cudaStream_t)stream>>>(x, w, bias, y, d->Cin, d->Cout,
-                                                                                                    d->HW, 0);
+  launch_pw(x, w, bias, y, d->Cin, d->Cout, d->HW, d->B, 0, (cudaStream_t)stream);
   KMU_LAUNCH_CHECK("pw_fwd");
   return KMU_OK;
 }
@@ -230,9 +245,7 @@ int kmu_pwconv_bwd(const kmu_pwconv_desc* d, const float* x, const float* dy, co
   KMU_REQUIRE(dy && w, KMU_ERR_BAD_ARG, "pwconv_bwd: null tensor");
   cudaStream_t st = (cudaStream_t)stream;
   if (dx) {
-    size_t smem = (size_t)d->Cout * OT * 4;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(pw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    pw_kernel<<<dim3(cdiv(d->HW, 2 * NTH), cdiv(d->Cin, OT), d->B), NTH, smem, st>>>(dy, w, nullptr, dx, d->Cout, d->Cin, d->HW, 1);
+    launch_pw(dy, w, nullptr, dx, d->Cout, d->Cin, d->HW, d->B, 1, st);
     KMU_LAUNCH_CHECK("pw_dgrad");
   }
   if (dw) {

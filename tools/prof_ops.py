@@ -32,4 +32,28 @@ if what in ("dys", "all"):
         run(K.DySample(64).to(dev), torch.randn(B, 64, S, S, device=dev, requires_grad=True))
 if what in ("dagem", "all"):
     run(K.DAGEM(input_channels=64).to(dev), torch.randn(B, 64, 16, 16, device=dev, requires_grad=True))
+if what in ("pw", "all"):
+    from km_unet_b200 import ops
+    for cin, cout, S in [(16, 64, 128), (64, 16, 128), (16, 48, 128), (32, 128, 64), (64, 256, 32)]:
+        w = torch.randn(cout, cin, 1, 1, device=dev, requires_grad=True)
+        bb = torch.randn(cout, device=dev, requires_grad=True)
+        x = torch.randn(B, cin, S, S, device=dev, requires_grad=True)
+        for _ in range(reps):
+            y = ops.pwconv(x, w, bb)
+            y.backward(torch.ones_like(y))
+        torch.cuda.synchronize()
+if what in ("shell", "all"):
+    from km_unet_b200 import ops
+    for C, S in [(16, 128), (64, 128), (32, 64)]:
+        x = torch.randn(B, C, S, S, device=dev, requires_grad=True)
+        r = torch.randn(B, C, S, S, device=dev, requires_grad=True)
+        w = torch.ones(C, device=dev, requires_grad=True)
+        bb = torch.zeros(C, device=dev, requires_grad=True)
+        al = torch.zeros(C, device=dev, requires_grad=True)
+        rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+        wd = torch.randn(C, 1, 3, 3, device=dev, requires_grad=True)
+        for _ in range(reps):
+            y = ops.bnmix(ops.dwconv3x3(x, wd), w, bb, rm, rv, True, 0.1, 1e-5, False, r, al)
+            y.backward(torch.ones_like(y))
+        torch.cuda.synchronize()
 print("ok")
