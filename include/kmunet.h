@@ -372,6 +372,57 @@ int kmu_pwconv_fwd(const kmu_pwconv_desc* d, const float* x, const float* w /* (
 int kmu_pwconv_bwd(const kmu_pwconv_desc* d, const float* x, const float* dy, const float* w, float* dx, float* dw, float* dbias,
                    void* workspace, size_t workspace_bytes, kmu_stream stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Caller-side fusions
+ *   kmu_triplenorm: TripleNorm.forward, KM_UNetV3_SH.py:277-284:
+ *       y = (GroupNorm(1,C; gh,bh)(x) + GroupNorm(1,C; gw,bw)(x) + LayerNorm_C(gc,bc)(x)) / 3     x (B,C,HW), C in {16,32,64}
+ *   kmu_qkv_gate:   DirectionAttention.forward, KM_UNetV3_SH.py:259-261:  out = sigmoid(q k) v, qkv (B,3C,HW) -> (B,C,HW)
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t B, C, HW;
+  float eps_gn, eps_ln;
+} kmu_triplenorm_desc;
+
+typedef struct {
+  kmu_triplenorm_desc d;
+  const float* x;
+  const float* gh; /* norm_h.weight (C) */
+  const float* bh;
+  const float* gw; /* norm_w.weight */
+  const float* bw;
+  const float* gc; /* norm_c.weight */
+  const float* bc;
+  float* y;
+  float* gstat; /* (B,2) per-sample mean, rstd: input of the backward call */
+  void* workspace;
+  size_t workspace_bytes;
+} kmu_triplenorm_fwd_args;
+
+typedef struct {
+  kmu_triplenorm_desc d;
+  const float* x;
+  const float* dy;
+  const float* gstat;
+  const float* gh;
+  const float* gw;
+  const float* gc;
+  float* dx;
+  float* d_gh;
+  float* d_bh;
+  float* d_gw;
+  float* d_bw;
+  float* d_gc;
+  float* d_bc;
+  void* workspace;
+  size_t workspace_bytes;
+} kmu_triplenorm_bwd_args;
+
+size_t kmu_triplenorm_workspace_bytes(const kmu_triplenorm_desc* d);
+int kmu_triplenorm_fwd(const kmu_triplenorm_fwd_args* a, kmu_stream stream);
+int kmu_triplenorm_bwd(const kmu_triplenorm_bwd_args* a, kmu_stream stream);
+int kmu_qkv_gate_fwd(const float* qkv, float* out, int32_t B, int32_t C, int32_t HW, kmu_stream stream);
+int kmu_qkv_gate_bwd(const float* qkv, const float* dout, float* dqkv, int32_t B, int32_t C, int32_t HW, kmu_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -108,6 +108,20 @@ class PwDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("B", "Cin", "Cout", "HW")]
 
 
+class TnDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B", "C", "HW")] + [("eps_gn", C.c_float), ("eps_ln", C.c_float)]
+
+
+class TnFwdArgs(C.Structure):
+    _fields_ = [("d", TnDesc)] + [(n, _f32p) for n in ("x", "gh", "bh", "gw", "bw", "gc", "bc", "y", "gstat")] + \
+               [("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+class TnBwdArgs(C.Structure):
+    _fields_ = [("d", TnDesc)] + [(n, _f32p) for n in ("x", "dy", "gstat", "gh", "gw", "gc", "dx", "d_gh", "d_bh", "d_gw", "d_bw",
+                                                       "d_gc", "d_bc")] + [("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
 # every symbol include/kmunet.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "kmu_version": (C.c_int, []),
@@ -143,6 +157,11 @@ SYMBOLS = {
     "kmu_pwconv_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(PwDesc)]),
     "kmu_pwconv_fwd": (C.c_int, [C.POINTER(PwDesc), _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
     "kmu_pwconv_bwd": (C.c_int, [C.POINTER(PwDesc), _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kmu_triplenorm_workspace_bytes": (C.c_size_t, [C.POINTER(TnDesc)]),
+    "kmu_triplenorm_fwd": (C.c_int, [C.POINTER(TnFwdArgs), C.c_void_p]),
+    "kmu_triplenorm_bwd": (C.c_int, [C.POINTER(TnBwdArgs), C.c_void_p]),
+    "kmu_qkv_gate_fwd": (C.c_int, [_f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "kmu_qkv_gate_bwd": (C.c_int, [_f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "kmu_dagem_saved_bytes": (C.c_size_t, [C.POINTER(DagemDesc)]),
     "kmu_dagem_fwd_workspace_bytes": (C.c_size_t, [C.POINTER(DagemDesc)]),
     "kmu_dagem_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(DagemDesc)]),

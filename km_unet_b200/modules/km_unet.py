@@ -78,8 +78,8 @@ class DirectionAttention(nn.Module):
     def forward(self, x):
         # the three pooling modes of the reference (mean over W then H, over H then W, or both) are the same global mean
         weight = self.fc(x.mean(dim=(2, 3)))
-        q, k, v = conv1x1(x, self.qkv.weight, self.qkv.bias).chunk(3, dim=1)
-        return ops.dwconv3x3(torch.sigmoid(q * k) * v, self.conv.weight, self.conv.bias) * weight[:, :, None, None]
+        attn = ops.qkv_gate(conv1x1(x, self.qkv.weight, self.qkv.bias))          # sigmoid(q k) v
+        return ops.dwconv3x3(attn, self.conv.weight, self.conv.bias) * weight[:, :, None, None]
 
 
 class DirectionViM(nn.Module):
@@ -111,6 +111,9 @@ class TripleNorm(nn.Module):
         self.norm_c = nn.LayerNorm(dim)
 
     def forward(self, x):
+        if ops.triplenorm_supported(x.shape[1]):
+            return ops.triplenorm(x, self.norm_h.weight, self.norm_h.bias, self.norm_w.weight, self.norm_w.bias, self.norm_c.weight,
+                                  self.norm_c.bias, self.norm_h.eps, self.norm_c.eps)
         c = self.norm_c(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
         return (self.norm_h(x) + self.norm_w(x) + c) / 3
 

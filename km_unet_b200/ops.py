@@ -9,10 +9,10 @@ import torch
 from torch.amp import custom_bwd, custom_fwd
 
 from . import _lib
-from ._lib import (PwDesc, BnMixBwdArgs, BnMixDesc, BnMixFwdArgs, DwDesc, DagemBn, DagemBwdArgs, DagemDesc, DagemFwdArgs, DysBwdArgs, DysDesc, DysFwdArgs, HsmBwdArgs, HsmDesc, HsmFwdArgs, KanBwdArgs, KanDesc, KanFwdArgs,
+from ._lib import (TnBwdArgs, TnDesc, TnFwdArgs, PwDesc, BnMixBwdArgs, BnMixDesc, BnMixFwdArgs, DwDesc, DagemBn, DagemBwdArgs, DagemDesc, DagemFwdArgs, DysBwdArgs, DysDesc, DysFwdArgs, HsmBwdArgs, HsmDesc, HsmFwdArgs, KanBwdArgs, KanDesc, KanFwdArgs,
                    KMU_PREC_BF16, KMU_PREC_FP32, check, ptr, stream_ptr)
 
-__all__ = ["kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dysample_sample", "dagem_gate", "bnmix", "dwconv3x3", "pwconv", "pwconv_supported", "KMU_PREC_FP32", "KMU_PREC_BF16"]
+__all__ = ["kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dysample_sample", "dagem_gate", "bnmix", "dwconv3x3", "pwconv", "pwconv_supported", "triplenorm", "qkv_gate", "KMU_PREC_FP32", "KMU_PREC_BF16"]
 
 
 # ------------------------------------------------------------------------------------------------------ op-level timing
@@ -533,3 +533,89 @@ def pwconv(x, weight, bias=None):
     if not x.is_cuda:
         raise RuntimeError("km_unet_b200.pwconv: CUDA tensors only (no CPU fallback)")
     return _PwConvFn.apply(x, weight, bias)
+
+
+# ------------------------------------------------------------------------------------------------------ caller-side fusions
+class _TripleNormFn(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, gh, bh, gw, bw, gc, bc, eps_gn, eps_ln):
+        lib = _lib.lib()
+        x = x.contiguous()
+        B, Cc = x.shape[0], x.shape[1]
+        HW = x.numel() // (B * Cc)
+        desc = TnDesc(B, Cc, HW, float(eps_gn), float(eps_ln))
+        nbytes = lib.kmu_triplenorm_workspace_bytes(C.byref(desc))
+        if nbytes == 0:
+            raise RuntimeError("triplenorm: " + _lib.last_error())
+        ps = [t.contiguous() for t in (gh, bh, gw, bw, gc, bc)]
+        y = torch.empty_like(x)
+        gstat = torch.empty(B, 2, dtype=torch.float32, device=x.device)
+        ws = _workspace(nbytes, x.device)
+        args = TnFwdArgs(desc, ptr(x), *[ptr(t) for t in ps], ptr(y), ptr(gstat), ws.data_ptr(), ws.numel())
+        check(_call("kmu_triplenorm_fwd", (B, Cc, HW), lib.kmu_triplenorm_fwd, C.byref(args), stream_ptr()), "kmu_triplenorm_fwd")
+        ctx.save_for_backward(x, gstat, ps[0], ps[2], ps[4])
+        ctx.desc = desc
+        return y
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        lib = _lib.lib()
+        x, gstat, gh, gw, gc = ctx.saved_tensors
+        desc = ctx.desc
+        dy = dy.to(torch.float32).contiguous()
+        dx = torch.empty_like(x)
+        grads = [torch.empty_like(gh) for _ in range(6)]
+        ws = _workspace(lib.kmu_triplenorm_workspace_bytes(C.byref(desc)), x.device)
+        args = TnBwdArgs(desc, ptr(x), ptr(dy), ptr(gstat), ptr(gh), ptr(gw), ptr(gc), ptr(dx), *[ptr(t) for t in grads], ws.data_ptr(),
+                         ws.numel())
+        check(_call("kmu_triplenorm_bwd", (desc.B, desc.C, desc.HW), lib.kmu_triplenorm_bwd, C.byref(args), stream_ptr()),
+              "kmu_triplenorm_bwd")
+        return (dx, *grads, None, None)
+
+
+def triplenorm_supported(channels):
+    return channels in (16, 32, 64)
+
+
+def triplenorm(x, gh, bh, gw, bw, gc, bc, eps_gn=1e-5, eps_ln=1e-5):
+    """TripleNorm.forward (KM_UNetV3_SH.py:277-284): (GN1(x; gh,bh) + GN1(x; gw,bw) + LayerNorm over C (gc,bc)) / 3."""
+    if not x.is_cuda:
+        raise RuntimeError("km_unet_b200.triplenorm: CUDA tensors only (no CPU fallback)")
+    return _TripleNormFn.apply(x, gh, bh, gw, bw, gc, bc, eps_gn, eps_ln)
+
+
+class _QkvGateFn(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, qkv):
+        lib = _lib.lib()
+        qkv = qkv.contiguous()
+        B, C3 = qkv.shape[0], qkv.shape[1]
+        Cc = C3 // 3
+        HW = qkv.numel() // (B * C3)
+        out = torch.empty((B, Cc) + tuple(qkv.shape[2:]), dtype=torch.float32, device=qkv.device)
+        check(_call("kmu_qkv_gate_fwd", (B, Cc, HW), lib.kmu_qkv_gate_fwd, ptr(qkv), ptr(out), B, Cc, HW, stream_ptr()), "kmu_qkv_gate_fwd")
+        ctx.save_for_backward(qkv)
+        ctx.dims = (B, Cc, HW)
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dout):
+        lib = _lib.lib()
+        (qkv,) = ctx.saved_tensors
+        B, Cc, HW = ctx.dims
+        dout = dout.to(torch.float32).contiguous()
+        dqkv = torch.empty_like(qkv)
+        check(_call("kmu_qkv_gate_bwd", (B, Cc, HW), lib.kmu_qkv_gate_bwd, ptr(qkv), ptr(dout), ptr(dqkv), B, Cc, HW, stream_ptr()),
+              "kmu_qkv_gate_bwd")
+        return dqkv
+
+
+def qkv_gate(qkv):
+    """DirectionAttention's gate (KM_UNetV3_SH.py:259-261): sigmoid(q * k) * v on the channel thirds of qkv (B,3C,H,W)."""
+    if not qkv.is_cuda:
+        raise RuntimeError("km_unet_b200.qkv_gate: CUDA tensors only (no CPU fallback)")
+    return _QkvGateFn.apply(qkv)

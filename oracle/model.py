@@ -57,6 +57,21 @@ def _pwconv(x, weight, bias=None):
     return F.conv2d(x, weight.reshape(weight.shape[0], weight.shape[1], 1, 1), bias)
 
 
+def _triplenorm(x, gh, bh, gw, bw, gc, bc, eps_gn=1e-5, eps_ln=1e-5):
+    """KM_UNetV3_SH.py:277-284, literally (incl. the permutes)."""
+    import torch.nn.functional as F
+    h = F.group_norm(x.permute(0, 1, 3, 2), 1, gh, bh, eps_gn).permute(0, 1, 3, 2)
+    w = F.group_norm(x, 1, gw, bw, eps_gn)
+    c = F.layer_norm(x.permute(0, 2, 3, 1), (x.shape[1],), gc, bc, eps_ln).permute(0, 3, 1, 2)
+    return (h + w + c) / 3
+
+
+def _qkv_gate(qkv):
+    import torch
+    q, k, v = qkv.chunk(3, dim=1)
+    return torch.sigmoid(q * k) * v
+
+
 def _gate(x, deformed, linears, bns, training, momentum=0.1, eps=1e-5):
     return _dagem.dagem_gate(x, deformed, linears, bns, training)
 
@@ -65,10 +80,11 @@ def _gate(x, deformed, linears, bns, training, momentum=0.1, eps=1e-5):
 def cpu_ops():
     from km_unet_b200 import ops
     saved = {n: getattr(ops, n) for n in ("kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dagem_gate", "bnmix",
-                                          "dwconv3x3", "pwconv")}
+                                          "dwconv3x3", "pwconv", "triplenorm", "qkv_gate")}
     ops.kanconv2d, ops.kanlinear, ops.layernorm1d = _kanconv2d, _kanlinear, _hsmssd.layernorm1d
     ops.hsmssd, ops.dysample, ops.dagem_gate = _hsm, _dys, _gate
     ops.bnmix, ops.dwconv3x3, ops.pwconv = _bnmix, _dwconv3x3, _pwconv
+    ops.triplenorm, ops.qkv_gate = _triplenorm, _qkv_gate
     try:
         yield
     finally:

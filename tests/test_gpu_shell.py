@@ -114,3 +114,43 @@ def test_pwconv_unsupported_pairs_are_reported():
     from km_unet_b200 import ops
     assert not ops.pwconv_supported(17, 16)      # IWP fusion conv (C + 1 inputs) stays a library conv
     assert not ops.pwconv_supported(96, 32)
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 16, 32, 32), (3, 32, 7, 9), (2, 64, 8, 8), (4, 16, 128, 128)])
+def test_triplenorm_vs_reference_composition(B, C, H, W):
+    """KM_UNetV3_SH.py:277-284 restated literally in torch fp64 (two GroupNorm(1), permuted LayerNorm, /3)."""
+    from km_unet_b200 import ops
+    from oracle.model import _triplenorm
+    torch.manual_seed(C * H)
+    x = torch.randn(B, C, H, W) * 1.3 + 0.2
+    ps = [torch.rand(C) + 0.5 if i % 2 == 0 else torch.randn(C) * 0.2 for i in range(6)]
+    gout = torch.randn(B, C, H, W)
+    xd = x.double().requires_grad_(True)
+    pd = [p.double().requires_grad_(True) for p in ps]
+    want = _triplenorm(xd, *pd)
+    want.backward(gout.double())
+    xc = x.cuda().requires_grad_(True)
+    pc = [p.cuda().requires_grad_(True) for p in ps]
+    y = ops.triplenorm(xc, *pc)
+    assert rel_err(y, want) < TOL
+    y.backward(gout.cuda())
+    assert rel_err(xc.grad, xd.grad) < TOL
+    for a, b in zip(pc, pd):
+        assert rel_err(a.grad, b.grad) < TOL
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 16, 16, 16), (3, 8, 5, 7), (4, 16, 128, 128)])
+def test_qkv_gate_vs_torch(B, C, H, W):
+    from km_unet_b200 import ops
+    torch.manual_seed(C + W)
+    qkv = torch.randn(B, 3 * C, H, W)
+    gout = torch.randn(B, C, H, W)
+    qd = qkv.double().requires_grad_(True)
+    q, k, v = qd.chunk(3, dim=1)
+    want = torch.sigmoid(q * k) * v
+    want.backward(gout.double())
+    qc = qkv.cuda().requires_grad_(True)
+    y = ops.qkv_gate(qc)
+    assert rel_err(y, want) < TOL
+    y.backward(gout.cuda())
+    assert rel_err(qc.grad, qd.grad) < TOL
