@@ -423,6 +423,21 @@ int kmu_triplenorm_bwd(const kmu_triplenorm_bwd_args* a, kmu_stream stream);
 int kmu_qkv_gate_fwd(const float* qkv, float* out, int32_t B, int32_t C, int32_t HW, kmu_stream stream);
 int kmu_qkv_gate_bwd(const float* qkv, const float* dout, float* dqkv, int32_t B, int32_t C, int32_t HW, kmu_stream stream);
 
+/* Dense "same" convolution with at most 9 taps (1x1, 1x3, 3x1, 3x3; stride 1, zero padding k/2) on NCHW:
+ * DirectionViM.proj (KM_UNetV3_SH.py:172-176), the decoder / fusion 3x3 convs (:292,299,427,437,439).
+ * w (Cout,Cin,kh,kw).  kmu_smallconv_supported: the weight-gradient kernel needs Cin a power of two in [16,1024],
+ * Cin*Cout <= 16384, and Cin*kh*kw*128 bytes of weights must fit shared memory. */
+typedef struct {
+  int32_t B, Cin, Cout, H, W, kh, kw;
+} kmu_smallconv_desc;
+
+int kmu_smallconv_supported(const kmu_smallconv_desc* d);
+size_t kmu_smallconv_bwd_workspace_bytes(const kmu_smallconv_desc* d);
+int kmu_smallconv_fwd(const kmu_smallconv_desc* d, const float* x, const float* w, const float* bias /* or NULL */, float* y,
+                      kmu_stream stream);
+int kmu_smallconv_bwd(const kmu_smallconv_desc* d, const float* x, const float* dy, const float* w, float* dx, float* dw,
+                      float* dbias, void* workspace, size_t workspace_bytes, kmu_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

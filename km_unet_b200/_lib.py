@@ -122,6 +122,10 @@ class TnBwdArgs(C.Structure):
                                                        "d_gc", "d_bc")] + [("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
+class ScDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B", "Cin", "Cout", "H", "W", "kh", "kw")]
+
+
 # every symbol include/kmunet.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "kmu_version": (C.c_int, []),
@@ -162,6 +166,10 @@ SYMBOLS = {
     "kmu_triplenorm_bwd": (C.c_int, [C.POINTER(TnBwdArgs), C.c_void_p]),
     "kmu_qkv_gate_fwd": (C.c_int, [_f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "kmu_qkv_gate_bwd": (C.c_int, [_f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "kmu_smallconv_supported": (C.c_int, [C.POINTER(ScDesc)]),
+    "kmu_smallconv_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(ScDesc)]),
+    "kmu_smallconv_fwd": (C.c_int, [C.POINTER(ScDesc), _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
+    "kmu_smallconv_bwd": (C.c_int, [C.POINTER(ScDesc), _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kmu_dagem_saved_bytes": (C.c_size_t, [C.POINTER(DagemDesc)]),
     "kmu_dagem_fwd_workspace_bytes": (C.c_size_t, [C.POINTER(DagemDesc)]),
     "kmu_dagem_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(DagemDesc)]),

@@ -22,7 +22,14 @@ from .. import ops
 from .dagem import DAGEM
 from .dysample import DySample
 from .kan import KANConv2d
-from .vim import EfficientViMBlock, conv1x1
+from .vim import EfficientViMBlock, conv1x1, conv_same
+
+
+def _run(seq, x):
+    """nn.Sequential forward with the plain convolutions routed through the streaming CUDA kernels where they apply."""
+    for m in seq:
+        x = conv_same(m, x) if type(m) is nn.Conv2d else m(x)
+    return x
 
 
 class DropPath(nn.Module):
@@ -97,8 +104,7 @@ class DirectionViM(nn.Module):
         self.attn = DirectionAttention(dim, mode)
 
     def forward(self, x):
-        x = conv1x1(x, self.proj.weight, self.proj.bias) if self.mode == 'channel' else self.proj(x)
-        return self.attn(self.vit_mamba(x))
+        return self.attn(self.vit_mamba(conv_same(self.proj, x)))
 
 
 class TripleNorm(nn.Module):
@@ -159,7 +165,7 @@ class MultiScaleFusion(nn.Module):
         self.fusion = nn.Sequential(nn.Conv2d(out * 3, out, 1), nn.Conv2d(out, out, 3, padding=1), ChannelAttention(out, reduction))
 
     def forward(self, features):
-        return self.fusion(torch.cat([blk(f) for blk, f in zip(self.blocks, features)], dim=1))
+        return _run(self.fusion, torch.cat([_run(blk, f) for blk, f in zip(self.blocks, features)], dim=1))
 
 
 class LocalContrastAttention(nn.Module):
@@ -256,9 +262,9 @@ class KM_UNetV3(nn.Module):
             e3 = self.bridge_attention(e3)
         d1 = self.dec1(e3)
         d1 = torch.cat([d1, self.attention1(self._skips(e1, e2, d1.shape[2:]))], dim=1)
-        d2 = self.dec2(d1)
+        d2 = _run(self.dec2, d1)
         d2 = torch.cat([d2, self.attention2(self._skips(e1, e2, d2.shape[2:]))], dim=1)
-        return self.activation(self.output_norm(self.dec3(d2)))
+        return self.activation(self.output_norm(_run(self.dec3, d2)))
 
 
 def KM_UNetV3_SH(num_classes=3, embed_dims=(16, 32, 64)):

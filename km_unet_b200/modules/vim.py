@@ -77,6 +77,20 @@ def conv1x1(x, weight, bias=None):
     return torch.nn.functional.conv2d(x, weight.reshape(weight.shape[0], weight.shape[1], 1, 1), bias)
 
 
+def conv_same(conv, x):
+    """An nn.Conv2d with stride 1 and 'same' zero padding through the streaming CUDA kernels when they cover it (1x1 and
+    <= 9-tap dense kernels with power-of-two input channels); anything else stays the library convolution."""
+    kh, kw = conv.kernel_size
+    plain = (conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1 and conv.padding == (kh // 2, kw // 2)
+             and conv.padding_mode == "zeros")
+    if plain and kh == kw == 1:
+        return conv1x1(x, conv.weight, conv.bias)
+    # 3x3 and larger stay on cuDNN: the per-tap weight-gradient passes re-read dy once per tap, which only pays for <= 3 taps
+    if plain and kh * kw <= 3 and ops.smallconv_supported(conv.in_channels, conv.out_channels, kh, kw):
+        return ops.smallconv(x, conv.weight, conv.bias)
+    return conv(x)
+
+
 def _bn2d(bn, x, relu=False, res=None, alpha=None):
     """BatchNorm2d module `bn` applied through the fused CUDA op (keeps the module's parameters, buffers and counters)."""
     training = bn.training or bn.running_mean is None

@@ -9,10 +9,10 @@ import torch
 from torch.amp import custom_bwd, custom_fwd
 
 from . import _lib
-from ._lib import (TnBwdArgs, TnDesc, TnFwdArgs, PwDesc, BnMixBwdArgs, BnMixDesc, BnMixFwdArgs, DwDesc, DagemBn, DagemBwdArgs, DagemDesc, DagemFwdArgs, DysBwdArgs, DysDesc, DysFwdArgs, HsmBwdArgs, HsmDesc, HsmFwdArgs, KanBwdArgs, KanDesc, KanFwdArgs,
+from ._lib import (ScDesc, TnBwdArgs, TnDesc, TnFwdArgs, PwDesc, BnMixBwdArgs, BnMixDesc, BnMixFwdArgs, DwDesc, DagemBn, DagemBwdArgs, DagemDesc, DagemFwdArgs, DysBwdArgs, DysDesc, DysFwdArgs, HsmBwdArgs, HsmDesc, HsmFwdArgs, KanBwdArgs, KanDesc, KanFwdArgs,
                    KMU_PREC_BF16, KMU_PREC_FP32, check, ptr, stream_ptr)
 
-__all__ = ["kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dysample_sample", "dagem_gate", "bnmix", "dwconv3x3", "pwconv", "pwconv_supported", "triplenorm", "qkv_gate", "KMU_PREC_FP32", "KMU_PREC_BF16"]
+__all__ = ["kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dysample_sample", "dagem_gate", "bnmix", "dwconv3x3", "pwconv", "pwconv_supported", "triplenorm", "qkv_gate", "smallconv", "smallconv_supported", "KMU_PREC_FP32", "KMU_PREC_BF16"]
 
 
 # ------------------------------------------------------------------------------------------------------ op-level timing
@@ -619,3 +619,51 @@ def qkv_gate(qkv):
     if not qkv.is_cuda:
         raise RuntimeError("km_unet_b200.qkv_gate: CUDA tensors only (no CPU fallback)")
     return _QkvGateFn.apply(qkv)
+
+
+class _SmallConvFn(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, weight, bias):
+        lib = _lib.lib()
+        x = x.contiguous()
+        B, Cin, H, W = x.shape
+        Cout, _, kh, kw = weight.shape
+        desc = ScDesc(B, Cin, Cout, H, W, kh, kw)
+        w = weight.contiguous()
+        b = None if bias is None else bias.contiguous()
+        y = torch.empty(B, Cout, H, W, dtype=torch.float32, device=x.device)
+        check(_call("kmu_smallconv_fwd", (B, Cin, Cout, H, W, kh, kw), lib.kmu_smallconv_fwd, C.byref(desc), ptr(x), ptr(w), ptr(b), ptr(y),
+                    stream_ptr()), "kmu_smallconv_fwd")
+        ctx.save_for_backward(x, w)
+        ctx.desc, ctx.has_bias = desc, bias is not None
+        return y
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        lib = _lib.lib()
+        x, w = ctx.saved_tensors
+        d = ctx.desc
+        dy = dy.to(torch.float32).contiguous()
+        need_x = ctx.needs_input_grad[0]
+        need_w = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
+        dx = torch.empty_like(x) if need_x else None
+        dw = torch.empty_like(w) if need_w else None
+        db = torch.empty(d.Cout, dtype=torch.float32, device=x.device) if (need_w and ctx.has_bias) else None
+        ws = _workspace(lib.kmu_smallconv_bwd_workspace_bytes(C.byref(d)), x.device)
+        check(_call("kmu_smallconv_bwd", (d.B, d.Cin, d.Cout, d.H, d.W, d.kh, d.kw), lib.kmu_smallconv_bwd, C.byref(d), ptr(x), ptr(dy),
+                    ptr(w), ptr(dx), ptr(dw), ptr(db), ws.data_ptr(), ws.numel(), stream_ptr()), "kmu_smallconv_bwd")
+        return dx, dw, db
+
+
+def smallconv_supported(cin, cout, kh, kw):
+    d = ScDesc(1, int(cin), int(cout), 1, 1, int(kh), int(kw))
+    return bool(_lib.lib().kmu_smallconv_supported(C.byref(d)))
+
+
+def smallconv(x, weight, bias=None):
+    """Dense stride-1 'same' convolution with <= 9 taps (1x3, 3x1, 3x3): weight (Cout,Cin,kh,kw), zero padding k//2."""
+    if not x.is_cuda:
+        raise RuntimeError("km_unet_b200.smallconv: CUDA tensors only (no CPU fallback)")
+    return _SmallConvFn.apply(x, weight, bias)

@@ -72,6 +72,11 @@ def _qkv_gate(qkv):
     return torch.sigmoid(q * k) * v
 
 
+def _smallconv(x, weight, bias=None):
+    import torch.nn.functional as F
+    return F.conv2d(x, weight, bias, padding=(weight.shape[2] // 2, weight.shape[3] // 2))
+
+
 def _gate(x, deformed, linears, bns, training, momentum=0.1, eps=1e-5):
     return _dagem.dagem_gate(x, deformed, linears, bns, training)
 
@@ -80,11 +85,11 @@ def _gate(x, deformed, linears, bns, training, momentum=0.1, eps=1e-5):
 def cpu_ops():
     from km_unet_b200 import ops
     saved = {n: getattr(ops, n) for n in ("kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dagem_gate", "bnmix",
-                                          "dwconv3x3", "pwconv", "triplenorm", "qkv_gate")}
+                                          "dwconv3x3", "pwconv", "triplenorm", "qkv_gate", "smallconv")}
     ops.kanconv2d, ops.kanlinear, ops.layernorm1d = _kanconv2d, _kanlinear, _hsmssd.layernorm1d
     ops.hsmssd, ops.dysample, ops.dagem_gate = _hsm, _dys, _gate
     ops.bnmix, ops.dwconv3x3, ops.pwconv = _bnmix, _dwconv3x3, _pwconv
-    ops.triplenorm, ops.qkv_gate = _triplenorm, _qkv_gate
+    ops.triplenorm, ops.qkv_gate, ops.smallconv = _triplenorm, _qkv_gate, _smallconv
     try:
         yield
     finally:

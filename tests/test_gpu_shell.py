@@ -154,3 +154,36 @@ def test_qkv_gate_vs_torch(B, C, H, W):
     assert rel_err(y, want) < TOL
     y.backward(gout.cuda())
     assert rel_err(qc.grad, qd.grad) < TOL
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W,kh,kw,bias", [(2, 16, 16, 32, 32, 3, 1, True), (2, 16, 16, 32, 32, 1, 3, True),
+                                                      (3, 32, 32, 7, 9, 3, 1, False), (2, 64, 32, 16, 16, 3, 3, True),
+                                                      (2, 64, 16, 12, 20, 3, 3, True), (1, 16, 20, 9, 9, 3, 3, True),
+                                                      (32, 16, 16, 128, 128, 1, 3, True), (2, 32, 32, 64, 64, 3, 3, False)])
+def test_smallconv_vs_torch(B, Cin, Cout, H, W, kh, kw, bias):
+    from km_unet_b200 import ops
+    assert ops.smallconv_supported(Cin, Cout, kh, kw)
+    torch.manual_seed(Cin + Cout + kh)
+    x = torch.randn(B, Cin, H, W)
+    w = torch.randn(Cout, Cin, kh, kw) / (Cin * kh * kw) ** 0.5
+    bv = torch.randn(Cout) if bias else None
+    gout = torch.randn(B, Cout, H, W)
+    xd, wd = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    bd = bv.double().requires_grad_(True) if bias else None
+    want = F.conv2d(xd, wd, bd, padding=(kh // 2, kw // 2))
+    want.backward(gout.double())
+    xc, wc = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+    bc = bv.cuda().requires_grad_(True) if bias else None
+    y = ops.smallconv(xc, wc, bc)
+    assert rel_err(y, want) < TOL
+    y.backward(gout.cuda())
+    assert rel_err(xc.grad, xd.grad) < TOL
+    assert rel_err(wc.grad, wd.grad) < TOL
+    if bias:
+        assert rel_err(bc.grad, bd.grad) < TOL
+
+
+def test_smallconv_unsupported_shapes_are_reported():
+    from km_unet_b200 import ops
+    assert not ops.smallconv_supported(5, 16, 3, 3)       # conv_f: 5 input frames
+    assert not ops.smallconv_supported(32, 32, 5, 5)      # more than 9 taps
