@@ -578,13 +578,35 @@ __global__ void __launch_bounds__(256) hsm_proj_dw_bwd_kernel(const float* __res
       wpt_s[nn * C + c] = w;
     }
     for (int i = tid; i < BN * 9; i += 256) wd_s[(i / 9) * 12 + (i % 9)] = wd[(size_t)n0 * 9 + i];
-    // dP tile with halo (zero outside the image)
-    for (int i = tid; i < BN * NHALO; i += 256) {
-      int nn = i / NHALO, pos = i - nn * NHALO;
-      int hy = pos / HW_, hx = pos - hy * HW_;
-      int yy = ty0 + hy - 1, xx = tx0 + hx - 1;
-      dp_s[i] = (yy >= 0 && yy < d.H && xx >= 0 && xx < d.H)
-                    ? __ldg(dP + ((size_t)b * N3 + n0 + nn) * d.L + (size_t)yy * d.H + xx) : 0.f;
+    // dP tile with halo (zero outside the image).  One warp per halo row, lanes along the row: no per-element div/mod, and
+    // the 20 row loads of a warp are issued back to back before any of them is stored.
+    {
+      constexpr int ROWS = BN * HH_ / 8;   // 20 halo rows per warp
+      float v[ROWS];
+      const int xx = tx0 + lane - 1;
+      const bool colok = xx >= 0 && xx < d.H;
+      const float* src0 = dP + ((size_t)b * N3 + n0) * d.L + xx;
+#pragma unroll
+      for (int k = 0; k < ROWS; ++k) {
+        const int row = wid + 8 * k;
+        const int nn = row / HH_, hy = row - nn * HH_;
+        const int yy = ty0 + hy - 1;
+        v[k] = (colok && yy >= 0 && yy < d.H) ? __ldg(src0 + (size_t)nn * d.L + (size_t)yy * d.H) : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < ROWS; ++k) {
+        const int row = wid + 8 * k;
+        const int nn = row / HH_, hy = row - nn * HH_;
+        dp_s[nn * NHALO + hy * HW_ + lane] = v[k];
+      }
+      // the two right-most halo columns (32, 33) of the 160 rows
+      for (int i = tid; i < BN * HH_ * 2; i += 256) {
+        const int row = i >> 1, hx = 32 + (i & 1);
+        const int nn = row / HH_, hy = row - nn * HH_;
+        const int yy = ty0 + hy - 1, x2 = tx0 + hx - 1;
+        dp_s[nn * NHALO + hy * HW_ + hx] = (yy >= 0 && yy < d.H && x2 < d.H)
+                                               ? __ldg(dP + ((size_t)b * N3 + n0 + nn) * d.L + (size_t)yy * d.H + x2) : 0.f;
+      }
     }
     __syncthreads();
     {
