@@ -137,6 +137,9 @@ def op_work(name, key):
     if name.startswith("kmu_smallconv"):
         B, Cin, Cout, H, W, kh, kw = key
         return ("hbm", (4.0 * (Cin + Cout) if name.endswith("fwd") else 4.0 * (2 * Cin + 2 * Cout)) * B * H * W, "byte")
+    if name.startswith("kmu_iwp"):
+        B, C, H, W = key                     # fwd: read x, write x/4; bwd: read x and dout, write dx
+        return ("hbm", (5.0 if name.endswith("fwd") else 9.0) * B * C * H * W, "byte")
     if name.startswith("kmu_triplenorm"):
         B, C, HW = key                       # fwd: x twice (statistics, apply) + y; bwd: x, dy twice + dx
         return ("hbm", (12.0 if name.endswith("fwd") else 20.0) * B * C * HW, "byte")

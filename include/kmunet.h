@@ -438,6 +438,15 @@ int kmu_smallconv_fwd(const kmu_smallconv_desc* d, const float* x, const float* 
 int kmu_smallconv_bwd(const kmu_smallconv_desc* d, const float* x, const float* dy, const float* w, float* dx, float* dw,
                       float* dbias, void* workspace, size_t workspace_bytes, kmu_stream stream);
 
+/* IntelligentWaveletPoolingModule.forward (WPL/iwp.py:116-132, Haar DWT of :9-113): x (B,C,H,W), H and W even ->
+ * out (B,C,H/2,W/2) = fusion_conv([LL ; mean over channels of (LH,HL,HH)]), last high-pass row / column zero (:79-82).
+ * wf = fusion_conv.weight (C, C+1), bias (C).  C in {16,32,64}. */
+size_t kmu_iwp_bwd_workspace_bytes(int32_t B, int32_t C, int32_t H, int32_t W);
+int kmu_iwp_fwd(const float* x, const float* wf, const float* bias, float* out, int32_t B, int32_t C, int32_t H, int32_t W,
+                kmu_stream stream);
+int kmu_iwp_bwd(const float* x, const float* wf, const float* dout, float* dx, float* d_wf, float* d_bias, int32_t B, int32_t C,
+                int32_t H, int32_t W, void* workspace, size_t workspace_bytes, kmu_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

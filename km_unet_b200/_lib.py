@@ -170,6 +170,10 @@ SYMBOLS = {
     "kmu_smallconv_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(ScDesc)]),
     "kmu_smallconv_fwd": (C.c_int, [C.POINTER(ScDesc), _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
     "kmu_smallconv_bwd": (C.c_int, [C.POINTER(ScDesc), _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kmu_iwp_bwd_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "kmu_iwp_fwd": (C.c_int, [_f32p, _f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "kmu_iwp_bwd": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                              C.c_size_t, C.c_void_p]),
     "kmu_dagem_saved_bytes": (C.c_size_t, [C.POINTER(DagemDesc)]),
     "kmu_dagem_fwd_workspace_bytes": (C.c_size_t, [C.POINTER(DagemDesc)]),
     "kmu_dagem_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(DagemDesc)]),

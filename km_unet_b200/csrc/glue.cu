@@ -324,6 +324,163 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const float* __restrict__
   }
 }
 
+// ================================================================================================ wavelet pooling (IWP)
+// WPL/iwp.py:116-132 with the Haar taps of :50-52 and the matrices of :58-103: for every 2x2 block [[a,b],[c,d]]
+//   LL = (a+b+c+d)/2, LH = (a-b+c-d)/2, HL = (a+b-c-d)/2, HH = (a-b-c+d)/2, the LAST high-pass row and column are zero,
+//   the Softmax2d over a one-channel map is identically 1, so out = fusion_conv([LL ; mean_c(LH,HL,HH)]).
+// The reference rebuilds its numpy filter matrices and uploads them on every call (a host sync inside the model) and runs
+// 6 matmuls + cat + conv + softmax + mean; here: one kernel forward, one backward (+ the weight-gradient reduction).
+// thread = output pixel; LL of all C channels in registers; weights [C+1][C] transposed in shared memory.
+template <int C>
+__global__ void __launch_bounds__(128) iwp_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wf,
+                                                      const float* __restrict__ bias, float* __restrict__ out, int B, int H, int W) {
+  __shared__ __align__(16) float w_s[(C + 1) * C];   // w_s[i][o] = wf[o][i]
+  for (int i = threadIdx.x; i < (C + 1) * C; i += 128) {
+    const int ii = i / C, o = i - ii * C;
+    w_s[i] = wf[o * (C + 1) + ii];
+  }
+  __syncthreads();
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long idx = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (idx >= (long long)B * Ho * Wo) return;
+  const int j = (int)(idx % Wo), i = (int)((idx / Wo) % Ho), b = (int)(idx / ((long long)Wo * Ho));
+  const float mlh = j < Wo - 1 ? 1.f : 0.f, mhl = i < Ho - 1 ? 1.f : 0.f, mhh = mlh * mhl;
+  const float* xp = x + ((size_t)b * C * H + 2 * i) * W + 2 * j;
+  float acc[C];
+#pragma unroll
+  for (int o = 0; o < C; ++o) acc[o] = bias[o];
+  float high = 0.f;
+#pragma unroll 4
+  for (int c = 0; c < C; ++c) {
+    const float2 r0 = *reinterpret_cast<const float2*>(xp + (size_t)c * H * W);
+    const float2 r1 = *reinterpret_cast<const float2*>(xp + (size_t)c * H * W + W);
+    const float ll = 0.5f * ((r0.x + r0.y) + (r1.x + r1.y));
+    high += 0.5f * (mlh * ((r0.x - r0.y) + (r1.x - r1.y)) + mhl * ((r0.x + r0.y) - (r1.x + r1.y)) + mhh * ((r0.x - r0.y) - (r1.x - r1.y)));
+    const float4* w4 = reinterpret_cast<const float4*>(w_s + c * C);
+#pragma unroll
+    for (int q = 0; q < C / 4; ++q) {
+      const float4 w = w4[q];
+      acc[4 * q + 0] = fmaf(w.x, ll, acc[4 * q + 0]);
+      acc[4 * q + 1] = fmaf(w.y, ll, acc[4 * q + 1]);
+      acc[4 * q + 2] = fmaf(w.z, ll, acc[4 * q + 2]);
+      acc[4 * q + 3] = fmaf(w.w, ll, acc[4 * q + 3]);
+    }
+  }
+  high *= 1.0f / (3 * C);
+  float* op = out + ((size_t)b * C * Ho + i) * Wo + j;
+#pragma unroll
+  for (int o = 0; o < C; ++o) op[(size_t)o * Ho * Wo] = fmaf(w_s[C * C + o], high, acc[o]);
+}
+
+// backward: dx and per-CTA partials of d wf [C][C+1] | d bias [C].  CTA = 64 output pixels, 128 threads = 64 pixels x 2 halves
+// of the channels for the dx part; the outer products run over the staged tiles.
+template <int C>
+__global__ void __launch_bounds__(128) iwp_bwd_kernel(const float* __restrict__ x, const float* __restrict__ wf,
+                                                      const float* __restrict__ dout, float* __restrict__ dx,
+                                                      float* __restrict__ partial, int B, int H, int W) {
+  constexpr int PADP = 65;
+  extern __shared__ __align__(16) float smem[];
+  float* w_s = smem;                      // [C][C+1] natural
+  float* g_s = w_s + C * (C + 1);         // [C][PADP]      dout tile
+  float* in_s = g_s + C * PADP;           // [C+1][PADP]    LL tile | mean-high
+  float* dav_s = in_s + (C + 1) * PADP;   // [64]           d(mean-high) per pixel
+  const int tid = threadIdx.x, px = tid & 63, half = tid >> 6;
+  for (int i = tid; i < C * (C + 1); i += 128) w_s[i] = wf[i];
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long idx = (long long)blockIdx.x * 64 + px;
+  const bool valid = idx < (long long)B * Ho * Wo;
+  const long long id2 = valid ? idx : 0;
+  const int j = (int)(id2 % Wo), i = (int)((id2 / Wo) % Ho), b = (int)(id2 / ((long long)Wo * Ho));
+  const float mlh = j < Wo - 1 ? 1.f : 0.f, mhl = i < Ho - 1 ? 1.f : 0.f, mhh = mlh * mhl;
+  const float* xp = x + ((size_t)b * C * H + 2 * i) * W + 2 * j;
+  const float* gp = dout + ((size_t)b * C * Ho + i) * Wo + j;
+  // stage dout and LL (this half's channels); the high-pass mean needs all channels: both halves add their part
+  float high = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < C / 2; ++k) {
+    const int c = half * (C / 2) + k;
+    float ll = 0.f, g = 0.f;
+    if (valid) {
+      const float2 r0 = *reinterpret_cast<const float2*>(xp + (size_t)c * H * W);
+      const float2 r1 = *reinterpret_cast<const float2*>(xp + (size_t)c * H * W + W);
+      ll = 0.5f * ((r0.x + r0.y) + (r1.x + r1.y));
+      high += 0.5f * (mlh * ((r0.x - r0.y) + (r1.x - r1.y)) + mhl * ((r0.x + r0.y) - (r1.x + r1.y)) + mhh * ((r0.x - r0.y) - (r1.x - r1.y)));
+      g = __ldg(gp + (size_t)c * Ho * Wo);
+    }
+    g_s[c * PADP + px] = g;
+    in_s[c * PADP + px] = ll;
+  }
+  if (half == 1) dav_s[px] = high;
+  __syncthreads();
+  if (half == 0) in_s[C * PADP + px] = (high + dav_s[px]) * (1.0f / (3 * C));
+  __syncthreads();
+  // d(mean-high) = sum_o wf[o][C] dout[o]
+  if (half == 0) {
+    float dv = 0.f;
+#pragma unroll 8
+    for (int o = 0; o < C; ++o) dv = fmaf(w_s[o * (C + 1) + C], g_s[o * PADP + px], dv);
+    dav_s[px] = dv * (1.0f / (6 * C));
+  }
+  __syncthreads();
+  if (valid) {
+    const float dav = dav_s[px];
+    const float ka = dav * (mlh + mhl + mhh), kb = dav * (-mlh + mhl - mhh), kc = dav * (mlh - mhl - mhh), kd = dav * (-mlh - mhl + mhh);
+    float* dxp = dx + ((size_t)b * C * H + 2 * i) * W + 2 * j;
+#pragma unroll 2
+    for (int k = 0; k < C / 2; ++k) {
+      const int c = half * (C / 2) + k;
+      float dll = 0.f;
+#pragma unroll 8
+      for (int o = 0; o < C; ++o) dll = fmaf(w_s[o * (C + 1) + c], g_s[o * PADP + px], dll);
+      dll *= 0.5f;
+      *reinterpret_cast<float2*>(dxp + (size_t)c * H * W) = make_float2(dll + ka, dll + kb);
+      *reinterpret_cast<float2*>(dxp + (size_t)c * H * W + W) = make_float2(dll + kc, dll + kd);
+    }
+  }
+  // weight-gradient partials
+  float* pb = partial + (size_t)blockIdx.x * (C * (C + 1) + C);
+  for (int e = tid; e < C * (C + 1); e += 128) {
+    const int o = e / (C + 1), ii = e - o * (C + 1);
+    const float* ar = g_s + o * PADP;
+    const float* br = in_s + ii * PADP;
+    float a = 0.f;
+#pragma unroll 8
+    for (int p = 0; p < 64; ++p) a = fmaf(ar[p], br[p], a);
+    pb[e] = a;
+  }
+  for (int o = tid; o < C; o += 128) {
+    float a = 0.f;
+    for (int p = 0; p < 64; ++p) a += g_s[o * PADP + p];
+    pb[C * (C + 1) + o] = a;
+  }
+}
+
+__global__ void __launch_bounds__(256) iwp_wreduce_kernel(const float* __restrict__ partial, int nparts, int n_w, int n_b,
+                                                          float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float red[8][33];
+  const int o = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 32 + o;
+  float s = 0.f;
+  if (idx < n_w + n_b)
+    for (int k = sl; k < nparts; k += 8) s += partial[(size_t)k * (n_w + n_b) + idx];
+  red[sl][o] = s;
+  __syncthreads();
+  if (sl == 0 && idx < n_w + n_b) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += red[q][o];
+    if (idx < n_w) dw[idx] = t;
+    else db[idx - n_w] = t;
+  }
+}
+
+static int iwp_check(int B, int C, int H, int W, const char* who) {
+  KMU_REQUIRE(B > 0 && H > 0 && W > 0, KMU_ERR_BAD_ARG, "%s: non-positive shape", who);
+  KMU_REQUIRE(C == 16 || C == 32 || C == 64, KMU_ERR_UNSUPPORTED, "%s: C=%d not in {16,32,64}", who, C);
+  KMU_REQUIRE((H & 1) == 0 && (W & 1) == 0, KMU_ERR_UNSUPPORTED, "%s: %dx%d map (even sizes only)", who, H, W);
+  return KMU_OK;
+}
+
 static int tn_check(const kmu_triplenorm_desc* d, const char* who) {
   KMU_REQUIRE(d != nullptr, KMU_ERR_BAD_ARG, "%s: null descriptor", who);
   KMU_REQUIRE(d->B > 0 && d->C > 0 && d->HW > 0, KMU_ERR_BAD_ARG, "%s: non-positive shape", who);
@@ -392,6 +549,53 @@ int kmu_triplenorm_bwd(const kmu_triplenorm_bwd_args* a, kmu_stream stream) {
 #undef KMU_TN_BWD
   tn_param_reduce_kernel<<<cdiv(3 * C, 256), 256, 0, st>>>(part2, B * TN_SPLIT, C, a->d_gh, a->d_bh, a->d_gw, a->d_bw, a->d_gc, a->d_bc);
   KMU_LAUNCH_CHECK("tn_param_reduce");
+  return KMU_OK;
+}
+
+size_t kmu_iwp_bwd_workspace_bytes(int32_t B, int32_t C, int32_t H, int32_t W) {
+  if (iwp_check(B, C, H, W, "iwp_bwd_workspace_bytes") != KMU_OK) return 0;
+  const long long npix = (long long)B * (H / 2) * (W / 2);
+  return align_up((size_t)cdiv(npix, 64) * ((size_t)C * (C + 1) + C) * 4, 256);
+}
+
+int kmu_iwp_fwd(const float* x, const float* wf, const float* bias, float* out, int32_t B, int32_t C, int32_t H, int32_t W,
+                kmu_stream stream) {
+  int rc = iwp_check(B, C, H, W, "iwp_fwd");
+  if (rc != KMU_OK) return rc;
+  KMU_REQUIRE(x && wf && bias && out, KMU_ERR_BAD_ARG, "iwp_fwd: null tensor");
+  const long long npix = (long long)B * (H / 2) * (W / 2);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C == 16) iwp_fwd_kernel<16><<<cdiv(npix, 128), 128, 0, st>>>(x, wf, bias, out, B, H, W);
+  else if (C == 32) iwp_fwd_kernel<32><<<cdiv(npix, 128), 128, 0, st>>>(x, wf, bias, out, B, H, W);
+  else iwp_fwd_kernel<64><<<cdiv(npix, 128), 128, 0, st>>>(x, wf, bias, out, B, H, W);
+  KMU_LAUNCH_CHECK("iwp_fwd");
+  return KMU_OK;
+}
+
+int kmu_iwp_bwd(const float* x, const float* wf, const float* dout, float* dx, float* d_wf, float* d_bias, int32_t B, int32_t C,
+                int32_t H, int32_t W, void* workspace, size_t workspace_bytes, kmu_stream stream) {
+  int rc = iwp_check(B, C, H, W, "iwp_bwd");
+  if (rc != KMU_OK) return rc;
+  KMU_REQUIRE(x && wf && dout && dx && d_wf && d_bias, KMU_ERR_BAD_ARG, "iwp_bwd: null tensor");
+  KMU_REQUIRE(workspace && workspace_bytes >= kmu_iwp_bwd_workspace_bytes(B, C, H, W), KMU_ERR_WORKSPACE, "iwp_bwd: workspace too small");
+  const long long npix = (long long)B * (H / 2) * (W / 2);
+  const int nblk = cdiv(npix, 64);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* partial = (float*)workspace;
+#define KMU_IWP_BWD(CC)                                                                                          \
+  do {                                                                                                           \
+    size_t smem = ((size_t)CC * (CC + 1) + (size_t)CC * 65 + (size_t)(CC + 1) * 65 + 64) * 4;                    \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(iwp_bwd_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    iwp_bwd_kernel<CC><<<nblk, 128, smem, st>>>(x, wf, dout, dx, partial, B, H, W);                              \
+  } while (0)
+  if (C == 16) KMU_IWP_BWD(16);
+  else if (C == 32) KMU_IWP_BWD(32);
+  else KMU_IWP_BWD(64);
+#undef KMU_IWP_BWD
+  KMU_LAUNCH_CHECK("iwp_bwd");
+  const int n_w = C * (C + 1), n_b = C;
+  iwp_wreduce_kernel<<<cdiv(n_w + n_b, 32), 256, 0, st>>>(partial, nblk, n_w, n_b, d_wf, d_bias);
+  KMU_LAUNCH_CHECK("iwp_wreduce");
   return KMU_OK;
 }
 

@@ -203,18 +203,26 @@ class IntelligentWaveletPoolingModule(nn.Module):
         B, C, H, W = x.shape
         if H != W or H % 2:
             raise RuntimeError("IntelligentWaveletPoolingModule: square, even-sized maps only (as in KM-UNet)")
-        a, b = x[:, :, 0::2, 0::2], x[:, :, 0::2, 1::2]
-        c, d = x[:, :, 1::2, 0::2], x[:, :, 1::2, 1::2]
-        ll = (a + b + c + d) * 0.5
-        lh = (a - b + c - d) * 0.5
-        hl = (a + b - c - d) * 0.5
-        hh = (a - b - c + d) * 0.5
-        row = torch.ones(H // 2, 1, device=x.device, dtype=x.dtype)
-        row[-1] = 0
-        col = torch.ones(1, W // 2, device=x.device, dtype=x.dtype)
-        col[:, -1] = 0
-        high = (lh * col + hl * row + hh * (row * col)).sum(dim=1, keepdim=True) / (3 * C)
-        return conv1x1(torch.cat([ll, high], dim=1), self.fusion_conv.weight, self.fusion_conv.bias)
+        if ops.iwp_supported(C, H, W):
+            return ops.iwp(x, self.fusion_conv.weight, self.fusion_conv.bias)
+        return conv1x1(torch.cat(haar_pool(x), dim=1), self.fusion_conv.weight, self.fusion_conv.bias)
+
+
+def haar_pool(x):
+    """(LL, mean over channels of the three high-pass bands) of WPL/iwp.py in strided-slice form."""
+    B, C, H, W = x.shape
+    a, b = x[:, :, 0::2, 0::2], x[:, :, 0::2, 1::2]
+    c, d = x[:, :, 1::2, 0::2], x[:, :, 1::2, 1::2]
+    ll = (a + b + c + d) * 0.5
+    lh = (a - b + c - d) * 0.5
+    hl = (a + b - c - d) * 0.5
+    hh = (a - b - c + d) * 0.5
+    row = torch.ones(H // 2, 1, device=x.device, dtype=x.dtype)
+    row[-1] = 0
+    col = torch.ones(1, W // 2, device=x.device, dtype=x.dtype)
+    col[:, -1] = 0
+    high = (lh * col + hl * row + hh * (row * col)).sum(dim=1, keepdim=True) / (3 * C)
+    return ll, high
 
 
 class KM_UNetV3(nn.Module):

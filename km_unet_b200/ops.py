@@ -12,7 +12,7 @@ from . import _lib
 from ._lib import (ScDesc, TnBwdArgs, TnDesc, TnFwdArgs, PwDesc, BnMixBwdArgs, BnMixDesc, BnMixFwdArgs, DwDesc, DagemBn, DagemBwdArgs, DagemDesc, DagemFwdArgs, DysBwdArgs, DysDesc, DysFwdArgs, HsmBwdArgs, HsmDesc, HsmFwdArgs, KanBwdArgs, KanDesc, KanFwdArgs,
                    KMU_PREC_BF16, KMU_PREC_FP32, check, ptr, stream_ptr)
 
-__all__ = ["kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dysample_sample", "dagem_gate", "bnmix", "dwconv3x3", "pwconv", "pwconv_supported", "triplenorm", "qkv_gate", "smallconv", "smallconv_supported", "KMU_PREC_FP32", "KMU_PREC_BF16"]
+__all__ = ["kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dysample_sample", "dagem_gate", "bnmix", "dwconv3x3", "pwconv", "pwconv_supported", "triplenorm", "qkv_gate", "smallconv", "smallconv_supported", "iwp", "iwp_supported", "KMU_PREC_FP32", "KMU_PREC_BF16"]
 
 
 # ------------------------------------------------------------------------------------------------------ op-level timing
@@ -667,3 +667,45 @@ def smallconv(x, weight, bias=None):
     if not x.is_cuda:
         raise RuntimeError("km_unet_b200.smallconv: CUDA tensors only (no CPU fallback)")
     return _SmallConvFn.apply(x, weight, bias)
+
+
+class _IwpFn(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, weight, bias):
+        lib = _lib.lib()
+        x = x.contiguous()
+        B, Cc, H, W = x.shape
+        w = weight.reshape(Cc, Cc + 1).contiguous()
+        b = bias.contiguous()
+        out = torch.empty(B, Cc, H // 2, W // 2, dtype=torch.float32, device=x.device)
+        check(_call("kmu_iwp_fwd", (B, Cc, H, W), lib.kmu_iwp_fwd, ptr(x), ptr(w), ptr(b), ptr(out), B, Cc, H, W, stream_ptr()), "kmu_iwp_fwd")
+        ctx.save_for_backward(x, w)
+        ctx.wshape = weight.shape
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dout):
+        lib = _lib.lib()
+        x, w = ctx.saved_tensors
+        B, Cc, H, W = x.shape
+        dout = dout.to(torch.float32).contiguous()
+        dx = torch.empty_like(x)
+        dw = torch.empty_like(w)
+        db = torch.empty(Cc, dtype=torch.float32, device=x.device)
+        ws = _workspace(lib.kmu_iwp_bwd_workspace_bytes(B, Cc, H, W), x.device)
+        check(_call("kmu_iwp_bwd", (B, Cc, H, W), lib.kmu_iwp_bwd, ptr(x), ptr(w), ptr(dout), ptr(dx), ptr(dw), ptr(db), B, Cc, H, W,
+                    ws.data_ptr(), ws.numel(), stream_ptr()), "kmu_iwp_bwd")
+        return dx, dw.reshape(ctx.wshape), db
+
+
+def iwp_supported(channels, H, W):
+    return channels in (16, 32, 64) and H % 2 == 0 and W % 2 == 0
+
+
+def iwp(x, fusion_weight, fusion_bias):
+    """IntelligentWaveletPoolingModule.forward (WPL/iwp.py:116-132): Haar 2x2 analysis + 1x1 fusion, (B,C,H,W) -> (B,C,H/2,W/2)."""
+    if not x.is_cuda:
+        raise RuntimeError("km_unet_b200.iwp: CUDA tensors only (no CPU fallback)")
+    return _IwpFn.apply(x, fusion_weight, fusion_bias)

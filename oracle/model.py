@@ -77,6 +77,29 @@ def _smallconv(x, weight, bias=None):
     return F.conv2d(x, weight, bias, padding=(weight.shape[2] // 2, weight.shape[3] // 2))
 
 
+def _iwp(x, fusion_weight, fusion_bias):
+    """WPL/iwp.py:58-132 with its banded Haar matrices written out (last high-pass row / column zero)."""
+    import torch
+    import torch.nn.functional as F
+    B, C, H, W = x.shape
+    s = 2 ** -0.5
+
+    def mats(n):
+        lo = torch.zeros(n // 2, n, dtype=x.dtype)
+        hi = torch.zeros(n // 2, n, dtype=x.dtype)
+        for i in range(n // 2):
+            lo[i, 2 * i], lo[i, 2 * i + 1] = s, s
+            if i < n // 2 - 1:
+                hi[i, 2 * i], hi[i, 2 * i + 1] = s, -s
+        return lo, hi
+    lo_h, hi_h = mats(H)
+    lo_w, hi_w = mats(W)
+    L, Hh = lo_h @ x, hi_h @ x
+    LL, LH, HL, HH = L @ lo_w.t(), L @ hi_w.t(), Hh @ lo_w.t(), Hh @ hi_w.t()
+    high = torch.cat([LH, HL, HH], dim=1).mean(dim=1, keepdim=True)
+    return F.conv2d(torch.cat([LL, high], dim=1), fusion_weight.reshape(C, C + 1, 1, 1), fusion_bias)
+
+
 def _gate(x, deformed, linears, bns, training, momentum=0.1, eps=1e-5):
     return _dagem.dagem_gate(x, deformed, linears, bns, training)
 
@@ -85,11 +108,11 @@ def _gate(x, deformed, linears, bns, training, momentum=0.1, eps=1e-5):
 def cpu_ops():
     from km_unet_b200 import ops
     saved = {n: getattr(ops, n) for n in ("kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dagem_gate", "bnmix",
-                                          "dwconv3x3", "pwconv", "triplenorm", "qkv_gate", "smallconv")}
+                                          "dwconv3x3", "pwconv", "triplenorm", "qkv_gate", "smallconv", "iwp")}
     ops.kanconv2d, ops.kanlinear, ops.layernorm1d = _kanconv2d, _kanlinear, _hsmssd.layernorm1d
     ops.hsmssd, ops.dysample, ops.dagem_gate = _hsm, _dys, _gate
     ops.bnmix, ops.dwconv3x3, ops.pwconv = _bnmix, _dwconv3x3, _pwconv
-    ops.triplenorm, ops.qkv_gate, ops.smallconv = _triplenorm, _qkv_gate, _smallconv
+    ops.triplenorm, ops.qkv_gate, ops.smallconv, ops.iwp = _triplenorm, _qkv_gate, _smallconv, _iwp
     try:
         yield
     finally:

@@ -187,3 +187,25 @@ def test_smallconv_unsupported_shapes_are_reported():
     from km_unet_b200 import ops
     assert not ops.smallconv_supported(5, 16, 3, 3)       # conv_f: 5 input frames
     assert not ops.smallconv_supported(32, 32, 5, 5)      # more than 9 taps
+
+
+@pytest.mark.parametrize("B,C,S", [(2, 16, 32), (3, 32, 12), (2, 64, 8), (4, 16, 128), (1, 16, 2)])
+def test_iwp_vs_matrix_form(B, C, S):
+    """Against the banded-matrix definition of WPL/iwp.py:58-132 (oracle.model._iwp, fp64 autograd)."""
+    from km_unet_b200 import ops
+    from oracle.model import _iwp
+    torch.manual_seed(C + S)
+    x = torch.randn(B, C, S, S)
+    w = torch.randn(C, C + 1, 1, 1) / C ** 0.5
+    bv = torch.randn(C) * 0.3
+    gout = torch.randn(B, C, S // 2, S // 2)
+    xd, wd, bd = x.double().requires_grad_(True), w.double().requires_grad_(True), bv.double().requires_grad_(True)
+    want = _iwp(xd, wd, bd)
+    want.backward(gout.double())
+    xc, wc, bc = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True), bv.cuda().requires_grad_(True)
+    y = ops.iwp(xc, wc, bc)
+    assert rel_err(y, want) < TOL
+    y.backward(gout.cuda())
+    assert rel_err(xc.grad, xd.grad) < TOL
+    assert rel_err(wc.grad, wd.grad) < TOL
+    assert rel_err(bc.grad, bd.grad) < TOL
