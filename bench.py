@@ -395,6 +395,7 @@ def run_model(h, args):
     from km_unet_b200.ddp import BucketedGradAllReduce, broadcast_parameters
     from km_unet_b200.loss import HybridLoss
     K.config.kan_precision = args.precision
+    K.config.hsm_precision = args.precision               # HSM-SSD BCdt projection on tcgen05 as well
     _lib.lib()                                            # fail loudly if the extension is missing
     metric, desc, variant, classes, fin, size, default_b, train = WORKLOADS[args.workload]
     B = args.batch or default_b
@@ -540,7 +541,8 @@ def run_model(h, args):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * world, "frames": f"{fin}->{classes}",
-                       "size": size, "precision": f"KANConv2d {args.precision} (tcgen05) / everything else fp32",
+                       "size": size, "precision": (f"KANConv2d and the HSM-SSD forward projection {args.precision} (tcgen05), everything else fp32"
+                                     if args.precision == "bf16" else "fp32 everywhere"),
                        "parallelism": f"dp{world}", "cuda_graph": bool(graphed is not None), "optimizer": "AdamW(lr 1e-3, wd 0.05, fused)" if train else None,
                        "l2": "activations per step (hundreds of %.0f MB tensors) exceed the 126 MB L2" % (B * 16 * size * size * 4 / 1e6),
                        "grad_allreduce": (f"bucketed NCCL, {nlive * 4 / 1e6:.1f} MB" if world > 1 else "none (1 GPU)")},

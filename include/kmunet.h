@@ -115,6 +115,9 @@ void kmu_debug_flags(int flags);
 typedef struct {
   int32_t B, C, L, H; /* L == H*H */
   int32_t N;          /* state_dim (64 in KM-UNet) */
+  int32_t precision;  /* kmu_precision of the BCdt projection + depthwise conv in the FORWARD call: KMU_PREC_BF16 runs them as
+                         one dense 3x3 convolution on tcgen05 (bf16 operands, fp32 TMEM accumulation, 2e-2 gate); everything
+                         else, and the whole backward call, is fp32 either way */
 } kmu_hsmssd_desc;
 
 typedef struct {

@@ -35,7 +35,7 @@ class KanBwdArgs(C.Structure):
 
 
 class HsmDesc(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("B", "C", "L", "H", "N")]
+    _fields_ = [(n, C.c_int32) for n in ("B", "C", "L", "H", "N", "precision")]
 
 
 class HsmFwdArgs(C.Structure):

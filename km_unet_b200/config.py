@@ -4,6 +4,8 @@ import os
 # "fp32": CUDA-core fp32 kernels (1e-4 parity gate).  "bf16": tcgen05 tensor-core kernels where the shape allows
 # (2e-2 parity gate), fp32 family otherwise.  Both run on the GPU; there is no CPU path.
 kan_precision = os.environ.get("KMU_KAN_PRECISION", "fp32")
+# same switch for the HSM-SSD projection (BCdt_proj + depthwise 3x3 of the forward as one tcgen05 convolution)
+hsm_precision = os.environ.get("KMU_HSM_PRECISION", "fp32")
 
 
 def precision_code(name=None):

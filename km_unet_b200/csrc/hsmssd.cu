@@ -22,6 +22,11 @@
 namespace kmu {
 namespace hsm {
 
+namespace tc {  // hsm_tc.cu: tcgen05 path of the projection
+size_t pack_bytes(int C);
+int project(const float* x, const float* wp, const float* wd, float* P, int B, int C, int H, void* workspace, cudaStream_t st);
+}  // namespace tc
+
 constexpr int N = 64;         // states
 constexpr int N3 = 192;       // projected channels
 constexpr int TH = 8, TW = 32, HW_ = TW + 2, HH_ = TH + 2, NHALO = HW_ * HH_;  // spatial tile + 1-pixel halo (340)
@@ -851,10 +856,11 @@ static int check(const kmu_hsmssd_desc* d, const char* who) {
   return KMU_OK;
 }
 
-struct FwdWs { size_t part_m, part_s, part_hs, total; };
+struct FwdWs { size_t part_m, part_s, part_hs, wpack, total; };
 static FwdWs fwd_ws(const Dims& d) {
   FwdWs w;
   size_t o = 0;
+  w.wpack = o; o += tc::pack_bytes(d.C);
   w.part_m = o; o += align_up((size_t)d.B * d.T * 64 * 4, 256);
   w.part_s = o; o += align_up((size_t)d.B * d.T * 64 * 4, 256);
   w.part_hs = o; o += align_up((size_t)d.B * d.T * d.C * 64 * 4, 256);
@@ -912,6 +918,10 @@ int kmu_hsmssd_fwd(const kmu_hsmssd_fwd_args* a, kmu_stream stream) {
   float* part_m = (float*)(ws + w.part_m);
   float* part_s = (float*)(ws + w.part_s);
   float* part_hs = (float*)(ws + w.part_hs);
+  if (a->d.precision == KMU_PREC_BF16) {
+    int rc = tc::project(a->x, a->w_bcdt, a->w_dw, a->P, d.B, d.C, d.H, ws + w.wpack, st);
+    if (rc != KMU_OK) return rc;
+  } else
   {
     size_t smem = ((size_t)d.C * HPN + (size_t)PCH * HPN + (size_t)d.C * PCH + PCH * 12) * 4;
     dim3 grid(d.tiles_x * d.tiles_y, d.B);

@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) kan_fwd_tc_kernel(const float*
       const int blocks = d.Cin / 16;
       for (int tile = blockIdx.x; tile < d.num_tiles; tile += gridDim.x, ++tcount) {
         const uint32_t buf = tcount & 1u;
-        mbar_wait(smem_u32(&acc_empty[buf]), ((tcount >> 1) & 1u) ^ 1u);
+        mbar_wait_hot(smem_u32(&acc_empty[buf]), ((tcount >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * 256u;
         for (int cb = 0; cb < blocks; ++cb, ++bc) {
@@ -215,13 +215,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) kan_fwd_tc_kernel(const float*
             const uint32_t sb = bc & 1u;
             if (j < 8) {
               r = it % R;
-              mbar_wait(smem_u32(&phi_full[r]), (it / R) & 1u);
+              mbar_wait_hot(smem_u32(&phi_full[r]), (it / R) & 1u);
               a0 = smem_u32(phi_base + (size_t)r * SLOT);
             } else {
-              mbar_wait(smem_u32(&silu_full[sb]), (bc >> 1) & 1u);
+              mbar_wait_hot(smem_u32(&silu_full[sb]), (bc >> 1) & 1u);
               a0 = smem_u32(silu_base + (size_t)sb * SLOT);
             }
-            mbar_wait(smem_u32(&w_full[ws]), (wit / W_STAGES) & 1u);
+            mbar_wait_hot(smem_u32(&w_full[ws]), (wit / W_STAGES) & 1u);
             tc_fence_after();
             const uint32_t b0 = smem_u32(w_base + (size_t)ws * WSTAGE);
 #pragma unroll

@@ -220,13 +220,13 @@ __global__ void __launch_bounds__(DX_THREADS, 1) kan_bwd_dx_tc_kernel(const floa
 #pragma unroll 1
         for (int t = 0; t < 9; ++t) bulk_g2s(smem_u32(w_base + (size_t)t * KS * WBLK), src + (size_t)t * KS * WBLK, KS * WBLK, bar);
       }
-      mbar_wait(smem_u32(w_full), 0);
+      mbar_wait_hot(smem_u32(w_full), 0);
       uint32_t it = 0;
       const uint32_t w0 = smem_u32(w_base);
       for (int tile = first; tile < d.num_tiles; tile += step, ++it) {
         const uint32_t s = it & 1u, ph = (it >> 1) & 1u;
-        mbar_wait(smem_u32(&acc_empty[s]), ph ^ 1u);
-        mbar_wait(smem_u32(&dy_full[s]), ph);
+        mbar_wait_hot(smem_u32(&acc_empty[s]), ph ^ 1u);
+        mbar_wait_hot(smem_u32(&dy_full[s]), ph);
         tc_fence_after();
         const uint32_t a0 = smem_u32(dy_base + (size_t)s * DYSTAGE);
         const uint32_t d_tmem = tmem_base + s * 256u;
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) kan_bwd_dw_tc_kernel(const floa
       uint32_t it = 0;
       for (int tile = split; tile < d.num_tiles; tile += step, ++it) {
         const int st = it % DW_STAGES;
-        mbar_wait(smem_u32(&full[st]), (it / DW_STAGES) & 1u);
+        mbar_wait_hot(smem_u32(&full[st]), (it / DW_STAGES) & 1u);
         tc_fence_after();
         const uint32_t phi0 = smem_u32(smem + (size_t)st * C::STAGE);
         const uint32_t dy0 = phi0 + C::PHI_STAGE;

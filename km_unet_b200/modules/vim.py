@@ -172,8 +172,9 @@ class HSMSSD(nn.Module):
         self.D._no_weight_decay = True
 
     def forward(self, x):
+        from .. import config
         return ops.hsmssd(x, self.BCdt_proj.conv.weight, self.dw.conv.weight, self.hz_proj.conv.weight,
-                          self.out_proj.conv.weight, self.A, self.D, self.state_dim)
+                          self.out_proj.conv.weight, self.A, self.D, self.state_dim, config.precision_code(config.hsm_precision))
 
 
 class EfficientViMBlock(nn.Module):

@@ -182,13 +182,13 @@ def layernorm1d(x, weight, bias, eps=1e-5):
 class _HsmssdFn(torch.autograd.Function):
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, x, w_bcdt, w_dw, w_hz, w_out, A, D, state_dim):
+    def forward(ctx, x, w_bcdt, w_dw, w_hz, w_out, A, D, state_dim, precision):
         lib = _lib.lib()
         x = x.contiguous()
         B, Cc, L = x.shape
         H = int(round(L ** 0.5))
         N = int(state_dim)
-        desc = HsmDesc(B, Cc, L, H, N)
+        desc = HsmDesc(B, Cc, L, H, N, int(precision))
         nbytes = lib.kmu_hsmssd_fwd_workspace_bytes(C.byref(desc))
         if nbytes == 0:
             raise RuntimeError("hsmssd: " + _lib.last_error())
@@ -229,14 +229,15 @@ class _HsmssdFn(torch.autograd.Function):
                           ptr(dD), ws.data_ptr(), ws.numel())
         check(_call("kmu_hsmssd_bwd", (desc.B, desc.C, desc.L), lib.kmu_hsmssd_bwd, C.byref(args), stream_ptr()), "kmu_hsmssd_bwd")
         s = ctx.shapes
-        return dx, dwp.reshape(s[0]), dwd.reshape(s[1]), dwhz.reshape(s[2]), dwo.reshape(s[3]), dA, dD, None
+        return dx, dwp.reshape(s[0]), dwd.reshape(s[1]), dwhz.reshape(s[2]), dwo.reshape(s[3]), dA, dD, None, None
 
 
-def hsmssd(x, w_bcdt, w_dw, w_hz, w_out, A, D, state_dim=64):
-    """HSMSSD.forward (vim_block_init/efficient_vim_init.py:33-61): x (B,C,L) -> (y (B,C,H,H), h (B,C,N))."""
+def hsmssd(x, w_bcdt, w_dw, w_hz, w_out, A, D, state_dim=64, precision=KMU_PREC_FP32):
+    """HSMSSD.forward (vim_block_init/efficient_vim_init.py:33-61): x (B,C,L) -> (y (B,C,H,H), h (B,C,N)).
+    precision=KMU_PREC_BF16 runs the BCdt projection + depthwise conv of the forward as one tcgen05 convolution."""
     if not x.is_cuda:
         raise RuntimeError("km_unet_b200.hsmssd: CUDA tensors only (no CPU fallback)")
-    return _HsmssdFn.apply(x, w_bcdt, w_dw, w_hz, w_out, A, D, state_dim)
+    return _HsmssdFn.apply(x, w_bcdt, w_dw, w_hz, w_out, A, D, state_dim, precision)
 
 
 # ------------------------------------------------------------------------------------------------------ DySample

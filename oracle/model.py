@@ -23,7 +23,7 @@ def _kanlinear(x, base_weight, spline_weight, spline_scaler, grid, grid_size=5, 
     return _kan.kan_linear(x, base_weight, spline_weight, spline_scaler, grid, spline_order)
 
 
-def _hsm(x, w_bcdt, w_dw, w_hz, w_out, A, D, state_dim=64):
+def _hsm(x, w_bcdt, w_dw, w_hz, w_out, A, D, state_dim=64, precision=0):
     y, h = _hsmssd.hsmssd(x, w_bcdt, w_dw, w_hz, w_out, A, D, state_dim)
     B, C, L = x.shape
     H = int(round(L ** 0.5))

@@ -134,3 +134,34 @@ def test_softmax_over_L_sums_to_one_full_size():
         m.dw.conv.weight[64:128].mul_(3.0)
     y2, _ = m(x)
     assert rel_err(y2, 3 * y1) < 1e-5
+
+
+@pytest.mark.parametrize("B,C,H", [(2, 16, 40), (1, 32, 33), (2, 64, 32), (2, 16, 128)])
+def test_hsmssd_tcgen05_projection_within_2e2(B, C, H):
+    """KMU_PREC_BF16: the BCdt projection + depthwise conv of the forward as one tcgen05 3x3 convolution (bf16 operands, fp32
+    accumulation).  Tolerance = the 2e-2 gate north_star states for bf16 tensor-core math; ragged tile edges included."""
+    import km_unet_b200 as K
+    from km_unet_b200 import HSMSSD
+    from oracle import hsmssd as O
+    torch.manual_seed(C + H)
+    m = HSMSSD(d_model=C)
+    sd = m.state_dict()
+    x = torch.randn(B, C, H * H)
+    xd = x.double().requires_grad_(True)
+    W = [sd[k].double().requires_grad_(True) for k in ("BCdt_proj.conv.weight", "dw.conv.weight", "hz_proj.conv.weight",
+                                                        "out_proj.conv.weight")]
+    want, _ = O.hsmssd(xd, W[0], W[1], W[2], W[3], sd["A"].double(), sd["D"].double())
+    gout = torch.randn(want.shape)
+    want.backward(gout.double())
+    m = m.cuda()
+    xc = x.cuda().requires_grad_(True)
+    old = K.config.hsm_precision
+    K.config.hsm_precision = "bf16"
+    try:
+        y, _ = m(xc)
+        y.backward(gout.cuda().reshape(y.shape))
+    finally:
+        K.config.hsm_precision = old
+    assert rel_err(y.reshape(want.shape), want) < 2e-2
+    assert rel_err(xc.grad, xd.grad) < 2e-2
+    assert rel_err(m.BCdt_proj.conv.weight.grad, W[0].grad) < 2e-2

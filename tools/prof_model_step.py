@@ -11,6 +11,7 @@ from km_unet_b200.loss import HybridLoss
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 K.config.kan_precision = "bf16"
+K.config.hsm_precision = "bf16"
 torch.manual_seed(1234)
 m = K.KM_UNetV3_SH(num_classes=20).cuda().train()
 crit = HybridLoss()
