@@ -396,6 +396,8 @@ def run_model(h, args):
     from km_unet_b200.loss import HybridLoss
     K.config.kan_precision = args.precision
     K.config.hsm_precision = args.precision               # HSM-SSD BCdt projection on tcgen05 as well
+    # the pointwise convolutions stay on their fp32 streaming kernels: their tcgen05 path (config.conv_precision = "bf16",
+    # pwconv_tc.cu) is parity-green but not faster yet (one 128-pixel tile per CTA; per-CTA set-up dominates)
     _lib.lib()                                            # fail loudly if the extension is missing
     metric, desc, variant, classes, fin, size, default_b, train = WORKLOADS[args.workload]
     B = args.batch or default_b

@@ -450,6 +450,17 @@ int kmu_iwp_fwd(const float* x, const float* wf, const float* bias, float* out, 
 int kmu_iwp_bwd(const float* x, const float* wf, const float* dout, float* dx, float* d_wf, float* d_bias, int32_t B, int32_t C,
                 int32_t H, int32_t W, void* workspace, size_t workspace_bytes, kmu_stream stream);
 
+/* tcgen05 path of the same pointwise convolution (bf16 operands, fp32 TMEM accumulation, 2e-2 gate): Cin, Cout multiples of
+ * 16 in [16,256]; the weight-gradient GEMM additionally needs Cin <= 240 (kmu_pwconv_tc_wgrad_supported) -- callers route the
+ * remaining pairs' weight gradient through kmu_pwconv_bwd.  One workspace size serves forward and backward. */
+int kmu_pwconv_tc_supported(const kmu_pwconv_desc* d);
+int kmu_pwconv_tc_wgrad_supported(const kmu_pwconv_desc* d);
+size_t kmu_pwconv_tc_workspace_bytes(const kmu_pwconv_desc* d);
+int kmu_pwconv_tc_fwd(const kmu_pwconv_desc* d, const float* x, const float* w, const float* bias, float* y, void* workspace,
+                      size_t workspace_bytes, kmu_stream stream);
+int kmu_pwconv_tc_bwd(const kmu_pwconv_desc* d, const float* x, const float* dy, const float* w, float* dx, float* dw, float* dbias,
+                      void* workspace, size_t workspace_bytes, kmu_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -174,6 +174,11 @@ SYMBOLS = {
     "kmu_iwp_fwd": (C.c_int, [_f32p, _f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "kmu_iwp_bwd": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                               C.c_size_t, C.c_void_p]),
+    "kmu_pwconv_tc_supported": (C.c_int, [C.POINTER(PwDesc)]),
+    "kmu_pwconv_tc_wgrad_supported": (C.c_int, [C.POINTER(PwDesc)]),
+    "kmu_pwconv_tc_workspace_bytes": (C.c_size_t, [C.POINTER(PwDesc)]),
+    "kmu_pwconv_tc_fwd": (C.c_int, [C.POINTER(PwDesc), _f32p, _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kmu_pwconv_tc_bwd": (C.c_int, [C.POINTER(PwDesc), _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kmu_dagem_saved_bytes": (C.c_size_t, [C.POINTER(DagemDesc)]),
     "kmu_dagem_fwd_workspace_bytes": (C.c_size_t, [C.POINTER(DagemDesc)]),
     "kmu_dagem_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(DagemDesc)]),

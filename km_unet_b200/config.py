@@ -6,6 +6,8 @@ import os
 kan_precision = os.environ.get("KMU_KAN_PRECISION", "fp32")
 # same switch for the HSM-SSD projection (BCdt_proj + depthwise 3x3 of the forward as one tcgen05 convolution)
 hsm_precision = os.environ.get("KMU_HSM_PRECISION", "fp32")
+# same switch for the pointwise (1x1) convolutions of the callers / EfficientViMBlock FFN
+conv_precision = os.environ.get("KMU_CONV_PRECISION", "fp32")
 
 
 def precision_code(name=None):

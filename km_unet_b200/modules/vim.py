@@ -73,7 +73,8 @@ def conv1x1(x, weight, bias=None):
     """Pointwise convolution on NCHW through the streaming CUDA kernel (cuDNN's implicit-GEMM path transposes to NHWC and
     back around every such call); channel pairs its weight-gradient kernel does not cover stay a library conv2d."""
     if ops.pwconv_supported(weight.shape[1], weight.shape[0]):
-        return ops.pwconv(x, weight, bias)
+        from .. import config
+        return ops.pwconv(x, weight, bias, config.precision_code(config.conv_precision))
     return torch.nn.functional.conv2d(x, weight.reshape(weight.shape[0], weight.shape[1], 1, 1), bias)
 
 

@@ -489,7 +489,7 @@ def dwconv3x3(x, weight, bias=None):
 class _PwConvFn(torch.autograd.Function):
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, precision):
         lib = _lib.lib()
         x = x.contiguous()
         B, Cin = x.shape[0], x.shape[1]
@@ -499,10 +499,16 @@ class _PwConvFn(torch.autograd.Function):
         w = weight.reshape(Cout, Cin).contiguous()
         b = None if bias is None else bias.contiguous()
         y = torch.empty((B, Cout) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
-        check(_call("kmu_pwconv_fwd", (B, Cin, Cout, HW), lib.kmu_pwconv_fwd, C.byref(desc), ptr(x), ptr(w), ptr(b), ptr(y), stream_ptr()),
-              "kmu_pwconv_fwd")
+        tc = precision == KMU_PREC_BF16 and bool(lib.kmu_pwconv_tc_supported(C.byref(desc)))
+        if tc:
+            ws = _workspace(lib.kmu_pwconv_tc_workspace_bytes(C.byref(desc)), x.device)
+            check(_call("kmu_pwconv_tc_fwd", (B, Cin, Cout, HW), lib.kmu_pwconv_tc_fwd, C.byref(desc), ptr(x), ptr(w), ptr(b), ptr(y),
+                        ws.data_ptr(), ws.numel(), stream_ptr()), "kmu_pwconv_tc_fwd")
+        else:
+            check(_call("kmu_pwconv_fwd", (B, Cin, Cout, HW), lib.kmu_pwconv_fwd, C.byref(desc), ptr(x), ptr(w), ptr(b), ptr(y),
+                        stream_ptr()), "kmu_pwconv_fwd")
         ctx.save_for_backward(x, w)
-        ctx.desc, ctx.has_bias, ctx.wshape = desc, bias is not None, weight.shape
+        ctx.desc, ctx.has_bias, ctx.wshape, ctx.tc = desc, bias is not None, weight.shape, tc
         return y
 
     @staticmethod
@@ -517,10 +523,22 @@ class _PwConvFn(torch.autograd.Function):
         dx = torch.empty_like(x) if need_x else None
         dw = torch.empty_like(w) if need_w else None
         db = torch.empty(desc.Cout, dtype=torch.float32, device=x.device) if (need_w and ctx.has_bias) else None
-        ws = _workspace(lib.kmu_pwconv_bwd_workspace_bytes(C.byref(desc)), x.device)
-        check(_call("kmu_pwconv_bwd", (desc.B, desc.Cin, desc.Cout, desc.HW), lib.kmu_pwconv_bwd, C.byref(desc), ptr(x), ptr(dy), ptr(w),
-                    ptr(dx), ptr(dw), ptr(db), ws.data_ptr(), ws.numel(), stream_ptr()), "kmu_pwconv_bwd")
-        return dx, None if dw is None else dw.reshape(ctx.wshape), db
+        key = (desc.B, desc.Cin, desc.Cout, desc.HW)
+        if ctx.tc:
+            tc_w = bool(lib.kmu_pwconv_tc_wgrad_supported(C.byref(desc)))
+            ws = _workspace(lib.kmu_pwconv_tc_workspace_bytes(C.byref(desc)), x.device)
+            check(_call("kmu_pwconv_tc_bwd", key, lib.kmu_pwconv_tc_bwd, C.byref(desc), ptr(x), ptr(dy), ptr(w), ptr(dx),
+                        ptr(dw) if tc_w else None, ptr(db) if tc_w else None, ws.data_ptr(), ws.numel(), stream_ptr()),
+                  "kmu_pwconv_tc_bwd")
+            if need_w and not tc_w:          # Cin > 240: the weight gradient stays on the fp32 kernel
+                ws2 = _workspace(lib.kmu_pwconv_bwd_workspace_bytes(C.byref(desc)), x.device)
+                check(_call("kmu_pwconv_bwd", key, lib.kmu_pwconv_bwd, C.byref(desc), ptr(x), ptr(dy), ptr(w), None, ptr(dw), ptr(db),
+                            ws2.data_ptr(), ws2.numel(), stream_ptr()), "kmu_pwconv_bwd")
+        else:
+            ws = _workspace(lib.kmu_pwconv_bwd_workspace_bytes(C.byref(desc)), x.device)
+            check(_call("kmu_pwconv_bwd", key, lib.kmu_pwconv_bwd, C.byref(desc), ptr(x), ptr(dy), ptr(w), ptr(dx), ptr(dw), ptr(db),
+                        ws.data_ptr(), ws.numel(), stream_ptr()), "kmu_pwconv_bwd")
+        return dx, None if dw is None else dw.reshape(ctx.wshape), db, None
 
 
 def pwconv_supported(cin, cout):
@@ -529,11 +547,12 @@ def pwconv_supported(cin, cout):
     return bool(_lib.lib().kmu_pwconv_wgrad_supported(C.byref(d)))
 
 
-def pwconv(x, weight, bias=None):
-    """1x1 convolution on NCHW: weight (Cout,Cin,1,1) or (Cout,Cin), optional bias (Cout)."""
+def pwconv(x, weight, bias=None, precision=KMU_PREC_FP32):
+    """1x1 convolution on NCHW: weight (Cout,Cin,1,1) or (Cout,Cin), optional bias (Cout).  precision=KMU_PREC_BF16 takes the
+    tcgen05 kernels where the channel counts allow (multiples of 16 up to 256), the fp32 kernels otherwise."""
     if not x.is_cuda:
         raise RuntimeError("km_unet_b200.pwconv: CUDA tensors only (no CPU fallback)")
-    return _PwConvFn.apply(x, weight, bias)
+    return _PwConvFn.apply(x, weight, bias, int(precision))
 
 
 # ------------------------------------------------------------------------------------------------------ caller-side fusions

@@ -52,7 +52,7 @@ def _dwconv3x3(x, weight, bias=None):
     return F.conv2d(x, weight, bias, stride=1, padding=1, groups=x.shape[1])
 
 
-def _pwconv(x, weight, bias=None):
+def _pwconv(x, weight, bias=None, precision=0):
     import torch.nn.functional as F
     return F.conv2d(x, weight.reshape(weight.shape[0], weight.shape[1], 1, 1), bias)
 

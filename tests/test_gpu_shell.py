@@ -209,3 +209,29 @@ def test_iwp_vs_matrix_form(B, C, S):
     assert rel_err(xc.grad, xd.grad) < TOL
     assert rel_err(wc.grad, wd.grad) < TOL
     assert rel_err(bc.grad, bd.grad) < TOL
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W,bias", [(2, 16, 64, 32, 32, True), (3, 64, 16, 7, 9, False), (2, 16, 48, 16, 16, True),
+                                                (1, 256, 64, 8, 8, True), (2, 64, 256, 12, 12, False), (2, 128, 32, 5, 5, True),
+                                                (8, 16, 64, 128, 128, True), (2, 32, 32, 64, 64, True), (2, 64, 192, 32, 32, True)])
+def test_pwconv_tcgen05_within_2e2(B, Cin, Cout, H, W, bias):
+    """bf16 tensor-core path of the pointwise convolution (forward, dgrad, MN-major wgrad with the ones-column bias gradient)."""
+    from km_unet_b200 import ops
+    torch.manual_seed(Cin + Cout + H)
+    x = torch.randn(B, Cin, H, W)
+    w = torch.randn(Cout, Cin, 1, 1) / Cin ** 0.5
+    bv = torch.randn(Cout) if bias else None
+    gout = torch.randn(B, Cout, H, W)
+    xd, wd = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    bd = bv.double().requires_grad_(True) if bias else None
+    want = F.conv2d(xd, wd, bd)
+    want.backward(gout.double())
+    xc, wc = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+    bc = bv.cuda().requires_grad_(True) if bias else None
+    y = ops.pwconv(xc, wc, bc, ops.KMU_PREC_BF16)
+    assert rel_err(y, want) < 2e-2
+    y.backward(gout.cuda())
+    assert rel_err(xc.grad, xd.grad) < 2e-2
+    assert rel_err(wc.grad, wd.grad) < 2e-2
+    if bias:
+        assert rel_err(bc.grad, bd.grad) < 2e-2
