@@ -119,6 +119,109 @@ __global__ void __launch_bounds__(128) pw_tc_kernel(const float* __restrict__ in
   }
 }
 
+// ---- persistent, software-pipelined variant of pw_tc_kernel for NI <= 64 (G = NI/8 in {2,4,8}): a CTA walks many tiles with
+// the weights resident, two A buffers and two TMEM accumulators; the next tile's global loads are issued into registers before
+// the current tile's epilogue stores, so load latency hides behind the store stream.
+template <int G>
+__global__ void __launch_bounds__(128) pw_tc_persistent_kernel(const float* __restrict__ in, const __nv_bfloat16* __restrict__ wpack,
+                                                               const float* __restrict__ bias, float* __restrict__ out, int NJ, int NJp,
+                                                               int HW, int ntiles, int tmem_cols) {
+  constexpr int NI = G * 8, KS = G / 2;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* a_base = smem;                                   // [2][G][128][16 B]
+  uint8_t* w_base = smem + (size_t)2 * G * PLANE;           // [KS][2][NJp][16 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_base + (size_t)NI * NJp * 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), (uint32_t)tmem_cols);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(wpack);
+    uint4* dst = reinterpret_cast<uint4*>(w_base);
+    for (int i = tid; i < NI * NJp * 2 / 16; i += 128) dst[i] = __ldg(src + i);
+  }
+  const int tiles_per_img = (HW + TPX - 1) / TPX;
+  float f[G][8];
+  auto fetch = [&](int tile) {
+    const int b = tile / tiles_per_img, p = (tile - b * tiles_per_img) * TPX + tid;
+    const float* sp = in + (size_t)b * NI * HW + p;
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[g][e] = p < HW ? __ldg(sp + (size_t)(g * 8 + e) * HW) : 0.f;
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+      *reinterpret_cast<uint4*>(a_base + (size_t)(buf * G + g) * PLANE + (size_t)tid * 16) =
+          make_uint4(pack_bf16x2(f[g][0], f[g][1]), pack_bf16x2(f[g][2], f[g][3]), pack_bf16x2(f[g][4], f[g][5]), pack_bf16x2(f[g][6], f[g][7]));
+  };
+  const uint32_t idesc = make_idesc_bf16(128, NJp);
+  auto issue = [&](uint32_t tmem_base, int buf) {          // one thread
+    const uint32_t a0 = smem_u32(a_base + (size_t)buf * G * PLANE), w0 = smem_u32(w_base);
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const uint64_t adesc = make_smem_desc(a0 + (uint32_t)(ks * 2 * PLANE), PLANE, 128);
+      const uint64_t bdesc = make_smem_desc(w0 + (uint32_t)(ks * 2 * NJp * 16), NJp * 16, 128);
+      umma_bf16(tmem_base + (uint32_t)(buf * NJp), adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
+    }
+    umma_commit(smem_u32(&bars[buf]));
+  };
+  int tile = blockIdx.x;
+  if (tile < ntiles) {
+    fetch(tile);
+    stash(0);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (tile < ntiles && tid == 0) issue(tmem_base, 0);
+  uint32_t it = 0;
+  for (; tile < ntiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const int next = tile + gridDim.x;
+    if (next < ntiles) fetch(next);                         // in flight during the epilogue below
+    mbar_wait(smem_u32(&bars[buf]), (it >> 1) & 1u);
+    tc_fence_after();
+    {
+      const int b = tile / tiles_per_img, p = (tile - b * tiles_per_img) * TPX + warp * 32 + lane;
+      float* op = out + (size_t)b * NJ * HW + p;
+      for (int n0 = 0; n0 < NJp; n0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * NJp + n0), v);
+        tmem_ld_wait();
+        if (p < HW) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int n = n0 + e;
+            if (n < NJ) op[(size_t)n * HW] = __uint_as_float(v[e]) + (bias ? __ldg(bias + n) : 0.f);
+          }
+        }
+      }
+    }
+    if (next < ntiles) {
+      stash(buf ^ 1);                                       // that buffer's MMA (tile it-1) completed before its epilogue ran
+      fence_proxy_async_smem();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (next < ntiles && tid == 0) issue(tmem_base, buf ^ 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+  }
+}
+
 // weight / bias gradient: D[o][c] = sum_p dy[o][p] x[c][p], both operands MN-major (K = pixels).  Column Cin of the N
 // dimension is a constant-one plane, so D[o][Cin] = sum_p dy[o][p] = the bias gradient.  A CTA walks its share of the
 // 128-pixel tiles, accumulating in TMEM the whole time; partial[cta][h][m][Np] for o = h*128 + m.
@@ -200,6 +303,121 @@ __global__ void __launch_bounds__(128) pw_wgrad_tc_kernel(const float* __restric
   }
 }
 
+// ---- software-pipelined variant for layers with at most 10 channel groups in total (Cin + Cout <= 80, i.e. the 16-channel
+// stages that hold most of the pixels): two shared-memory buffers; the next tile's dy / x values are fetched into registers
+// while the tensor core contracts the current tile.
+constexpr int WG_MAXG = 10;
+__global__ void __launch_bounds__(128) pw_wgrad_tc_pipe_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                               float* __restrict__ partial, int Cin, int Cout, int HW, int ntiles,
+                                                               int Np, int tmem_cols) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int GA = 16, GB = Np / 8, GT = GA + GB;             // MH == 1 here
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)2 * GT * PLANE);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 2 * GT * PLANE / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), (uint32_t)tmem_cols);
+  const int tiles_per_img = (HW + TPX - 1) / TPX;
+  const int gx = Cin / 8, gy = Cout / 8;
+  float f[WG_MAXG][8];
+  bool pvalid = false;
+  auto fetch = [&](int tile) {
+    const int b = tile / tiles_per_img, p = (tile - b * tiles_per_img) * TPX + tid;
+    pvalid = p < HW;
+    const float* yp = dy + (size_t)b * Cout * HW + p;
+    const float* xp = x + (size_t)b * Cin * HW + p;
+#pragma unroll
+    for (int g = 0; g < WG_MAXG; ++g) {
+      if (g < gy) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[g][e] = pvalid ? __ldg(yp + (size_t)(g * 8 + e) * HW) : 0.f;
+      } else if (g < gy + gx) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[g][e] = pvalid ? __ldg(xp + (size_t)((g - gy) * 8 + e) * HW) : 0.f;
+      }
+    }
+  };
+  auto stash = [&](int buf) {
+    uint8_t* a_base = smem + (size_t)buf * GT * PLANE;
+    uint8_t* b_base = a_base + (size_t)GA * PLANE;
+#pragma unroll
+    for (int g = 0; g < WG_MAXG; ++g) {
+      if (g < gy + gx) {
+        uint8_t* dst = (g < gy ? a_base + (size_t)g * PLANE : b_base + (size_t)(g - gy) * PLANE) + (size_t)tid * 16;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(f[g][0], f[g][1]), pack_bf16x2(f[g][2], f[g][3]),
+                                                    pack_bf16x2(f[g][4], f[g][5]), pack_bf16x2(f[g][6], f[g][7]));
+      }
+    }
+    *reinterpret_cast<uint4*>(b_base + (size_t)gx * PLANE + (size_t)tid * 16) = make_uint4(pvalid ? 0x00003F80u : 0u, 0u, 0u, 0u);
+  };
+  const uint32_t idesc = make_idesc_bf16_mn(128, Np);
+  auto issue = [&](uint32_t tmem_base, int buf, bool first) {
+    const uint32_t a0 = smem_u32(smem + (size_t)buf * GT * PLANE), b0 = a0 + (uint32_t)(GA * PLANE);
+#pragma unroll
+    for (int ks = 0; ks < TPX / 16; ++ks) {
+      const uint64_t adesc = make_smem_desc(a0 + (uint32_t)(ks * 256), 128, PLANE);
+      const uint64_t bdesc = make_smem_desc(b0 + (uint32_t)(ks * 256), 128, PLANE);
+      umma_bf16(tmem_base, adesc, bdesc, idesc, (!first || ks > 0) ? 1u : 0u);
+    }
+    umma_commit(smem_u32(&bars[buf]));
+  };
+  int tile = blockIdx.x;
+  __syncthreads();                                          // zero fill done before the first stash
+  if (tile < ntiles) {
+    fetch(tile);
+    stash(0);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (tile < ntiles && tid == 0) issue(tmem_base, 0, true);
+  uint32_t it = 0;
+  for (; tile < ntiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const int next = tile + gridDim.x;
+    if (next < ntiles) {
+      fetch(next);                                          // overlaps MMA(it)
+      if (it >= 1) {                                        // buffer buf^1 was read by MMA(it-1)
+        mbar_wait(smem_u32(&bars[buf ^ 1]), ((it - 1) >> 1) & 1u);
+        tc_fence_after();
+      }
+      stash(buf ^ 1);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+      if (tid == 0) issue(tmem_base, buf ^ 1, false);
+    }
+  }
+  if (it > 0) {
+    // the last two MMAs (tiles it-1 and, if any, it-2) must be complete: waiting for the last one is enough (in-order pipe)
+    mbar_wait(smem_u32(&bars[(it - 1) & 1]), ((it - 1) >> 1) & 1u);
+    tc_fence_after();
+    const int m = warp * 32 + lane;
+    float* pp = partial + ((size_t)blockIdx.x * 128 + m) * Np;
+    for (int n0 = 0; n0 < Np; n0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 16; ++e) pp[n0 + e] = __uint_as_float(v[e]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+  }
+}
+
 // dW[o][c] = sum over CTAs; db[o] = column Cin.  CTAs with no tile wrote nothing: only the first `nparts` are summed.
 __global__ void __launch_bounds__(256) pw_wreduce_tc_kernel(const float* __restrict__ partial, int nparts, int MH, int Np, int Cin,
                                                             int Cout, float* __restrict__ dw, float* __restrict__ db) {
@@ -259,10 +477,33 @@ static int run_gemm(const float* in, const float* w, const float* bias, float* o
   const int NJp = (NJ + 15) / 16 * 16;
   pw_tc_pack_kernel<<<cdiv(NI * NJp, 256), 256, 0, st>>>(w, wpack, NI, NJ, NJp, dgrad);
   KMU_LAUNCH_CHECK("pw_tc_pack");
-  const size_t smem = (size_t)(NI / 8) * PLANE + (size_t)NI * NJp * 2 + 64;
-  cudaError_t e = cudaFuncSetAttribute(pw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  KMU_REQUIRE(e == cudaSuccess, KMU_ERR_LAUNCH, "pw_tc: cannot opt in to %zu B shared memory: %s", smem, cudaGetErrorString(e));
-  pw_tc_kernel<<<dim3(cdiv(HW, TPX), B), 128, smem, st>>>(in, wpack, bias, out, NI, NJ, NJp, HW, pow2_cols(NJp));
+  if (NI == 16 || NI == 32 || NI == 64) {
+    // persistent pipelined kernel: a few CTAs per SM, each walking its share of the tiles
+    const int G = NI / 8, ntiles = B * cdiv(HW, TPX);
+    const size_t smem = (size_t)2 * G * PLANE + (size_t)NI * NJp * 2 + 64;
+    int per_sm = (int)(200 * 1024 / (smem + 1024));
+    const int cols = pow2_cols(2 * NJp);
+    if (per_sm > 512 / cols) per_sm = 512 / cols;
+    if (per_sm > 6) per_sm = 6;
+    if (per_sm < 1) per_sm = 1;
+    int grid = 148 * per_sm;
+    if (grid > ntiles) grid = ntiles;
+#define KMU_PW_TC_P(GG)                                                                                                     \
+  do {                                                                                                                      \
+    cudaError_t e = cudaFuncSetAttribute(pw_tc_persistent_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    KMU_REQUIRE(e == cudaSuccess, KMU_ERR_LAUNCH, "pw_tc: cannot opt in to %zu B shared memory: %s", smem, cudaGetErrorString(e)); \
+    pw_tc_persistent_kernel<GG><<<grid, 128, smem, st>>>(in, wpack, bias, out, NJ, NJp, HW, ntiles, cols);                    \
+  } while (0)
+    if (G == 2) KMU_PW_TC_P(2);
+    else if (G == 4) KMU_PW_TC_P(4);
+    else KMU_PW_TC_P(8);
+#undef KMU_PW_TC_P
+  } else {
+    const size_t smem = (size_t)(NI / 8) * PLANE + (size_t)NI * NJp * 2 + 64;
+    cudaError_t e = cudaFuncSetAttribute(pw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    KMU_REQUIRE(e == cudaSuccess, KMU_ERR_LAUNCH, "pw_tc: cannot opt in to %zu B shared memory: %s", smem, cudaGetErrorString(e));
+    pw_tc_kernel<<<dim3(cdiv(HW, TPX), B), 128, smem, st>>>(in, wpack, bias, out, NI, NJ, NJp, HW, pow2_cols(NJp));
+  }
   KMU_LAUNCH_CHECK(dgrad ? "pw_tc_dgrad" : "pw_tc_fwd");
   return KMU_OK;
 }
@@ -309,10 +550,17 @@ int kmu_pwconv_tc_bwd(const kmu_pwconv_desc* d, const float* x, const float* dy,
     const int MH = cdiv(d->Cout, 128), Np = d->Cin + 16;
     const int ctas = wgrad_ctas(*d), ntiles = d->B * cdiv(d->HW, TPX);
     float* partial = (float*)((char*)workspace + wl.partial);
-    const size_t smem = (size_t)(MH * 16 + Np / 8) * PLANE + 64;
-    cudaError_t e = cudaFuncSetAttribute(pw_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    KMU_REQUIRE(e == cudaSuccess, KMU_ERR_LAUNCH, "pw_wgrad_tc: cannot opt in to %zu B shared memory: %s", smem, cudaGetErrorString(e));
-    pw_wgrad_tc_kernel<<<ctas, 128, smem, st>>>(x, dy, partial, d->Cin, d->Cout, d->HW, ntiles, MH, Np, pow2_cols(MH * Np));
+    if (MH == 1 && (d->Cin + d->Cout) / 8 <= WG_MAXG) {
+      const size_t smem = (size_t)2 * (16 + Np / 8) * PLANE + 64;
+      cudaError_t e = cudaFuncSetAttribute(pw_wgrad_tc_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      KMU_REQUIRE(e == cudaSuccess, KMU_ERR_LAUNCH, "pw_wgrad_tc: cannot opt in to %zu B shared memory: %s", smem, cudaGetErrorString(e));
+      pw_wgrad_tc_pipe_kernel<<<ctas, 128, smem, st>>>(x, dy, partial, d->Cin, d->Cout, d->HW, ntiles, Np, pow2_cols(Np));
+    } else {
+      const size_t smem = (size_t)(MH * 16 + Np / 8) * PLANE + 64;
+      cudaError_t e = cudaFuncSetAttribute(pw_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      KMU_REQUIRE(e == cudaSuccess, KMU_ERR_LAUNCH, "pw_wgrad_tc: cannot opt in to %zu B shared memory: %s", smem, cudaGetErrorString(e));
+      pw_wgrad_tc_kernel<<<ctas, 128, smem, st>>>(x, dy, partial, d->Cin, d->Cout, d->HW, ntiles, MH, Np, pow2_cols(MH * Np));
+    }
     KMU_LAUNCH_CHECK("pw_wgrad_tc");
     const int total = d->Cout * (d->Cin + 1);
     pw_wreduce_tc_kernel<<<cdiv(total, 32), 256, 0, st>>>(partial, ctas, MH, Np, d->Cin, d->Cout, dw, dbias);

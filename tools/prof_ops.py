@@ -39,7 +39,7 @@ if what in ("pw", "all"):
         bb = torch.randn(cout, device=dev, requires_grad=True)
         x = torch.randn(B, cin, S, S, device=dev, requires_grad=True)
         for _ in range(reps):
-            y = ops.pwconv(x, w, bb)
+            y = ops.pwconv(x, w, bb, K.config.precision_code(K.config.conv_precision))
             y.backward(torch.ones_like(y))
         torch.cuda.synchronize()
 if what in ("shell", "all"):
