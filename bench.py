@@ -521,9 +521,15 @@ def run_model(h, args):
     table.sort(key=lambda r: -r["ms_per_step"])
     ours_ms = sum(r["ms_per_step"] for r in table)
     dom = table[0]
-    roofline = {"kernel": f"{dom['op']} {tuple(dom['shape'])}", "bound": dom["bound"], "achieved": dom["achieved"],
+    dom_key = f"{dom['op']} {tuple(dom['shape'])}"
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(dom_key)         # DRAM bytes per call from the committed `ncu --set full` capture
+    roofline = {"kernel": dom_key, "bound": dom["bound"], "achieved": dom["achieved"],
                 "peak": peaks["hbm_gbs"] if dom["bound"] == "hbm" else (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]),
-                "unit": dom["unit"], "frac": dom["frac"], "traffic": None,
+                "unit": dom["unit"], "frac": dom["frac"], "traffic": traffic,
                 "peak_source": peaks["source"] + (" HBM copy" if dom["bound"] == "hbm" else " bf16 sustained"),
                 "share_of_step": dom["ms_per_step"] / (total_ms / args.steps),
                 "libkmunet_ms_per_step": ours_ms, "library_and_glue_ms_per_step": total_ms / args.steps - ours_ms, "ops": table[:12]}
