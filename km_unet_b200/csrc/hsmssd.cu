@@ -17,6 +17,8 @@
 //     hsm_proj_dw_bwd  dP -> dx += Wp^T dQ, per-CTA partials of dWp and dWd ; hsm_wgrad_reduce sums them in fixed order.
 // P is materialised in fp32 (B,192,L): with 180 GB of HBM3e that is cheaper than recomputing the projection in the
 // three backward sweeps on CUDA cores.  All reductions are deterministic (no atomics).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace kmu {
@@ -26,6 +28,12 @@ namespace tc {  // hsm_tc.cu: tcgen05 path of the projection
 size_t pack_bytes(int C);
 int project(const float* x, const float* wp, const float* wd, float* P, int B, int C, int H, void* workspace, cudaStream_t st);
 }  // namespace tc
+namespace tcb {  // hsm_tc_bwd.cu: tcgen05 / TMA path of the projection backward
+size_t dpp_bytes(int B, int L);
+size_t workspace_bytes(int B, int C, int H);
+int backward(const float* x, const float* wp, const float* wd, const void* dPp, float* dx, float* dwp, float* dwd, int B, int C, int H,
+             void* workspace, cudaStream_t st);
+}  // namespace tcb
 
 constexpr int N = 64;         // states
 constexpr int N3 = 192;       // projected channels
@@ -440,7 +448,13 @@ __global__ void __launch_bounds__(GT) hsm_gate_bwd_kernel(const float* __restric
 }
 
 // ---- dP = [dBm; dCm; ddt] and the direct part of dx.  thread = position.  grid (ceil(L/256), B).
-template <int C>
+//      PACK: dP is written as bf16 K-group planes dPp[b][n / 8][l][n % 8] (16 bytes per thread and group, fully coalesced) --
+//      the operand image of the tcgen05 backward (hsm_tc_bwd.cu) -- instead of fp32 (B,192,L).
+__device__ __forceinline__ uint32_t dp_pack2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+template <int C, bool PACK>
 __global__ void __launch_bounds__(256, 2) hsm_dp_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                      const float* __restrict__ P, const float* __restrict__ stats,
                                                      const float* __restrict__ dhs, const float* __restrict__ ho,
@@ -467,6 +481,7 @@ __global__ void __launch_bounds__(256, 2) hsm_dp_kernel(const float* __restrict_
   const float* dyb = dy + (size_t)b * C * d.L + l;
   const float* Pb = P + (size_t)b * N3 * d.L + l;
   float* dPb = dP + (size_t)b * N3 * d.L + l;
+  uint4* dPq = reinterpret_cast<uint4*>(dP) + (size_t)b * 24 * d.L + l;  // PACK: plane g at dPq[g * L]
   float t[64];
 #pragma unroll
   for (int nn = 0; nn < 64; ++nn) t[nn] = 0.f;
@@ -485,14 +500,29 @@ __global__ void __launch_bounds__(256, 2) hsm_dp_kernel(const float* __restrict_
     }
   }
 #pragma unroll
-  for (int nn = 0; nn < 64; ++nn) {
-    float dtv = __ldg(Pb + (size_t)(2 * N + nn) * d.L);
-    float bm = __ldg(Pb + (size_t)nn * d.L);
-    float a = expf(dtv - m_s[nn]) * m_s[64 + nn];
-    float dG = t[nn];
-    dPb[(size_t)nn * d.L] = dG * a;                                   // dBm
-    dPb[(size_t)(2 * N + nn) * d.L] = a * (dG * bm - m_s[128 + nn]);  // ddt
-    t[nn] = a * bm;
+  for (int g = 0; g < 8; ++g) {
+    float vb[8], vt[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int nn = g * 8 + e;
+      float dtv = __ldg(Pb + (size_t)(2 * N + nn) * d.L);
+      float bm = __ldg(Pb + (size_t)nn * d.L);
+      float a = expf(dtv - m_s[nn]) * m_s[64 + nn];
+      float dG = t[nn];
+      vb[e] = dG * a;                             // dBm
+      vt[e] = a * (dG * bm - m_s[128 + nn]);      // ddt
+      t[nn] = a * bm;
+    }
+    if (PACK) {
+      dPq[(size_t)g * d.L] = make_uint4(dp_pack2(vb[0], vb[1]), dp_pack2(vb[2], vb[3]), dp_pack2(vb[4], vb[5]), dp_pack2(vb[6], vb[7]));
+      dPq[(size_t)(16 + g) * d.L] = make_uint4(dp_pack2(vt[0], vt[1]), dp_pack2(vt[2], vt[3]), dp_pack2(vt[4], vt[5]), dp_pack2(vt[6], vt[7]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        dPb[(size_t)(g * 8 + e) * d.L] = vb[e];
+        dPb[(size_t)(2 * N + g * 8 + e) * d.L] = vt[e];
+      }
+    }
   }
   // direct dx[c] = sum_n dhs[c][n] A[n] Bm[n]
   float* dxb = dx + (size_t)b * C * d.L + l;
@@ -526,8 +556,15 @@ __global__ void __launch_bounds__(256, 2) hsm_dp_kernel(const float* __restrict_
       t[4 * i + 3] = fmaf(h.w, gv, t[4 * i + 3]);
     }
   }
+  if (PACK) {
 #pragma unroll
-  for (int nn = 0; nn < 64; ++nn) dPb[(size_t)(N + nn) * d.L] = t[nn];
+    for (int g = 0; g < 8; ++g)
+      dPq[(size_t)(8 + g) * d.L] = make_uint4(dp_pack2(t[g * 8], t[g * 8 + 1]), dp_pack2(t[g * 8 + 2], t[g * 8 + 3]),
+                                              dp_pack2(t[g * 8 + 4], t[g * 8 + 5]), dp_pack2(t[g * 8 + 6], t[g * 8 + 7]));
+  } else {
+#pragma unroll
+    for (int nn = 0; nn < 64; ++nn) dPb[(size_t)(N + nn) * d.L] = t[nn];
+  }
 }
 
 // ---- projection / depthwise backward on a spatial tile.  grid (tiles, B), 256 threads, tile = 8 rows x 32 columns.
@@ -868,15 +905,20 @@ static FwdWs fwd_ws(const Dims& d) {
   return w;
 }
 struct BwdWs { size_t part_dho, dhs, r, wpart, dP, tpart, total; };
-static BwdWs bwd_ws(const Dims& d) {
+static BwdWs bwd_ws(const Dims& d, int precision) {
   BwdWs w;
   size_t o = 0;
   w.part_dho = o; o += align_up((size_t)d.B * d.T * d.C * 64 * 4, 256);
   w.dhs = o; o += align_up((size_t)d.B * d.C * 64 * 4, 256);
   w.r = o; o += align_up((size_t)d.B * 64 * 4, 256);
   w.wpart = o; o += align_up((size_t)d.B * (3 * d.C * d.C + 1) * 4, 256);
-  w.dP = o; o += align_up((size_t)d.B * N3 * d.L * 4, 256);
-  w.tpart = o; o += align_up((size_t)d.B * d.tiles_x * d.tiles_y * (N3 * d.C + N3 * 9) * 4, 256);
+  if (precision == KMU_PREC_BF16) {  // dP as bf16 planes; tpart = the tcgen05 backward's own workspace
+    w.dP = o; o += tcb::dpp_bytes(d.B, d.L);
+    w.tpart = o; o += tcb::workspace_bytes(d.B, d.C, d.H);
+  } else {
+    w.dP = o; o += align_up((size_t)d.B * N3 * d.L * 4, 256);
+    w.tpart = o; o += align_up((size_t)d.B * d.tiles_x * d.tiles_y * (N3 * d.C + N3 * 9) * 4, 256);
+  }
   w.total = o;
   return w;
 }
@@ -900,7 +942,7 @@ size_t kmu_hsmssd_fwd_workspace_bytes(const kmu_hsmssd_desc* dd) {
 }
 size_t kmu_hsmssd_bwd_workspace_bytes(const kmu_hsmssd_desc* dd) {
   if (check(dd, "hsmssd_bwd_workspace_bytes") != KMU_OK) return 0;
-  return bwd_ws(make_dims(*dd)).total;
+  return bwd_ws(make_dims(*dd), dd->precision).total;
 }
 
 int kmu_hsmssd_fwd(const kmu_hsmssd_fwd_args* a, kmu_stream stream) {
@@ -978,7 +1020,8 @@ int kmu_hsmssd_bwd(const kmu_hsmssd_bwd_args* a, kmu_stream stream) {
   KMU_REQUIRE(a->dx && a->d_w_bcdt && a->d_w_dw && a->d_w_hz && a->d_w_out && a->d_D, KMU_ERR_BAD_ARG,
               "hsmssd_bwd: null output tensor");
   Dims d = make_dims(a->d);
-  BwdWs w = bwd_ws(d);
+  const bool tcbwd = a->d.precision == KMU_PREC_BF16;
+  BwdWs w = bwd_ws(d, a->d.precision);
   KMU_REQUIRE(a->workspace && a->workspace_bytes >= w.total, KMU_ERR_WORKSPACE, "hsmssd_bwd: workspace %zu < %zu",
               a->workspace_bytes, w.total);
   cudaStream_t st = (cudaStream_t)stream;
@@ -1019,8 +1062,13 @@ int kmu_hsmssd_bwd(const kmu_hsmssd_bwd_args* a, kmu_stream stream) {
     dim3 grid(cdiv(d.L, 256), d.B);
 #define KMU_HSM_DP(CC)                                                                                              \
   do {                                                                                                              \
-    opt_in_smem(hsm_dp_kernel<CC>, smem);                                                                           \
-    hsm_dp_kernel<CC><<<grid, 256, smem, st>>>(a->x, a->dy, a->P, a->stats, dhs, a->h, r, dP, a->dx, d);             \
+    if (tcbwd) {                                                                                                    \
+      opt_in_smem(hsm_dp_kernel<CC, true>, smem);                                                                   \
+      hsm_dp_kernel<CC, true><<<grid, 256, smem, st>>>(a->x, a->dy, a->P, a->stats, dhs, a->h, r, dP, a->dx, d);     \
+    } else {                                                                                                        \
+      opt_in_smem(hsm_dp_kernel<CC, false>, smem);                                                                  \
+      hsm_dp_kernel<CC, false><<<grid, 256, smem, st>>>(a->x, a->dy, a->P, a->stats, dhs, a->h, r, dP, a->dx, d);    \
+    }                                                                                                               \
   } while (0)
     switch (C) {
       case 16: KMU_HSM_DP(16); break;
@@ -1030,7 +1078,10 @@ int kmu_hsmssd_bwd(const kmu_hsmssd_bwd_args* a, kmu_stream stream) {
 #undef KMU_HSM_DP
     KMU_LAUNCH_CHECK("hsm_dp");
   }
-  {
+  if (tcbwd) {
+    int rc = tcb::backward(a->x, a->w_bcdt, a->w_dw, dP, a->dx, a->d_w_bcdt, a->d_w_dw, d.B, C, d.H, tpart, st);
+    if (rc != KMU_OK) return rc;
+  } else {
     size_t smem = ((size_t)BN * NHALO + 2 * (size_t)BN * QP + (size_t)C * QP + 2 * (size_t)C * BN + BN * 12) * 4;
     int tiles = d.tiles_x * d.tiles_y;
     dim3 grid(tiles, d.B);

@@ -136,7 +136,7 @@ def test_softmax_over_L_sums_to_one_full_size():
     assert rel_err(y2, 3 * y1) < 1e-5
 
 
-@pytest.mark.parametrize("B,C,H", [(2, 16, 40), (1, 32, 33), (2, 64, 32), (2, 16, 128)])
+@pytest.mark.parametrize("B,C,H", [(2, 16, 40), (1, 32, 33), (2, 64, 32), (2, 16, 128), (3, 64, 17), (2, 32, 64)])
 def test_hsmssd_tcgen05_projection_within_2e2(B, C, H):
     """KMU_PREC_BF16: the BCdt projection + depthwise conv of the forward as one tcgen05 3x3 convolution (bf16 operands, fp32
     accumulation).  Tolerance = the 2e-2 gate north_star states for bf16 tensor-core math; ragged tile edges included."""
@@ -165,3 +165,7 @@ def test_hsmssd_tcgen05_projection_within_2e2(B, C, H):
     assert rel_err(y.reshape(want.shape), want) < 2e-2
     assert rel_err(xc.grad, xd.grad) < 2e-2
     assert rel_err(m.BCdt_proj.conv.weight.grad, W[0].grad) < 2e-2
+    # backward of the projection = tcgen05 dgrad + wgrad of the same dense 3x3 convolution (hsm_tc_bwd.cu)
+    assert rel_err(m.dw.conv.weight.grad, W[1].grad) < 2e-2
+    assert rel_err(m.hz_proj.conv.weight.grad, W[2].grad) < 2e-2
+    assert rel_err(m.out_proj.conv.weight.grad, W[3].grad) < 2e-2
