@@ -88,14 +88,15 @@ __global__ void __launch_bounds__(128) hsm_proj_tc_kernel(const float* __restric
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (tid == 0) {
-    const uint32_t a0 = smem_u32(a_base), w0 = smem_u32(w_base);
+    const uint64_t adesc0 = make_smem_desc(smem_u32(a_base), PLANE, PITCH * 16);
+    const uint64_t bdesc0 = make_smem_desc(smem_u32(w_base), NS * 16, 128);
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const int ki = t / 3, kj = t - ki * 3;
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
-        const uint64_t adesc = make_smem_desc(a0 + (uint32_t)(ks * 2 * PLANE + (ki * PITCH + kj) * 16), PLANE, PITCH * 16);
-        const uint64_t bdesc = make_smem_desc(w0 + (uint32_t)((t * KS + ks) * WBLK), NS * 16, 128);
+        const uint64_t adesc = desc_advance(adesc0, (uint32_t)(ks * 2 * PLANE + (ki * PITCH + kj) * 16));
+        const uint64_t bdesc = desc_advance(bdesc0, (uint32_t)((t * KS + ks) * WBLK));
         umma_bf16(tmem_base, adesc, bdesc, IDESC, (t > 0 || ks > 0) ? 1u : 0u);
       }
     }

@@ -137,14 +137,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) hsm_dgrad_tc_kernel(const __grid_
     // ===================================================================== MMA issuer
     if (lane == 0) {
       constexpr uint32_t IDESC = make_idesc_bf16(128, 16);
-      const uint32_t w0 = smem_u32(w_base);
+      const uint64_t bdesc0 = make_smem_desc(smem_u32(w_base), 16 * 16, 128);
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const uint32_t s = it & 1u;
         mbar_wait_hot(smem_u32(&acc_empty[s]), ((it >> 1) & 1u) ^ 1u);
         mbar_wait_hot(smem_u32(&full[s]), (it >> 1) & 1u);
         tc_fence_after();
-        const uint32_t a0 = smem_u32(a_base + (size_t)s * DG_STAGE);
+        const uint64_t adesc0 = make_smem_desc(smem_u32(a_base + (size_t)s * DG_STAGE), PLANE, PITCH * 16);
         const uint32_t d_tmem = tmem_base + s * 16u;
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
@@ -152,8 +152,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) hsm_dgrad_tc_kernel(const __grid_
           const uint32_t ashift = (uint32_t)(((2 - ki) * PITCH + (2 - kj)) * 16);
 #pragma unroll
           for (int ks = 0; ks < 12; ++ks) {
-            const uint64_t adesc = make_smem_desc(a0 + (uint32_t)(ks * 2 * PLANE) + ashift, PLANE, PITCH * 16);
-            const uint64_t bdesc = make_smem_desc(w0 + (uint32_t)((t * 12 + ks) * DG_WBLK), 16 * 16, 128);
+            const uint64_t adesc = desc_advance(adesc0, (uint32_t)(ks * 2 * PLANE) + ashift);
+            const uint64_t bdesc = desc_advance(bdesc0, (uint32_t)((t * 12 + ks) * DG_WBLK));
             umma_bf16(d_tmem, adesc, bdesc, IDESC, (t > 0 || ks > 0) ? 1u : 0u);
           }
         }
@@ -268,15 +268,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) hsm_wgrad_tc_kernel(const __grid_
         const uint32_t s = it % WG_STAGES;
         mbar_wait_hot(smem_u32(&full[s]), (it / WG_STAGES) & 1u);
         tc_fence_after();
-        const uint32_t a0 = smem_u32(smem + (size_t)s * STAGE), x0 = a0 + (uint32_t)WG_A;
+        // MN-major: LBO = byte step between the two 8-pixel K groups (next tile row), SBO = byte step between 8-channel groups
+        const uint64_t adesc0 = make_smem_desc(smem_u32(smem + (size_t)s * STAGE), PITCH * 16, PLANE);
+        const uint64_t bdesc0 = desc_advance(adesc0, (uint32_t)WG_A);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {  // K step = two tile rows of 8 pixels
-          // MN-major: LBO = byte step between the two 8-pixel K groups (next tile row), SBO = byte step between 8-channel groups
-          const uint64_t adesc = make_smem_desc(a0 + (uint32_t)(((1 + 2 * ks) * PITCH + 1) * 16), PITCH * 16, PLANE);
+          const uint64_t adesc = desc_advance(adesc0, (uint32_t)(((1 + 2 * ks) * PITCH + 1) * 16));
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
             const int ki = t / 3, kj = t - ki * 3;
-            const uint64_t bdesc = make_smem_desc(x0 + (uint32_t)(((2 * ks + ki) * PITCH + kj) * 16), PITCH * 16, PLANE);
+            const uint64_t bdesc = desc_advance(bdesc0, (uint32_t)(((2 * ks + ki) * PITCH + kj) * 16));
             umma_bf16(tmem_base + (uint32_t)(t * NCW), adesc, bdesc, IDESC, (it > 0 || ks > 0) ? 1u : 0u);
           }
         }

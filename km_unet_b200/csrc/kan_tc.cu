@@ -223,14 +223,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) kan_fwd_tc_kernel(const float*
             }
             mbar_wait_hot(smem_u32(&w_full[ws]), (wit / W_STAGES) & 1u);
             tc_fence_after();
-            const uint32_t b0 = smem_u32(w_base + (size_t)ws * WSTAGE);
+            const uint64_t bdesc0 = make_smem_desc(smem_u32(w_base + (size_t)ws * WSTAGE), N * 16, 128);
+            const uint64_t adesc0 = make_smem_desc(a0, PLANE, PITCH * 16);
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
               const int ki = t / 3, kj = t - ki * 3;
-              const uint64_t bdesc = make_smem_desc(b0 + (uint32_t)t * (2 * N * 16), N * 16, 128);
+              const uint64_t bdesc = desc_advance(bdesc0, (uint32_t)t * (2 * N * 16));
 #pragma unroll
               for (int i = 0; i < TT; ++i) {
-                const uint64_t adesc = make_smem_desc(a0 + (uint32_t)(((i * 16 + ki) * PITCH + kj) * 16), PLANE, PITCH * 16);
+                const uint64_t adesc = desc_advance(adesc0, (uint32_t)(((i * 16 + ki) * PITCH + kj) * 16));
                 umma_bf16(d_tmem + (uint32_t)(i * N), adesc, bdesc, IDESC, (cb > 0 || j > 0 || t > 0) ? 1u : 0u);
               }
             }

@@ -228,15 +228,16 @@ __global__ void __launch_bounds__(DX_THREADS, 1) kan_bwd_dx_tc_kernel(const floa
         mbar_wait_hot(smem_u32(&acc_empty[s]), ph ^ 1u);
         mbar_wait_hot(smem_u32(&dy_full[s]), ph);
         tc_fence_after();
-        const uint32_t a0 = smem_u32(dy_base + (size_t)s * DYSTAGE);
+        const uint64_t adesc0 = make_smem_desc(smem_u32(dy_base + (size_t)s * DYSTAGE), BPLANE, BP * 16);
+        const uint64_t bdesc0 = make_smem_desc(w0, DX_N * 16, 128);
         const uint32_t d_tmem = tmem_base + s * 256u;
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
           const int si = t / 3, sj = t - si * 3;
 #pragma unroll
           for (int ks = 0; ks < KS; ++ks) {
-            const uint64_t adesc = make_smem_desc(a0 + (uint32_t)(ks * 2 * BPLANE + (si * BP + sj) * 16), BPLANE, BP * 16);
-            const uint64_t bdesc = make_smem_desc(w0 + (uint32_t)((t * KS + ks) * WBLK), DX_N * 16, 128);
+            const uint64_t adesc = desc_advance(adesc0, (uint32_t)(ks * 2 * BPLANE + (si * BP + sj) * 16));
+            const uint64_t bdesc = desc_advance(bdesc0, (uint32_t)((t * KS + ks) * WBLK));
             umma_bf16(d_tmem, adesc, bdesc, IDESC, (t > 0 || ks > 0) ? 1u : 0u);
           }
         }
@@ -445,17 +446,19 @@ __global__ void __launch_bounds__(DW_THREADS, 1) kan_bwd_dw_tc_kernel(const floa
         tc_fence_after();
         const uint32_t phi0 = smem_u32(smem + (size_t)st * C::STAGE);
         const uint32_t dy0 = phi0 + C::PHI_STAGE;
+        const uint64_t bdesc0 = mn_swap ? make_smem_desc(phi0, BPLANE, BP * 16) : make_smem_desc(phi0, BP * 16, BPLANE);
+        const uint64_t adesc0 = mn_swap ? make_smem_desc(dy0, 128, C::DY_ROWB) : make_smem_desc(dy0, C::DY_ROWB, 128);
 #pragma unroll 1
         for (int hk = 0; hk < (BR + 2) / 2; ++hk) {
           const int h = 2 * hk;
+          const uint64_t bdesc_h = desc_advance(bdesc0, (uint32_t)(h * BP * 16));
+          const uint64_t adesc_h = desc_advance(adesc0, (uint32_t)(h * C::DY_ROWB));
 #pragma unroll
           for (int kj = 0; kj < 3; ++kj) {
-            const uint32_t bs = phi0 + (uint32_t)((h * BP + kj) * 16);
-            const uint64_t bdesc = mn_swap ? make_smem_desc(bs, BPLANE, BP * 16) : make_smem_desc(bs, BP * 16, BPLANE);
+            const uint64_t bdesc = desc_advance(bdesc_h, (uint32_t)(kj * 16));
 #pragma unroll
             for (int s = 0; s < C::SETS; ++s) {
-              const uint32_t as = dy0 + (uint32_t)((h + s * C::SLOTS) * C::DY_ROWB);
-              const uint64_t adesc = mn_swap ? make_smem_desc(as, 128, C::DY_ROWB) : make_smem_desc(as, C::DY_ROWB, 128);
+              const uint64_t adesc = desc_advance(adesc_h, (uint32_t)(s * C::SLOTS * C::DY_ROWB));
               umma_bf16(tmem_base + (uint32_t)((s * 3 + kj) * C::N), adesc, bdesc, IDESC, (it > 0 || hk > 0) ? 1u : 0u);
             }
           }

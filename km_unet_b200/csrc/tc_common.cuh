@@ -88,6 +88,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)1 << 46;
   return d;
 }
+// Same descriptor with the start address moved by byte_off (a multiple of 16).  Shared-memory addresses are < 256 KB, so the
+// sum never carries out of the 14-bit field: one 32-bit add per MMA instead of re-deriving the descriptor through a chain
+// of dependent uniform-datapath instructions (measured: ~64 cycles per small-N MMA with the chain, issue-bound).
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t byte_off) {
+  const uint32_t lo = (uint32_t)desc + (byte_off >> 4);
+  return (desc & 0xFFFFFFFF00000000ull) | (uint64_t)lo;
+}
 // Instruction descriptor for kind::f16: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), both K-major, N>>3 at
 // [17,23), M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
