@@ -534,6 +534,10 @@ def run_model(h, args):
                 "share_of_step": dom["ms_per_step"] / (total_ms / args.steps),
                 "libkmunet_ms_per_step": ours_ms, "library_and_glue_ms_per_step": total_ms / args.steps - ours_ms, "ops": table[:12]}
 
+    if rank == 0 and os.environ.get("KMU_BENCH_OPS_DUMP"):   # full per-entry-point table for profiles/
+        with open(os.environ["KMU_BENCH_OPS_DUMP"], "w") as f:
+            json.dump({"ms_per_step": total_ms / args.steps, "libkmunet_ms_per_step": ours_ms, "ops": table}, f, indent=1)
+
     kan = kan_microbench(h, 32, 5, 3, args.precision) if not args.no_kan_microbench else None
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -549,7 +553,7 @@ def run_model(h, args):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * world, "frames": f"{fin}->{classes}",
-                       "size": size, "precision": (f"KANConv2d and the HSM-SSD forward projection {args.precision} (tcgen05), everything else fp32"
+                       "size": size, "precision": (f"KANConv2d and the HSM-SSD projection (forward, dgrad, wgrad) {args.precision} (tcgen05), everything else fp32"
                                      if args.precision == "bf16" else "fp32 everywhere"),
                        "parallelism": f"dp{world}", "cuda_graph": bool(graphed is not None), "optimizer": "AdamW(lr 1e-3, wd 0.05, fused)" if train else None,
                        "l2": "activations per step (hundreds of %.0f MB tensors) exceed the 126 MB L2" % (B * 16 * size * size * 4 / 1e6),

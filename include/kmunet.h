@@ -461,6 +461,16 @@ int kmu_pwconv_tc_fwd(const kmu_pwconv_desc* d, const float* x, const float* w, 
 int kmu_pwconv_tc_bwd(const kmu_pwconv_desc* d, const float* x, const float* dy, const float* w, float* dx, float* dw, float* dbias,
                       void* workspace, size_t workspace_bytes, kmu_stream stream);
 
+/* Fused backward of the same pointwise convolution (replaces the autograd pair of vim_utils_init.py:122-130 FFN /
+ * KM_UNetV3_SH.py:59,118-122,178,221 1x1 convolutions): ONE persistent TMA -> tcgen05 kernel reads x and dy once and writes dx,
+ * dW and (if dbias != NULL) db.  bf16 operands, fp32 TMEM accumulation (2e-2 gate).  Supported when Cin, Cout are multiples of
+ * 16 (Cin <= 240, Cout <= 256), HW >= 128 and a multiple of 4, x / dy 16-byte aligned and the tile ring fits shared memory
+ * (kmu_pwconv_fused_bwd_supported); dx and dw are both required. */
+int kmu_pwconv_fused_bwd_supported(const kmu_pwconv_desc* d);
+size_t kmu_pwconv_fused_bwd_workspace_bytes(const kmu_pwconv_desc* d);
+int kmu_pwconv_fused_bwd(const kmu_pwconv_desc* d, const float* x, const float* dy, const float* w, float* dx, float* dw,
+                         float* dbias, void* workspace, size_t workspace_bytes, kmu_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

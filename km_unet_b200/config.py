@@ -8,6 +8,10 @@ kan_precision = os.environ.get("KMU_KAN_PRECISION", "fp32")
 hsm_precision = os.environ.get("KMU_HSM_PRECISION", "fp32")
 # same switch for the pointwise (1x1) convolutions of the callers / EfficientViMBlock FFN
 conv_precision = os.environ.get("KMU_CONV_PRECISION", "fp32")
+# backward of the pointwise convolutions: "split" = input-gradient kernel + weight-gradient kernel of conv_precision's family;
+# "fused" = one persistent TMA -> tcgen05 kernel that reads x and dy once and writes dx, dW, db (bf16 operands, 2e-2 gate) where
+# the shape allows, the split kernels otherwise
+conv_bwd = os.environ.get("KMU_CONV_BWD", "split")
 
 
 def precision_code(name=None):

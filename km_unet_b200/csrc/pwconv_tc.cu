@@ -444,6 +444,14 @@ __global__ void __launch_bounds__(256) pw_wreduce_tc_kernel(const float* __restr
   }
 }
 
+// host-side launchers for pwconv_bwd_tc.cu (kernels cannot be launched across translation units without -rdc)
+void launch_pack(const float* w, __nv_bfloat16* wpack, int NI, int NJ, int NJp, int dgrad, cudaStream_t st) {
+  pw_tc_pack_kernel<<<cdiv(NI * NJp, 256), 256, 0, st>>>(w, wpack, NI, NJ, NJp, dgrad);
+}
+void launch_wreduce(const float* partial, int nparts, int MH, int Np, int Cin, int Cout, float* dw, float* db, cudaStream_t st) {
+  pw_wreduce_tc_kernel<<<cdiv(Cout * (Cin + 1), 32), 256, 0, st>>>(partial, nparts, MH, Np, Cin, Cout, dw, db);
+}
+
 static int pow2_cols(int n) {
   int c = 32;
   while (c < n) c <<= 1;

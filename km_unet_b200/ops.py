@@ -524,7 +524,13 @@ class _PwConvFn(torch.autograd.Function):
         dw = torch.empty_like(w) if need_w else None
         db = torch.empty(desc.Cout, dtype=torch.float32, device=x.device) if (need_w and ctx.has_bias) else None
         key = (desc.B, desc.Cin, desc.Cout, desc.HW)
-        if ctx.tc:
+        from . import config
+        if (config.conv_bwd == "fused" and need_x and need_w and dy.data_ptr() % 16 == 0 and x.data_ptr() % 16 == 0
+                and bool(lib.kmu_pwconv_fused_bwd_supported(C.byref(desc)))):
+            ws = _workspace(lib.kmu_pwconv_fused_bwd_workspace_bytes(C.byref(desc)), x.device)
+            check(_call("kmu_pwconv_fused_bwd", key, lib.kmu_pwconv_fused_bwd, C.byref(desc), ptr(x), ptr(dy), ptr(w), ptr(dx),
+                        ptr(dw), ptr(db), ws.data_ptr(), ws.numel(), stream_ptr()), "kmu_pwconv_fused_bwd")
+        elif ctx.tc:
             tc_w = bool(lib.kmu_pwconv_tc_wgrad_supported(C.byref(desc)))
             ws = _workspace(lib.kmu_pwconv_tc_workspace_bytes(C.byref(desc)), x.device)
             check(_call("kmu_pwconv_tc_bwd", key, lib.kmu_pwconv_tc_bwd, C.byref(desc), ptr(x), ptr(dy), ptr(w), ptr(dx),

@@ -235,3 +235,40 @@ def test_pwconv_tcgen05_within_2e2(B, Cin, Cout, H, W, bias):
     assert rel_err(wc.grad, wd.grad) < 2e-2
     if bias:
         assert rel_err(bc.grad, bd.grad) < 2e-2
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W,bias", [(2, 16, 64, 32, 32, True), (3, 64, 16, 16, 20, False), (2, 16, 48, 16, 16, True),
+                                                (2, 32, 128, 24, 24, True), (2, 128, 32, 16, 16, True), (5, 16, 16, 12, 12, True),
+                                                (8, 16, 64, 128, 128, True), (2, 32, 96, 64, 64, False), (40, 64, 64, 16, 8, True),
+                                                (2, 32, 32, 13, 12, True)])
+def test_pwconv_fused_backward_within_2e2(B, Cin, Cout, H, W, bias):
+    """config.conv_bwd = "fused": dx, dW, db from ONE persistent TMA -> tcgen05 kernel (bf16 operands, fp32 accumulation).
+    Covers ragged last tiles (HW not a multiple of 128), several tiles per CTA, both plane-buffer / stage plans."""
+    import km_unet_b200 as K
+    from km_unet_b200 import _lib, ops
+    import ctypes as C
+    assert _lib.lib().kmu_pwconv_fused_bwd_supported(C.byref(ops.PwDesc(B, Cin, Cout, H * W)))
+    torch.manual_seed(Cin + Cout + H)
+    x = torch.randn(B, Cin, H, W)
+    w = torch.randn(Cout, Cin, 1, 1) / Cin ** 0.5
+    bv = torch.randn(Cout) if bias else None
+    gout = torch.randn(B, Cout, H, W)
+    xd, wd = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    bd = bv.double().requires_grad_(True) if bias else None
+    want = F.conv2d(xd, wd, bd)
+    want.backward(gout.double())
+    xc, wc = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+    bc = bv.cuda().requires_grad_(True) if bias else None
+    old = K.config.conv_bwd
+    K.config.conv_bwd = "fused"
+    try:
+        n0 = _lib.launch_count()
+        y = ops.pwconv(xc, wc, bc)
+        y.backward(gout.cuda())
+    finally:
+        K.config.conv_bwd = old
+    assert rel_err(y, want) < 1e-4                   # the forward stays on the fp32 kernel
+    assert rel_err(xc.grad, xd.grad) < 2e-2
+    assert rel_err(wc.grad, wd.grad) < 2e-2
+    if bias:
+        assert rel_err(bc.grad, bd.grad) < 2e-2
