@@ -131,6 +131,9 @@ def op_work(name, key):
     if name.startswith("kmu_dwconv3x3"):
         B, C, H, W = key                     # fwd: read x, write y; bwd: read dy (dx), read x and dy (dw), write dx
         return ("hbm", (8.0 if name.endswith("fwd") else 16.0) * B * C * H * W, "byte")
+    if name == "kmu_pwconv_fused_bwd":
+        B, Cin, Cout, HW = key               # one kernel: read x and dy once, write dx
+        return ("hbm", 4.0 * (2 * Cin + Cout) * B * HW, "byte")
     if name.startswith("kmu_pwconv"):
         B, Cin, Cout, HW = key               # fwd: read x, write y; bwd: read dy (dx) + x and dy (dw), write dx
         return ("hbm", (4.0 * (Cin + Cout) if name.endswith("fwd") else 4.0 * (2 * Cin + 2 * Cout)) * B * HW, "byte")
@@ -396,8 +399,9 @@ def run_model(h, args):
     from km_unet_b200.loss import HybridLoss
     K.config.kan_precision = args.precision
     K.config.hsm_precision = args.precision               # HSM-SSD BCdt projection on tcgen05 as well
-    # the pointwise convolutions stay on their fp32 streaming kernels: their tcgen05 path (config.conv_precision = "bf16",
-    # pwconv_tc.cu) is parity-green but not faster yet (one 128-pixel tile per CTA; per-CTA set-up dominates)
+    # pointwise convolutions: forward on the fp32 streaming kernels, backward as ONE fused TMA -> tcgen05 kernel (dx, dW, db from a
+    # single pass over x and dy, pwconv_bwd_tc.cu) when the tensor-core precision class is selected
+    K.config.conv_bwd = "fused" if args.precision == "bf16" else "split"
     _lib.lib()                                            # fail loudly if the extension is missing
     metric, desc, variant, classes, fin, size, default_b, train = WORKLOADS[args.workload]
     B = args.batch or default_b
@@ -553,7 +557,7 @@ def run_model(h, args):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * world, "frames": f"{fin}->{classes}",
-                       "size": size, "precision": (f"KANConv2d and the HSM-SSD projection (forward, dgrad, wgrad) {args.precision} (tcgen05), everything else fp32"
+                       "size": size, "precision": (f"KANConv2d, the HSM-SSD projection (forward, dgrad, wgrad) and the 1x1-convolution backward {args.precision} (tcgen05), everything else fp32"
                                      if args.precision == "bf16" else "fp32 everywhere"),
                        "parallelism": f"dp{world}", "cuda_graph": bool(graphed is not None), "optimizer": "AdamW(lr 1e-3, wd 0.05, fused)" if train else None,
                        "l2": "activations per step (hundreds of %.0f MB tensors) exceed the 126 MB L2" % (B * 16 * size * size * 4 / 1e6),
