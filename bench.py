@@ -402,6 +402,7 @@ def run_model(h, args):
     # pointwise convolutions: forward on the fp32 streaming kernels, backward as ONE fused TMA -> tcgen05 kernel (dx, dW, db from a
     # single pass over x and dy, pwconv_bwd_tc.cu) when the tensor-core precision class is selected
     K.config.conv_bwd = "fused" if args.precision == "bf16" else "split"
+    torch.backends.cudnn.benchmark = True                 # as the reference's training script does (train_shanghai.py:331)
     _lib.lib()                                            # fail loudly if the extension is missing
     metric, desc, variant, classes, fin, size, default_b, train = WORKLOADS[args.workload]
     B = args.batch or default_b

@@ -20,7 +20,7 @@ using namespace kmu::tcx;
 
 constexpr int PITCH = 10, ROWS = 18, NPOS = PITCH * ROWS;  // 8x16 tile + 1-pixel halo
 constexpr int PLANE = NPOS * 16;                           // bytes of one K-group plane (8 channels x bf16 per position)
-constexpr int NS = 64;                                     // output channels per CTA
+constexpr int NS = 64;                                     // output channels per CTA of the projection
 constexpr int WBLK = 2 * NS * 16;                          // bytes of one (tap, k-step) weight block [gi][n][8]
 
 // wpack[slice][tap][ks][gi][n][e] = bf16( wd[slice*64+n][tap] * Wp[slice*64+n][ks*16 + gi*8 + e] )
@@ -40,10 +40,15 @@ __global__ void hsm_tc_pack_kernel(const float* __restrict__ wp, const float* __
   wpack[idx] = __float2bfloat16_rn(wd[ng * 9 + tap] * wp[(size_t)ng * C + c]);
 }
 
-template <int C>
+// Generic form: out[b, z * oz_step + n, p] = sum_{tap, c} w[b][z][n, tap, c] x[b, c, p + tap], n < NSL.  The projection uses
+// NSL = 64 with weights shared by the batch (wb_stride = 0) and z = the Bm / dt slices; the output contraction y = ho Cm uses
+// NSL = C with per-batch weights (see out() below).
+template <int C, int NSL>
 __global__ void __launch_bounds__(128) hsm_proj_tc_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ wpack,
-                                                          float* __restrict__ P, int H, int tiles_x) {
+                                                          float* __restrict__ P, int H, int tiles_x, int out_ch, int oz_step,
+                                                          size_t wz_stride, size_t wb_stride) {
   constexpr int G = C / 8, KS = C / 16;
+  constexpr int NS = NSL, WBLK = 2 * NSL * 16, TCOLS = NSL < 32 ? 32 : NSL;
   constexpr uint32_t IDESC = make_idesc_bf16(128, NS);
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* a_base = smem;                               // [G][NPOS][16 B]
@@ -59,10 +64,10 @@ __global__ void __launch_bounds__(128) hsm_proj_tc_kernel(const float* __restric
     mbar_init(smem_u32(bar), 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 64);
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TCOLS);
   // weights of this slice: plain 16-byte copies (L2-resident, shared by every CTA of the slice)
   {
-    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(wpack) + (size_t)slice * 9 * KS * WBLK);
+    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(wpack) + (size_t)slice * wz_stride + (size_t)b * wb_stride);
     uint4* dst = reinterpret_cast<uint4*>(w_base);
     for (int i = tid; i < 9 * KS * WBLK / 16; i += 128) dst[i] = __ldg(src + i);
   }
@@ -109,7 +114,7 @@ __global__ void __launch_bounds__(128) hsm_proj_tc_kernel(const float* __restric
     const int m = warp * 32 + lane;
     const int gy = ty0 + (m >> 3), gx = tx0 + (m & 7);
     const bool ok = gy < H && gx < H;
-    float* pp = P + ((size_t)b * 192 + slice * NS) * L + (size_t)gy * H + gx;
+    float* pp = P + ((size_t)b * out_ch + slice * oz_step) * L + (size_t)gy * H + gx;
 #pragma unroll
     for (int c0 = 0; c0 < NS; c0 += 16) {
       uint32_t v[16];
@@ -125,34 +130,103 @@ __global__ void __launch_bounds__(128) hsm_proj_tc_kernel(const float* __restric
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 64);
+    tmem_dealloc(tmem_base, TCOLS);
   }
+}
+
+// weff[b][tap][ks][gi][n][e] = bf16( sum_m ho[b, n, m] wd[64 + m, tap] Wp[64 + m, ks*16 + gi*8 + e] ): y = ho Cm with
+// Cm = conv3x3(x; W rows 64..127) is itself a 3x3 convolution of x with these per-batch C x C weights (everything is linear),
+// so the Cm slice of P never has to exist.  grid (9 taps, B), 256 threads; ho[b] and the tap's weight rows staged in shared memory.
+__global__ void __launch_bounds__(256) hsm_tc_weff_kernel(const float* __restrict__ ho, const float* __restrict__ wp,
+                                                          const float* __restrict__ wd, __nv_bfloat16* __restrict__ weff, int C) {
+  extern __shared__ float sm[];
+  float* ho_s = sm;             // [C][65]
+  float* w_s = sm + C * 65;     // [C][65]: w_s[c][m] = wd[64 + m, tap] Wp[64 + m, c]
+  const int tap = blockIdx.x, b = blockIdx.y, KS = C / 16;
+  for (int i = threadIdx.x; i < C * 64; i += 256) {
+    const int r = i >> 6, m = i & 63;
+    ho_s[r * 65 + m] = ho[(size_t)b * C * 64 + i];
+  }
+  for (int i = threadIdx.x; i < C * 64; i += 256) {
+    const int m = i / C, c = i - m * C;              // coalesced along c (rows of Wp)
+    w_s[c * 65 + m] = wd[(64 + m) * 9 + tap] * wp[(size_t)(64 + m) * C + c];
+  }
+  __syncthreads();
+  __nv_bfloat16* wb = weff + ((size_t)b * 9 + tap) * C * C;
+  for (int o = threadIdx.x; o < C * C; o += 256) {  // o = ((ks*2 + gi)*C + n)*8 + e
+    const int e = o & 7, n = (o >> 3) % C, kg = o / (8 * C);
+    const int c = kg * 8 + e;                          // = ks*16 + gi*8 + e
+    const float* hr = ho_s + n * 65;
+    const float* wr = w_s + c * 65;
+    float s = 0.f;
+#pragma unroll 8
+    for (int m = 0; m < 64; ++m) s = fmaf(hr[m], wr[m], s);
+    wb[o] = __float2bfloat16_rn(s);
+  }
+  (void)KS;
 }
 
 size_t pack_bytes(int C) { return align_up((size_t)192 * 9 * C * 2, 256); }
 
+// slices: 3 = Bm, Cm, dt (everything materialised); 2 = Bm and dt only (the Cm slice is folded into out() / the backward's
+// correlation and is neither written nor read)
 template <int C>
-static int launch(const float* x, const __nv_bfloat16* wpack, float* P, int B, int H, cudaStream_t st) {
+static int launch(const float* x, const __nv_bfloat16* wpack, float* P, int B, int H, int slices, cudaStream_t st) {
   constexpr int G = C / 8, KS = C / 16;
   const size_t smem = (size_t)G * PLANE + (size_t)9 * KS * WBLK + 64;
-  cudaError_t e = cudaFuncSetAttribute(hsm_proj_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(hsm_proj_tc_kernel<C, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   KMU_REQUIRE(e == cudaSuccess, KMU_ERR_LAUNCH, "hsm_proj_tc: cannot opt in to %zu B shared memory: %s", smem, cudaGetErrorString(e));
   const int tiles_x = cdiv(H, 8), tiles_y = cdiv(H, 16);
-  hsm_proj_tc_kernel<C><<<dim3(tiles_x * tiles_y, B, 3), 128, smem, st>>>(x, wpack, P, H, tiles_x);
+  const size_t wslice = (size_t)9 * KS * WBLK;
+  if (slices == 3)
+    hsm_proj_tc_kernel<C, NS><<<dim3(tiles_x * tiles_y, B, 3), 128, smem, st>>>(x, wpack, P, H, tiles_x, 192, NS, wslice, 0);
+  else
+    hsm_proj_tc_kernel<C, NS><<<dim3(tiles_x * tiles_y, B, 2), 128, smem, st>>>(x, wpack, P, H, tiles_x, 192, 2 * NS, 2 * wslice, 0);
   KMU_LAUNCH_CHECK("hsm_proj_tc");
   return KMU_OK;
 }
 
+template <int C>
+static int launch_out(const float* x, const __nv_bfloat16* weff, float* y, int B, int H, cudaStream_t st) {
+  constexpr int G = C / 8, KS = C / 16;
+  const size_t wbytes = (size_t)9 * KS * 2 * C * 16;
+  const size_t smem = (size_t)G * PLANE + wbytes + 64;
+  cudaError_t e = cudaFuncSetAttribute(hsm_proj_tc_kernel<C, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  KMU_REQUIRE(e == cudaSuccess, KMU_ERR_LAUNCH, "hsm_out_tc: cannot opt in to %zu B shared memory: %s", smem, cudaGetErrorString(e));
+  const int tiles_x = cdiv(H, 8), tiles_y = cdiv(H, 16);
+  hsm_proj_tc_kernel<C, C><<<dim3(tiles_x * tiles_y, B, 1), 128, smem, st>>>(x, weff, y, H, tiles_x, C, 0, 0, wbytes);
+  KMU_LAUNCH_CHECK("hsm_out_tc");
+  return KMU_OK;
+}
+
+size_t weff_bytes(int B, int C) { return align_up((size_t)B * 9 * C * C * 2, 256); }
+
+// y[b] = ho[b] Cm[b] = conv3x3(x[b]; ho[b] (x) W_Cm) on tensor cores.  workspace >= weff_bytes(B, C).
+int out(const float* x, const float* ho, const float* wp, const float* wd, float* y, int B, int C, int H, void* workspace,
+        cudaStream_t st) {
+  __nv_bfloat16* weff = (__nv_bfloat16*)workspace;
+  hsm_tc_weff_kernel<<<dim3(9, B), 256, (size_t)2 * C * 65 * sizeof(float), st>>>(ho, wp, wd, weff, C);
+  KMU_LAUNCH_CHECK("hsm_tc_weff");
+  switch (C) {
+    case 16: return launch_out<16>(x, weff, y, B, H, st);
+    case 32: return launch_out<32>(x, weff, y, B, H, st);
+    case 64: return launch_out<64>(x, weff, y, B, H, st);
+  }
+  set_error("hsm_out_tc: unsupported C=%d", C);
+  return KMU_ERR_UNSUPPORTED;
+}
+
 // P = conv3x3(x; wd (x) Wp) on tensor cores.  workspace >= pack_bytes(C).
-int project(const float* x, const float* wp, const float* wd, float* P, int B, int C, int H, void* workspace, cudaStream_t st) {
+int project(const float* x, const float* wp, const float* wd, float* P, int B, int C, int H, int slices, void* workspace,
+            cudaStream_t st) {
   __nv_bfloat16* wpack = (__nv_bfloat16*)workspace;
   const int total = 192 * 9 * C;
   hsm_tc_pack_kernel<<<cdiv(total, 256), 256, 0, st>>>(wp, wd, wpack, C);
   KMU_LAUNCH_CHECK("hsm_tc_pack");
   switch (C) {
-    case 16: return launch<16>(x, wpack, P, B, H, st);
-    case 32: return launch<32>(x, wpack, P, B, H, st);
-    case 64: return launch<64>(x, wpack, P, B, H, st);
+    case 16: return launch<16>(x, wpack, P, B, H, slices, st);
+    case 32: return launch<32>(x, wpack, P, B, H, slices, st);
+    case 64: return launch<64>(x, wpack, P, B, H, slices, st);
   }
   set_error("hsm_proj_tc: unsupported C=%d", C);
   return KMU_ERR_UNSUPPORTED;

@@ -205,11 +205,16 @@ constexpr int WG_A = 16 * PLANE;  // dP planes of one 128-row half (46080 B)
 // grid (persistent CTAs, 2 halves of n, C / NCW): the CTA keeps dWfull[half rows][9 taps][NCW channels] in TMEM (9 * NCW columns)
 // over all its tiles and writes it once: partial[cta][half][cz][128][9 * NCW].  Rows 64..127 of half 1 do not exist (n < 192):
 // their A planes stay zero and their accumulator rows are never read back.
+//
+// per_batch != 0 turns the same pipeline into the per-image correlation G[b][c'][tap][c] = sum_p dy[b, c', p] x[b, c, p + tap - 1]
+// (A = dy planes, a_planes_per_b = C / 8 of them per image in ONE box; grid (CTAs per image, 1, Z * B); rows >= C are not
+// written): d(ho)[b] = G[b] . W_Cm replaces the backward's sweep over the materialised Cm slice (hsm_dho_kernel below).
 template <int NCW>
 __global__ void __launch_bounds__(NTHREADS, 1) hsm_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dp,
                                                                    const __grid_constant__ CUtensorMap map_x,
                                                                    float* __restrict__ partial, int C, int tiles_x, int tiles_per_img,
-                                                                   int ntiles) {
+                                                                   int ntiles, int per_batch, int a_planes_per_b, int a_box_planes,
+                                                                   int Z) {
   constexpr int XB = (NCW / 8) * PLANE;          // x planes of one tile
   constexpr int STAGE = WG_A + XB;
   constexpr int NCOL = 9 * NCW;
@@ -221,7 +226,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) hsm_wgrad_tc_kernel(const __grid_
   uint64_t* acc_full = bars + 2 * WG_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WG_STAGES + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int half = blockIdx.y, cz = blockIdx.z;
+  const int half = blockIdx.y, cz = blockIdx.z % Z;
+  // tile range of this CTA: every tile of the batch, or the tiles of image blockIdx.z / Z
+  const int tile_begin = per_batch ? (int)(blockIdx.z / Z) * tiles_per_img + (int)blockIdx.x : (int)blockIdx.x;
+  const int tile_end = per_batch ? (int)(blockIdx.z / Z + 1) * tiles_per_img : ntiles;
 
   for (int i = tid; i < WG_STAGES * STAGE / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (tid == 0) {
@@ -244,18 +252,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) hsm_wgrad_tc_kernel(const __grid_
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (lane == 0) {
-      const int nbox = half == 0 ? 2 : 1;
+      const int nbox = per_batch ? 1 : (half == 0 ? 2 : 1);
+      const int box_bytes = a_box_planes * PLANE;
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      for (int tile = tile_begin; tile < tile_end; tile += gridDim.x, ++it) {
         const int b = tile / tiles_per_img, tr = tile - b * tiles_per_img;
         const int ty0 = (tr / tiles_x) * 16, tx0 = (tr % tiles_x) * 8;
         const uint32_t s = it % WG_STAGES;
         mbar_wait(smem_u32(&empty[s]), ((it / WG_STAGES) & 1u) ^ 1u);
         const uint32_t bar = smem_u32(&full[s]);
-        mbar_expect_tx(bar, (uint32_t)(nbox * BOX_BYTES + XB));
+        mbar_expect_tx(bar, (uint32_t)(nbox * box_bytes + XB));
         const uint32_t dst = smem_u32(smem + (size_t)s * STAGE);
         for (int k = 0; k < nbox; ++k)
-          tma_load_3d(dst + (uint32_t)(k * BOX_BYTES), &map_dp, (tx0 - 1) * 8, ty0 - 1, b * 24 + half * 16 + k * BOXP, bar);
+          tma_load_3d(dst + (uint32_t)(k * box_bytes), &map_dp, (tx0 - 1) * 8, ty0 - 1, b * a_planes_per_b + half * 16 + k * a_box_planes, bar);
         tma_load_3d(dst + (uint32_t)WG_A, &map_x, (tx0 - 1) * 8, ty0 - 1, b * (C / 8) + cz * (NCW / 8), bar);
       }
     }
@@ -264,7 +273,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) hsm_wgrad_tc_kernel(const __grid_
     if (lane == 0) {
       constexpr uint32_t IDESC = make_idesc_bf16_mn(128, NCW);
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      for (int tile = tile_begin; tile < tile_end; tile += gridDim.x, ++it) {
         const uint32_t s = it % WG_STAGES;
         mbar_wait_hot(smem_u32(&full[s]), (it / WG_STAGES) & 1u);
         tc_fence_after();
@@ -291,8 +300,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) hsm_wgrad_tc_kernel(const __grid_
     mbar_wait(smem_u32(acc_full), 0);
     tc_fence_after();
     const int m = q * 32 + lane;
-    float* pp = partial + ((((size_t)blockIdx.x * 2 + half) * gridDim.z + cz) * 128 + m) * NCOL;
-    const bool real = half == 0 || m < 64;
+    float* pp = partial + ((((size_t)blockIdx.x * gridDim.y + half) * gridDim.z + blockIdx.z) * 128 + m) * NCOL;
+    const bool real = per_batch ? (m < a_planes_per_b * 8) : (half == 0 || m < 64);
 #pragma unroll 1
     for (int c0 = 0; c0 < NCOL; c0 += 16) {
       uint32_t v[16];
@@ -409,26 +418,116 @@ static int wgrad_ctas(int B, int C, int H) {
   return (int)(ntiles < g ? ntiles : g);
 }
 
+// wt[tap][c][m] = wd[64 + m, tap] * Wp[64 + m, c]: the Cm rows of the merged convolution, state index m fastest (coalesced reads)
+__global__ void hsm_wt_kernel(const float* __restrict__ wp, const float* __restrict__ wd, float* __restrict__ wt, int C) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 9 * C * 64) return;
+  const int m = idx & 63, c = (idx >> 6) % C, t = idx / (64 * C);
+  wt[idx] = wd[(64 + m) * 9 + t] * wp[(size_t)(64 + m) * C + c];
+}
+
+// d(ho)[b][c'][m] = sum_{tap, c} G[b][c'][tap][c] * wt[tap][c][m],  G = fixed-order sum of the CTAs' partials.
+// CTA = (b, c'): the G row is reduced into shared memory once, thread m contracts it with column m of wt.
+__global__ void __launch_bounds__(64) hsm_dho_kernel(const float* __restrict__ gpart, const float* __restrict__ wt,
+                                                     float* __restrict__ dho, int B, int C, int nct, int Z, int NCW) {
+  extern __shared__ float g_s[];  // [9][C]
+  const int b = blockIdx.x / C, cp = blockIdx.x - b * C, m = threadIdx.x;
+  const size_t ncol = (size_t)9 * NCW;
+  for (int j = m; j < 9 * C; j += 64) {
+    const int t = j / C, c = j - t * C;
+    const int cz = c / NCW, cc = c - cz * NCW;
+    float g = 0.f;
+    for (int k = 0; k < nct; ++k) g += gpart[((((size_t)k * B + b) * Z + cz) * 128 + cp) * ncol + (size_t)t * NCW + cc];
+    g_s[j] = g;
+  }
+  __syncthreads();
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  const int n = 9 * C;   // multiple of 4
+  for (int j = 0; j < n; j += 4) {
+    s0 = fmaf(g_s[j], __ldg(wt + (size_t)j * 64 + m), s0);
+    s1 = fmaf(g_s[j + 1], __ldg(wt + (size_t)(j + 1) * 64 + m), s1);
+    s2 = fmaf(g_s[j + 2], __ldg(wt + (size_t)(j + 2) * 64 + m), s2);
+    s3 = fmaf(g_s[j + 3], __ldg(wt + (size_t)(j + 3) * 64 + m), s3);
+  }
+  dho[((size_t)b * C + cp) * 64 + m] = (s0 + s1) + (s2 + s3);
+}
+
+static int corr_ctas(int B, int C, int H) {
+  const int Z = C / wgrad_ncw(C);
+  int per = 148 / (B * Z);
+  if (per < 1) per = 1;
+  const int tiles = cdiv(H, 8) * cdiv(H, 16);
+  return per < tiles ? per : tiles;
+}
+
 size_t dpp_bytes(int B, int L) { return align_up((size_t)B * 24 * L * 16, 256); }
 
-struct Ws { size_t xp, w2, partial, dwfull, total; };
+struct Ws { size_t xp, dyp, w2, partial, dwfull, total; };
 static Ws ws_layout(int B, int C, int H) {
   Ws w;
   size_t o = 0;
   const int L = H * H;
   w.xp = o; o += align_up((size_t)B * (C / 8) * L * 16, 256);
+  w.dyp = o; o += align_up((size_t)B * (C / 8) * L * 16, 256);
   w.w2 = o; o += align_up((size_t)9 * 192 * C * 2, 256);
   const int NCW = wgrad_ncw(C), Z = C / NCW;
-  w.partial = o; o += align_up((size_t)wgrad_ctas(B, C, H) * 2 * Z * 128 * 9 * NCW * 4, 256);
+  size_t part = (size_t)wgrad_ctas(B, C, H) * 2 * Z * 128 * 9 * NCW * 4;
+  const size_t gpart = (size_t)corr_ctas(B, C, H) * B * Z * 128 * 9 * NCW * 4;    // the correlation runs first, same buffer
+  if (gpart > part) part = gpart;
+  w.partial = o; o += align_up(part, 256);
   w.dwfull = o; o += align_up((size_t)192 * 9 * C * 4, 256);
   w.total = o;
   return w;
 }
 size_t workspace_bytes(int B, int C, int H) { return ws_layout(B, C, H).total; }
 
+// part_dho[b][c'][m] = sum_p dy[b, c', p] Cm[b, m, p] without Cm: correlation of dy and x on tensor cores, then . W_Cm.
+// Also leaves x packed (xp) in the workspace for backward().
+int contract(const float* x, const float* dy, const float* wp, const float* wd, float* dho, int B, int C, int H, void* workspace,
+             cudaStream_t st) {
+  KMU_REQUIRE(C == 16 || C == 32 || C == 64, KMU_ERR_UNSUPPORTED, "hsm_tc_bwd: unsupported C=%d", C);
+  const int L = H * H;
+  const Ws wl = ws_layout(B, C, H);
+  char* ws = (char*)workspace;
+  uint4* xp = (uint4*)(ws + wl.xp);
+  uint4* dyp = (uint4*)(ws + wl.dyp);
+  float* gpart = (float*)(ws + wl.partial);
+  const int tiles_x = cdiv(H, 8), tiles_per_img = tiles_x * cdiv(H, 16), ntiles = B * tiles_per_img;
+  const int NCW = wgrad_ncw(C), Z = C / NCW;
+  CUtensorMap map_dy, map_x;
+  int rc = make_plane_map(&map_dy, dyp, (long long)B * (C / 8), H, C / 8);
+  if (rc != KMU_OK) return rc;
+  rc = make_plane_map(&map_x, xp, (long long)B * (C / 8), H, NCW / 8);
+  if (rc != KMU_OK) return rc;
+  const long long total = (long long)B * (C / 8) * L;
+  hsm_xpack_kernel<<<(unsigned)cdiv(total, 256), 256, 0, st>>>(x, xp, C, L, total);
+  KMU_LAUNCH_CHECK("hsm_xpack");
+  hsm_xpack_kernel<<<(unsigned)cdiv(total, 256), 256, 0, st>>>(dy, dyp, C, L, total);
+  KMU_LAUNCH_CHECK("hsm_xpack(dy)");
+  const int nct = corr_ctas(B, C, H);
+  const size_t smem = (size_t)WG_STAGES * (WG_A + (NCW / 8) * PLANE) + 128;
+  cudaError_t e;
+  if (NCW == 16) {
+    e = cudaFuncSetAttribute(hsm_wgrad_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    KMU_REQUIRE(e == cudaSuccess, KMU_ERR_LAUNCH, "hsm_corr_tc: cannot opt in to %zu B shared memory: %s", smem, cudaGetErrorString(e));
+    hsm_wgrad_tc_kernel<16><<<dim3(nct, 1, Z * B), NTHREADS, smem, st>>>(map_dy, map_x, gpart, C, tiles_x, tiles_per_img, ntiles, 1, C / 8, C / 8, Z);
+  } else {
+    e = cudaFuncSetAttribute(hsm_wgrad_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    KMU_REQUIRE(e == cudaSuccess, KMU_ERR_LAUNCH, "hsm_corr_tc: cannot opt in to %zu B shared memory: %s", smem, cudaGetErrorString(e));
+    hsm_wgrad_tc_kernel<32><<<dim3(nct, 1, Z * B), NTHREADS, smem, st>>>(map_dy, map_x, gpart, C, tiles_x, tiles_per_img, ntiles, 1, C / 8, C / 8, Z);
+  }
+  KMU_LAUNCH_CHECK("hsm_corr_tc");
+  float* wt = (float*)(ws + wl.dwfull);   // 9 * C * 64 floats: fits the (later) dWfull buffer of 192 * 9 * C floats
+  hsm_wt_kernel<<<cdiv(9 * C * 64, 256), 256, 0, st>>>(wp, wd, wt, C);
+  KMU_LAUNCH_CHECK("hsm_wt");
+  hsm_dho_kernel<<<B * C, 64, 9 * C * sizeof(float), st>>>(gpart, wt, dho, B, C, nct, Z, NCW);
+  KMU_LAUNCH_CHECK("hsm_dho");
+  return KMU_OK;
+}
+
 // dx += dgrad(dPp) ; dWp, dWd = chain(wgrad(dPp, x)).  dPp = bf16 planes written by hsm_dp; workspace >= workspace_bytes().
 int backward(const float* x, const float* wp, const float* wd, const void* dPp, float* dx, float* dwp, float* dwd, int B, int C, int H,
-             void* workspace, cudaStream_t st) {
+             void* workspace, int x_packed, cudaStream_t st) {
   KMU_REQUIRE(C == 16 || C == 32 || C == 64, KMU_ERR_UNSUPPORTED, "hsm_tc_bwd: unsupported C=%d", C);
   const int L = H * H;
   const Ws wl = ws_layout(B, C, H);
@@ -448,8 +547,10 @@ int backward(const float* x, const float* wp, const float* wd, const void* dPp, 
 
   {
     const long long total = (long long)B * (C / 8) * L;
-    hsm_xpack_kernel<<<(unsigned)cdiv(total, 256), 256, 0, st>>>(x, xp, C, L, total);
-    KMU_LAUNCH_CHECK("hsm_xpack");
+    if (!x_packed) {
+      hsm_xpack_kernel<<<(unsigned)cdiv(total, 256), 256, 0, st>>>(x, xp, C, L, total);
+      KMU_LAUNCH_CHECK("hsm_xpack");
+    }
     hsm_w2pack_kernel<<<cdiv(9 * 192 * C, 256), 256, 0, st>>>(wp, wd, w2, C);
     KMU_LAUNCH_CHECK("hsm_w2pack");
   }
@@ -470,11 +571,11 @@ int backward(const float* x, const float* wp, const float* wd, const void* dPp, 
     if (NCW == 16) {
       e = cudaFuncSetAttribute(hsm_wgrad_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       KMU_REQUIRE(e == cudaSuccess, KMU_ERR_LAUNCH, "hsm_wgrad_tc: cannot opt in to %zu B shared memory: %s", smem, cudaGetErrorString(e));
-      hsm_wgrad_tc_kernel<16><<<dim3(ctas, 2, Z), NTHREADS, smem, st>>>(map_dp, map_x, partial, C, tiles_x, tiles_per_img, ntiles);
+      hsm_wgrad_tc_kernel<16><<<dim3(ctas, 2, Z), NTHREADS, smem, st>>>(map_dp, map_x, partial, C, tiles_x, tiles_per_img, ntiles, 0, 24, BOXP, Z);
     } else {
       e = cudaFuncSetAttribute(hsm_wgrad_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       KMU_REQUIRE(e == cudaSuccess, KMU_ERR_LAUNCH, "hsm_wgrad_tc: cannot opt in to %zu B shared memory: %s", smem, cudaGetErrorString(e));
-      hsm_wgrad_tc_kernel<32><<<dim3(ctas, 2, Z), NTHREADS, smem, st>>>(map_dp, map_x, partial, C, tiles_x, tiles_per_img, ntiles);
+      hsm_wgrad_tc_kernel<32><<<dim3(ctas, 2, Z), NTHREADS, smem, st>>>(map_dp, map_x, partial, C, tiles_x, tiles_per_img, ntiles, 0, 24, BOXP, Z);
     }
     KMU_LAUNCH_CHECK("hsm_wgrad_tc");
     hsm_wgrad_tc_reduce_kernel<<<cdiv(192 * 9 * C, 32), 256, 0, st>>>(partial, ctas, Z, NCW, C, dwfull);

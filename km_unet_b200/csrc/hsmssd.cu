@@ -26,13 +26,19 @@ namespace hsm {
 
 namespace tc {  // hsm_tc.cu: tcgen05 path of the projection
 size_t pack_bytes(int C);
-int project(const float* x, const float* wp, const float* wd, float* P, int B, int C, int H, void* workspace, cudaStream_t st);
+size_t weff_bytes(int B, int C);
+int project(const float* x, const float* wp, const float* wd, float* P, int B, int C, int H, int slices, void* workspace,
+            cudaStream_t st);
+int out(const float* x, const float* ho, const float* wp, const float* wd, float* y, int B, int C, int H, void* workspace,
+        cudaStream_t st);
 }  // namespace tc
 namespace tcb {  // hsm_tc_bwd.cu: tcgen05 / TMA path of the projection backward
 size_t dpp_bytes(int B, int L);
 size_t workspace_bytes(int B, int C, int H);
+int contract(const float* x, const float* dy, const float* wp, const float* wd, float* dho, int B, int C, int H, void* workspace,
+             cudaStream_t st);
 int backward(const float* x, const float* wp, const float* wd, const void* dPp, float* dx, float* dwp, float* dwd, int B, int C, int H,
-             void* workspace, cudaStream_t st);
+             void* workspace, int x_packed, cudaStream_t st);
 }  // namespace tcb
 
 constexpr int N = 64;         // states
@@ -893,11 +899,12 @@ static int check(const kmu_hsmssd_desc* d, const char* who) {
   return KMU_OK;
 }
 
-struct FwdWs { size_t part_m, part_s, part_hs, wpack, total; };
+struct FwdWs { size_t part_m, part_s, part_hs, wpack, weff, total; };
 static FwdWs fwd_ws(const Dims& d) {
   FwdWs w;
   size_t o = 0;
   w.wpack = o; o += tc::pack_bytes(d.C);
+  w.weff = o; o += tc::weff_bytes(d.B, d.C);
   w.part_m = o; o += align_up((size_t)d.B * d.T * 64 * 4, 256);
   w.part_s = o; o += align_up((size_t)d.B * d.T * 64 * 4, 256);
   w.part_hs = o; o += align_up((size_t)d.B * d.T * d.C * 64 * 4, 256);
@@ -961,7 +968,8 @@ int kmu_hsmssd_fwd(const kmu_hsmssd_fwd_args* a, kmu_stream stream) {
   float* part_s = (float*)(ws + w.part_s);
   float* part_hs = (float*)(ws + w.part_hs);
   if (a->d.precision == KMU_PREC_BF16) {
-    int rc = tc::project(a->x, a->w_bcdt, a->w_dw, a->P, d.B, d.C, d.H, ws + w.wpack, st);
+    // Bm and dt slices only: y = ho Cm is folded into one more convolution of x (tc::out), d(ho) into a correlation (tcb::contract)
+    int rc = tc::project(a->x, a->w_bcdt, a->w_dw, a->P, d.B, d.C, d.H, 2, ws + w.wpack, st);
     if (rc != KMU_OK) return rc;
   } else
   {
@@ -1003,7 +1011,10 @@ int kmu_hsmssd_fwd(const kmu_hsmssd_fwd_args* a, kmu_stream stream) {
                                                     a->h, d);
     KMU_LAUNCH_CHECK("hsm_combine_gate");
   }
-  {
+  if (a->d.precision == KMU_PREC_BF16) {
+    int rc = tc::out(a->x, a->h, a->w_bcdt, a->w_dw, a->y, d.B, d.C, d.H, ws + w.weff, st);
+    if (rc != KMU_OK) return rc;
+  } else {
     size_t smem = (size_t)d.C * 64 * 4;
     hsm_out_kernel<<<dim3(cdiv(d.L, 256), d.B), 256, smem, st>>>(a->h, a->P, a->y, d);
     KMU_LAUNCH_CHECK("hsm_out");
@@ -1033,7 +1044,12 @@ int kmu_hsmssd_bwd(const kmu_hsmssd_bwd_args* a, kmu_stream stream) {
   float* dP = (float*)(ws + w.dP);
   float* tpart = (float*)(ws + w.tpart);
   const int C = d.C;
-  {
+  Dims dg = d;                    // gate backward: number of d(ho) partials per batch element
+  if (tcbwd) {
+    int rc = tcb::contract(a->x, a->dy, a->w_bcdt, a->w_dw, part_dho, d.B, C, d.H, tpart, st);
+    if (rc != KMU_OK) return rc;
+    dg.T = 1;
+  } else {
     size_t smem = ((size_t)SUB * 65 + (size_t)C * SUB) * 4;
     dim3 grid(d.T, d.B);
     if (C <= 16) {
@@ -1051,7 +1067,7 @@ int kmu_hsmssd_bwd(const kmu_hsmssd_bwd_args* a, kmu_stream stream) {
   {
     size_t smem = ((size_t)5 * C * 64 + (size_t)3 * C * C + GT) * 4;
     opt_in_smem(hsm_gate_bwd_kernel, smem);
-    hsm_gate_bwd_kernel<<<d.B, GT, smem, st>>>(part_dho, a->dh, a->hs, a->hz, a->w_hz, a->w_out, a->D, dhs, r, wpart, d);
+    hsm_gate_bwd_kernel<<<d.B, GT, smem, st>>>(part_dho, a->dh, a->hs, a->hz, a->w_hz, a->w_out, a->D, dhs, r, wpart, dg);
     KMU_LAUNCH_CHECK("hsm_gate_bwd");
     int n = 3 * C * C + 1;
     hsm_wgrad_reduce_kernel<<<cdiv(n, 32), 256, 0, st>>>(wpart, d.B, n, a->d_w_out, C * C, a->d_w_hz, 2 * C * C, a->d_D, 1);
@@ -1079,7 +1095,7 @@ int kmu_hsmssd_bwd(const kmu_hsmssd_bwd_args* a, kmu_stream stream) {
     KMU_LAUNCH_CHECK("hsm_dp");
   }
   if (tcbwd) {
-    int rc = tcb::backward(a->x, a->w_bcdt, a->w_dw, dP, a->dx, a->d_w_bcdt, a->d_w_dw, d.B, C, d.H, tpart, st);
+    int rc = tcb::backward(a->x, a->w_bcdt, a->w_dw, dP, a->dx, a->d_w_bcdt, a->d_w_dw, d.B, C, d.H, tpart, 1, st);
     if (rc != KMU_OK) return rc;
   } else {
     size_t smem = ((size_t)BN * NHALO + 2 * (size_t)BN * QP + (size_t)C * QP + 2 * (size_t)C * BN + BN * 12) * 4;

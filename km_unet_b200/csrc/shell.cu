@@ -366,17 +366,24 @@ __global__ void __launch_bounds__(256) dw3x3_wgrad_kernel(const float* __restric
   }
 }
 
-// dw[c][t] = sum over b and row slices; thread = (c, t)
+// dw[c][t] = sum over b and row slices; warp = (c, t), lanes stride over the B * RS partials, fixed-order tree (deterministic)
 __global__ void __launch_bounds__(128) dw3x3_wreduce_kernel(const float* __restrict__ part, int B, int C, int RS,
                                                             float* __restrict__ dw, float* __restrict__ dbias) {
-  int idx = blockIdx.x * 128 + threadIdx.x;
+  const int idx = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (idx >= C * 10) return;
   const int c = idx / 10, t = idx - c * 10;
   double s = 0.0;
-  for (int b = 0; b < B; ++b)
-    for (int r = 0; r < RS; ++r) s += (double)part[(((size_t)b * C + c) * RS + r) * 10 + t];
-  if (t < 9) dw[c * 9 + t] = (float)s;
-  else if (dbias) dbias[c] = (float)s;
+  const int n = B * RS;
+  for (int i = lane; i < n; i += 32) {
+    const int b = i / RS, r = i - b * RS;
+    s += (double)part[(((size_t)b * C + c) * RS + r) * 10 + t];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    if (t < 9) dw[c * 9 + t] = (float)s;
+    else if (dbias) dbias[c] = (float)s;
+  }
 }
 
 static int dw_check(const kmu_dwconv3x3_desc* d, const char* who) {
@@ -502,7 +509,7 @@ int kmu_dwconv3x3_bwd(const kmu_dwconv3x3_desc* dd, const float* x, const float*
     const int rs2 = cdiv(d.H, rows);
     dw3x3_wgrad_kernel<<<dim3(rs2, d.B * d.C), 256, 0, st>>>(x, dy, (float*)workspace, d, rows);
     KMU_LAUNCH_CHECK("dw3x3_wgrad");
-    dw3x3_wreduce_kernel<<<cdiv(d.C * 10, 128), 128, 0, st>>>((const float*)workspace, d.B, d.C, rs2, dw, dbias);
+    dw3x3_wreduce_kernel<<<cdiv(d.C * 10, 4), 128, 0, st>>>((const float*)workspace, d.B, d.C, rs2, dw, dbias);
     KMU_LAUNCH_CHECK("dw3x3_wreduce");
   }
   return KMU_OK;
