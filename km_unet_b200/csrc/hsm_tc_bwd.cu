@@ -199,8 +199,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) hsm_dgrad_tc_kernel(const __grid_
 }
 
 // ------------------------------------------------------------------------------------------------ wgrad
-constexpr int WG_STAGES = 3;
-constexpr int WG_A = 16 * PLANE;  // dP planes of one 128-row half (46080 B)
+// One tcgen05.mma of M = 128 takes ~45-64 cycles whatever N <= 128 is (tools/probes/mma_align_probe.cu), so nine N = 16 MMAs per K
+// step (one per tap, the tap being a start offset into ONE halo tile of x) cost nine times the tensor-pipe time of a single
+// N = 144 MMA.  The taps are therefore moved into the N dimension: the TMA unit builds the im2col image of x itself -- nine boxes
+// of the same [NCW/8 planes][16 rows][8 pixels] shape, each shifted by its tap (out-of-image parts zero-filled) -- which lands as
+// [tap][channel group][128 pixels][16 B], i.e. an MN-major B operand with N = 9 * NCW whose groups sit at one uniform stride.
+constexpr int WPLANE = 128 * 16;     // one 8-channel plane of a 16 x 8 pixel tile WITHOUT halo (2048 B)
+constexpr int WG_A = 16 * WPLANE;    // dP planes of one 128-row half (32768 B)
 
 // grid (persistent CTAs, 2 halves of n, C / NCW): the CTA keeps dWfull[half rows][9 taps][NCW channels] in TMEM (9 * NCW columns)
 // over all its tiles and writes it once: partial[cta][half][cz][128][9 * NCW].  Rows 64..127 of half 1 do not exist (n < 192):
@@ -215,25 +220,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) hsm_wgrad_tc_kernel(const __grid_
                                                                    float* __restrict__ partial, int C, int tiles_x, int tiles_per_img,
                                                                    int ntiles, int per_batch, int a_planes_per_b, int a_box_planes,
                                                                    int Z) {
-  constexpr int XB = (NCW / 8) * PLANE;          // x planes of one tile
+  constexpr int XT = (NCW / 8) * WPLANE;         // x planes of one tap
+  constexpr int XB = 9 * XT;                     // im2col image of x for one tile
   constexpr int STAGE = WG_A + XB;
+  constexpr int STAGES = NCW == 16 ? 3 : 2;
   constexpr int NCOL = 9 * NCW;
   constexpr int TCOLS = NCOL <= 256 ? 256 : 512;
   extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)WG_STAGES * STAGE);
-  uint64_t* full = bars;                  // [WG_STAGES]
-  uint64_t* empty = bars + WG_STAGES;     // [WG_STAGES]
-  uint64_t* acc_full = bars + 2 * WG_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WG_STAGES + 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE);
+  uint64_t* full = bars;                  // [STAGES]
+  uint64_t* empty = bars + STAGES;        // [STAGES]
+  uint64_t* acc_full = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int half = blockIdx.y, cz = blockIdx.z % Z;
   // tile range of this CTA: every tile of the batch, or the tiles of image blockIdx.z / Z
   const int tile_begin = per_batch ? (int)(blockIdx.z / Z) * tiles_per_img + (int)blockIdx.x : (int)blockIdx.x;
   const int tile_end = per_batch ? (int)(blockIdx.z / Z + 1) * tiles_per_img : ntiles;
 
-  for (int i = tid; i < WG_STAGES * STAGE / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < STAGES * STAGE / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (tid == 0) {
-    for (int i = 0; i < WG_STAGES; ++i) {
+    for (int i = 0; i < STAGES; ++i) {
       mbar_init(smem_u32(&full[i]), 1);
       mbar_init(smem_u32(&empty[i]), 1);
     }
@@ -253,41 +260,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) hsm_wgrad_tc_kernel(const __grid_
     // ===================================================================== TMA producer
     if (lane == 0) {
       const int nbox = per_batch ? 1 : (half == 0 ? 2 : 1);
-      const int box_bytes = a_box_planes * PLANE;
+      const int box_bytes = a_box_planes * WPLANE;
       uint32_t it = 0;
       for (int tile = tile_begin; tile < tile_end; tile += gridDim.x, ++it) {
         const int b = tile / tiles_per_img, tr = tile - b * tiles_per_img;
         const int ty0 = (tr / tiles_x) * 16, tx0 = (tr % tiles_x) * 8;
-        const uint32_t s = it % WG_STAGES;
-        mbar_wait(smem_u32(&empty[s]), ((it / WG_STAGES) & 1u) ^ 1u);
+        const uint32_t s = it % STAGES;
+        mbar_wait(smem_u32(&empty[s]), ((it / STAGES) & 1u) ^ 1u);
         const uint32_t bar = smem_u32(&full[s]);
         mbar_expect_tx(bar, (uint32_t)(nbox * box_bytes + XB));
         const uint32_t dst = smem_u32(smem + (size_t)s * STAGE);
         for (int k = 0; k < nbox; ++k)
-          tma_load_3d(dst + (uint32_t)(k * box_bytes), &map_dp, (tx0 - 1) * 8, ty0 - 1, b * a_planes_per_b + half * 16 + k * a_box_planes, bar);
-        tma_load_3d(dst + (uint32_t)WG_A, &map_x, (tx0 - 1) * 8, ty0 - 1, b * (C / 8) + cz * (NCW / 8), bar);
+          tma_load_3d(dst + (uint32_t)(k * box_bytes), &map_dp, tx0 * 8, ty0, b * a_planes_per_b + half * 16 + k * a_box_planes, bar);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int ki = t / 3, kj = t - ki * 3;
+          tma_load_3d(dst + (uint32_t)(WG_A + t * XT), &map_x, (tx0 + kj - 1) * 8, ty0 + ki - 1, b * (C / 8) + cz * (NCW / 8), bar);
+        }
       }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t IDESC = make_idesc_bf16_mn(128, NCW);
       uint32_t it = 0;
       for (int tile = tile_begin; tile < tile_end; tile += gridDim.x, ++it) {
-        const uint32_t s = it % WG_STAGES;
-        mbar_wait_hot(smem_u32(&full[s]), (it / WG_STAGES) & 1u);
+        const uint32_t s = it % STAGES;
+        mbar_wait_hot(smem_u32(&full[s]), (it / STAGES) & 1u);
         tc_fence_after();
-        // MN-major: LBO = byte step between the two 8-pixel K groups (next tile row), SBO = byte step between 8-channel groups
-        const uint64_t adesc0 = make_smem_desc(smem_u32(smem + (size_t)s * STAGE), PITCH * 16, PLANE);
+        // MN-major: LBO = byte step between the two 8-pixel K groups (next tile row, 128 B), SBO = byte step between 8-channel groups
+        const uint64_t adesc0 = make_smem_desc(smem_u32(smem + (size_t)s * STAGE), 128, WPLANE);
         const uint64_t bdesc0 = desc_advance(adesc0, (uint32_t)WG_A);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {  // K step = two tile rows of 8 pixels
-          const uint64_t adesc = desc_advance(adesc0, (uint32_t)(((1 + 2 * ks) * PITCH + 1) * 16));
-#pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            const int ki = t / 3, kj = t - ki * 3;
-            const uint64_t bdesc = desc_advance(bdesc0, (uint32_t)(((2 * ks + ki) * PITCH + kj) * 16));
-            umma_bf16(tmem_base + (uint32_t)(t * NCW), adesc, bdesc, IDESC, (it > 0 || ks > 0) ? 1u : 0u);
+          const uint64_t adesc = desc_advance(adesc0, (uint32_t)(ks * 256));
+          const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+          if (NCW == 16) {
+            umma_bf16(tmem_base, adesc, desc_advance(bdesc0, (uint32_t)(ks * 256)), make_idesc_bf16_mn(128, 144), acc);
+          } else {  // N = 288 > 256: taps 0..3 (128 columns) and 4..8 (160 columns)
+            umma_bf16(tmem_base, adesc, desc_advance(bdesc0, (uint32_t)(ks * 256)), make_idesc_bf16_mn(128, 128), acc);
+            umma_bf16(tmem_base + 128u, adesc, desc_advance(bdesc0, (uint32_t)(4 * XT + ks * 256)), make_idesc_bf16_mn(128, 160), acc);
           }
         }
         umma_commit(smem_u32(&empty[s]));
@@ -322,6 +333,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) hsm_wgrad_tc_kernel(const __grid_
     tmem_dealloc(tmem_base, TCOLS);
   }
 }
+
+static size_t wgrad_smem(int NCW) { return (size_t)(NCW == 16 ? 3 : 2) * (WG_A + 9 * (NCW / 8) * WPLANE) + 128; }
 
 // dWfull[n][tap][c] = sum over CTAs, fixed order.  CTA = 32 outputs x 8 interleaved slices of the CTA list.
 __global__ void __launch_bounds__(256) hsm_wgrad_tc_reduce_kernel(const float* __restrict__ partial, int nctas, int Z, int NCW, int C,
@@ -387,13 +400,13 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// bf16 planes [planes][H][H * 8 elements], box = [box_planes][18 rows][80 elements]
-static int make_plane_map(CUtensorMap* m, const void* base, long long planes, int H, int box_planes) {
+// bf16 planes [planes][H][H * 8 elements], box = [box_planes][18 rows][10 pixels] (tile + halo) or [box_planes][16 rows][8 pixels]
+static int make_plane_map(CUtensorMap* m, const void* base, long long planes, int H, int box_planes, bool halo = true) {
   EncodeTiledFn fn = encode_fn();
   KMU_REQUIRE(fn != nullptr, KMU_ERR_LAUNCH, "hsm_tc_bwd: cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t dims[3] = {(cuuint64_t)H * 8, (cuuint64_t)H, (cuuint64_t)planes};
   cuuint64_t strides[2] = {(cuuint64_t)H * 16, (cuuint64_t)H * H * 16};
-  cuuint32_t box[3] = {(cuuint32_t)(PITCH * 8), (cuuint32_t)ROWS, (cuuint32_t)box_planes};
+  cuuint32_t box[3] = {(cuuint32_t)((halo ? PITCH : 8) * 8), (cuuint32_t)(halo ? ROWS : 16), (cuuint32_t)box_planes};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -495,9 +508,9 @@ int contract(const float* x, const float* dy, const float* wp, const float* wd, 
   const int tiles_x = cdiv(H, 8), tiles_per_img = tiles_x * cdiv(H, 16), ntiles = B * tiles_per_img;
   const int NCW = wgrad_ncw(C), Z = C / NCW;
   CUtensorMap map_dy, map_x;
-  int rc = make_plane_map(&map_dy, dyp, (long long)B * (C / 8), H, C / 8);
+  int rc = make_plane_map(&map_dy, dyp, (long long)B * (C / 8), H, C / 8, false);
   if (rc != KMU_OK) return rc;
-  rc = make_plane_map(&map_x, xp, (long long)B * (C / 8), H, NCW / 8);
+  rc = make_plane_map(&map_x, xp, (long long)B * (C / 8), H, NCW / 8, false);
   if (rc != KMU_OK) return rc;
   const long long total = (long long)B * (C / 8) * L;
   hsm_xpack_kernel<<<(unsigned)cdiv(total, 256), 256, 0, st>>>(x, xp, C, L, total);
@@ -505,7 +518,7 @@ int contract(const float* x, const float* dy, const float* wp, const float* wd, 
   hsm_xpack_kernel<<<(unsigned)cdiv(total, 256), 256, 0, st>>>(dy, dyp, C, L, total);
   KMU_LAUNCH_CHECK("hsm_xpack(dy)");
   const int nct = corr_ctas(B, C, H);
-  const size_t smem = (size_t)WG_STAGES * (WG_A + (NCW / 8) * PLANE) + 128;
+  const size_t smem = wgrad_smem(NCW);
   cudaError_t e;
   if (NCW == 16) {
     e = cudaFuncSetAttribute(hsm_wgrad_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -539,10 +552,12 @@ int backward(const float* x, const float* wp, const float* wd, const void* dPp, 
   const int tiles_x = cdiv(H, 8), tiles_per_img = tiles_x * cdiv(H, 16), ntiles = B * tiles_per_img;
   const int NCW = wgrad_ncw(C), Z = C / NCW;
 
-  CUtensorMap map_dp, map_x;
-  int rc = make_plane_map(&map_dp, dPp, (long long)B * 24, H, BOXP);
+  CUtensorMap map_dp, map_dpw, map_x;
+  int rc = make_plane_map(&map_dp, dPp, (long long)B * 24, H, BOXP);            // dgrad: tile + halo
   if (rc != KMU_OK) return rc;
-  rc = make_plane_map(&map_x, xp, (long long)B * (C / 8), H, NCW / 8);
+  rc = make_plane_map(&map_dpw, dPp, (long long)B * 24, H, BOXP, false);         // wgrad: the tile itself
+  if (rc != KMU_OK) return rc;
+  rc = make_plane_map(&map_x, xp, (long long)B * (C / 8), H, NCW / 8, false);    // wgrad: nine tap-shifted boxes of x
   if (rc != KMU_OK) return rc;
 
   {
@@ -566,16 +581,16 @@ int backward(const float* x, const float* wp, const float* wd, const void* dPp, 
   }
   {
     const int ctas = wgrad_ctas(B, C, H);
-    const size_t smem = (size_t)WG_STAGES * (WG_A + (NCW / 8) * PLANE) + 128;
+    const size_t smem = wgrad_smem(NCW);
     cudaError_t e;
     if (NCW == 16) {
       e = cudaFuncSetAttribute(hsm_wgrad_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       KMU_REQUIRE(e == cudaSuccess, KMU_ERR_LAUNCH, "hsm_wgrad_tc: cannot opt in to %zu B shared memory: %s", smem, cudaGetErrorString(e));
-      hsm_wgrad_tc_kernel<16><<<dim3(ctas, 2, Z), NTHREADS, smem, st>>>(map_dp, map_x, partial, C, tiles_x, tiles_per_img, ntiles, 0, 24, BOXP, Z);
+      hsm_wgrad_tc_kernel<16><<<dim3(ctas, 2, Z), NTHREADS, smem, st>>>(map_dpw, map_x, partial, C, tiles_x, tiles_per_img, ntiles, 0, 24, BOXP, Z);
     } else {
       e = cudaFuncSetAttribute(hsm_wgrad_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       KMU_REQUIRE(e == cudaSuccess, KMU_ERR_LAUNCH, "hsm_wgrad_tc: cannot opt in to %zu B shared memory: %s", smem, cudaGetErrorString(e));
-      hsm_wgrad_tc_kernel<32><<<dim3(ctas, 2, Z), NTHREADS, smem, st>>>(map_dp, map_x, partial, C, tiles_x, tiles_per_img, ntiles, 0, 24, BOXP, Z);
+      hsm_wgrad_tc_kernel<32><<<dim3(ctas, 2, Z), NTHREADS, smem, st>>>(map_dpw, map_x, partial, C, tiles_x, tiles_per_img, ntiles, 0, 24, BOXP, Z);
     }
     KMU_LAUNCH_CHECK("hsm_wgrad_tc");
     hsm_wgrad_tc_reduce_kernel<<<cdiv(192 * 9 * C, 32), 256, 0, st>>>(partial, ctas, Z, NCW, C, dwfull);
