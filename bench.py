@@ -131,6 +131,9 @@ def op_work(name, key):
     if name.startswith("kmu_dwconv3x3"):
         B, C, H, W = key                     # fwd: read x, write y; bwd: read dy (dx), read x and dy (dw), write dx
         return ("hbm", (8.0 if name.endswith("fwd") else 16.0) * B * C * H * W, "byte")
+    if name == "kmu_pwconv_tma_fwd":
+        B, Cin, Cout, HW = key
+        return ("hbm", 4.0 * (Cin + Cout) * B * HW, "byte")
     if name == "kmu_pwconv_fused_bwd":
         B, Cin, Cout, HW = key               # one kernel: read x and dy once, write dx
         return ("hbm", 4.0 * (2 * Cin + Cout) * B * HW, "byte")
@@ -402,6 +405,7 @@ def run_model(h, args):
     # pointwise convolutions: forward on the fp32 streaming kernels, backward as ONE fused TMA -> tcgen05 kernel (dx, dW, db from a
     # single pass over x and dy, pwconv_bwd_tc.cu) when the tensor-core precision class is selected
     K.config.conv_bwd = "fused" if args.precision == "bf16" else "split"
+    K.config.conv_fwd = "tma" if args.precision == "bf16" else "simt"
     torch.backends.cudnn.benchmark = True                 # as the reference's training script does (train_shanghai.py:331)
     _lib.lib()                                            # fail loudly if the extension is missing
     metric, desc, variant, classes, fin, size, default_b, train = WORKLOADS[args.workload]

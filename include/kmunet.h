@@ -467,6 +467,12 @@ int kmu_pwconv_tc_bwd(const kmu_pwconv_desc* d, const float* x, const float* dy,
  * 16 (Cin <= 240, Cout <= 256), HW >= 128 and a multiple of 4, x / dy 16-byte aligned and the tile ring fits shared memory
  * (kmu_pwconv_fused_bwd_supported); dx and dw are both required. */
 int kmu_pwconv_fused_bwd_supported(const kmu_pwconv_desc* d);
+/* Forward of the same convolution on the same pipeline (TMA fp32 box -> bf16 planes -> tcgen05 -> NCHW stores); same shape rules
+ * with Cin <= 256. */
+int kmu_pwconv_tma_fwd_supported(const kmu_pwconv_desc* d);
+size_t kmu_pwconv_tma_fwd_workspace_bytes(const kmu_pwconv_desc* d);
+int kmu_pwconv_tma_fwd(const kmu_pwconv_desc* d, const float* x, const float* w, const float* bias, float* y, void* workspace,
+                       size_t workspace_bytes, kmu_stream stream);
 size_t kmu_pwconv_fused_bwd_workspace_bytes(const kmu_pwconv_desc* d);
 int kmu_pwconv_fused_bwd(const kmu_pwconv_desc* d, const float* x, const float* dy, const float* w, float* dx, float* dw,
                          float* dbias, void* workspace, size_t workspace_bytes, kmu_stream stream);

@@ -179,6 +179,9 @@ SYMBOLS = {
     "kmu_pwconv_tc_workspace_bytes": (C.c_size_t, [C.POINTER(PwDesc)]),
     "kmu_pwconv_tc_fwd": (C.c_int, [C.POINTER(PwDesc), _f32p, _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kmu_pwconv_tc_bwd": (C.c_int, [C.POINTER(PwDesc), _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kmu_pwconv_tma_fwd_supported": (C.c_int, [C.POINTER(PwDesc)]),
+    "kmu_pwconv_tma_fwd_workspace_bytes": (C.c_size_t, [C.POINTER(PwDesc)]),
+    "kmu_pwconv_tma_fwd": (C.c_int, [C.POINTER(PwDesc), _f32p, _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kmu_pwconv_fused_bwd_supported": (C.c_int, [C.POINTER(PwDesc)]),
     "kmu_pwconv_fused_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(PwDesc)]),
     "kmu_pwconv_fused_bwd": (C.c_int, [C.POINTER(PwDesc), _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),

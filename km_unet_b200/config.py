@@ -12,6 +12,9 @@ conv_precision = os.environ.get("KMU_CONV_PRECISION", "fp32")
 # "fused" = one persistent TMA -> tcgen05 kernel that reads x and dy once and writes dx, dW, db (bf16 operands, 2e-2 gate) where
 # the shape allows, the split kernels otherwise
 conv_bwd = os.environ.get("KMU_CONV_BWD", "split")
+# forward of the pointwise convolutions: "simt" = fp32 streaming kernel (or the tcgen05 kernel of conv_precision = "bf16");
+# "tma" = persistent TMA -> tcgen05 pipeline (bf16 operands, 2e-2 gate) where the shape allows
+conv_fwd = os.environ.get("KMU_CONV_FWD", "simt")
 
 
 def precision_code(name=None):

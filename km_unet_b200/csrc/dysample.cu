@@ -89,29 +89,27 @@ __device__ __forceinline__ Coord make_coord(float rx, float ry, int W, int H) {
 }
 
 // ---------------------------------------------------------------------------------------------- sample (fwd)
-// thread = VEC consecutive output columns of one (b, offset group, output row): the sampling coordinates depend on the
-// group only, so they are computed ONCE and reused by the group's Cg channels (the first version recomputed them per
-// channel and was instruction-bound at 80 % issue utilisation); per channel: 4*VEC tap loads, VEC outputs, one 128-bit store.
+// thread = VEC consecutive output columns of one (b, channel, output row)
 template <int VEC>
-__global__ void __launch_bounds__(256, 2) dys_sample_fwd_kernel(const float* __restrict__ x, const float* __restrict__ offset,
+__global__ void __launch_bounds__(256) dys_sample_fwd_kernel(const float* __restrict__ x, const float* __restrict__ offset,
                                                              float* __restrict__ out, Dims d) {
   const int owv = d.OW / VEC;
   long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  long long total = (long long)d.B * d.G * d.OH * owv;
+  long long total = (long long)d.B * d.C * d.OH * owv;
   if (idx >= total) return;
   int ow0 = (int)(idx % owv) * VEC;
   long long t = idx / owv;
   int oh = (int)(t % d.OH);
   t /= d.OH;
-  int g = (int)(t % d.G);
-  int b = (int)(t / d.G);
+  int c = (int)(t % d.C);
+  int b = (int)(t / d.C);
+  int g = c / d.Cg;
   int h = oh / d.s, i = oh - h * d.s;
-  const long long HW = (long long)d.H * d.W, OHW = (long long)d.OH * d.OW;
+  const long long HW = (long long)d.H * d.W;
+  const float* xp = x + ((size_t)b * d.C + c) * HW;
   const float* offb = offset + (size_t)b * d.NOFF * HW + (size_t)h * d.W;
   const int ss = d.s * d.s;
-  int o00[VEC];                    // offset of the top-left tap inside a channel plane
-  float w00[VEC], w01[VEC], w10[VEC], w11[VEC];
-  int dxo[VEC], dyo[VEC];          // +1 column / +1 row step, 0 when that neighbour is outside (its weight is zeroed too)
+  float res[VEC];
 #pragma unroll
   for (int e = 0; e < VEC; ++e) {
     int ow = ow0 + e;
@@ -120,33 +118,20 @@ __global__ void __launch_bounds__(256, 2) dys_sample_fwd_kernel(const float* __r
     float ox = __ldg(offb + (size_t)ch * HW + w);
     float oy = __ldg(offb + (size_t)(d.G * ss + ch) * HW + w);
     Coord q = make_coord((float)w + ox, (float)h + oy, d.W, d.H);
-    o00[e] = q.y0 * d.W + q.x0;
-    dxo[e] = q.x1ok ? 1 : 0;
-    dyo[e] = q.y1ok ? d.W : 0;
-    const float wx1 = q.x1ok ? q.fx : 0.f, wy1 = q.y1ok ? q.fy : 0.f;
-    const float wx0 = 1.f - q.fx, wy0 = 1.f - q.fy;
-    w00[e] = wx0 * wy0;
-    w01[e] = wx1 * wy0;
-    w10[e] = wx0 * wy1;
-    w11[e] = wx1 * wy1;
+    const float* r0 = xp + (size_t)q.y0 * d.W + q.x0;
+    float v00 = __ldg(r0);
+    float v01 = q.x1ok ? __ldg(r0 + 1) : 0.f;
+    float v10 = q.y1ok ? __ldg(r0 + d.W) : 0.f;
+    float v11 = (q.x1ok && q.y1ok) ? __ldg(r0 + d.W + 1) : 0.f;
+    float wx1 = q.fx, wx0 = 1.f - q.fx, wy1 = q.fy, wy0 = 1.f - q.fy;
+    res[e] = v00 * (wx0 * wy0) + v01 * (wx1 * wy0) + v10 * (wx0 * wy1) + v11 * (wx1 * wy1);
   }
-  const float* xp = x + ((size_t)b * d.C + (size_t)g * d.Cg) * HW;
-  float* op = out + ((size_t)b * d.C + (size_t)g * d.Cg) * OHW + (size_t)oh * d.OW + ow0;
-#pragma unroll 2
-  for (int c = 0; c < d.Cg; ++c) {
-    const float* xc = xp + (size_t)c * HW;
-    float res[VEC];
+  float* op = out + (((size_t)b * d.C + c) * d.OH + oh) * d.OW + ow0;
+  if (VEC == 4) {
+    *reinterpret_cast<float4*>(op) = make_float4(res[0], res[1], res[2], res[3]);
+  } else {
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-      const float* r0 = xc + o00[e];
-      res[e] = __ldg(r0) * w00[e] + __ldg(r0 + dxo[e]) * w01[e] + __ldg(r0 + dyo[e]) * w10[e] + __ldg(r0 + dyo[e] + dxo[e]) * w11[e];
-    }
-    if (VEC == 4) {
-      *reinterpret_cast<float4*>(op + (size_t)c * OHW) = make_float4(res[0], res[1], res[2], res[3]);
-    } else {
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) op[(size_t)c * OHW + e] = res[e];
-    }
+    for (int e = 0; e < VEC; ++e) op[e] = res[e];
   }
 }
 
@@ -280,20 +265,33 @@ __global__ void __launch_bounds__(128) dys_offset_bwd_kernel(const float* __rest
   }
 }
 
-__global__ void dys_offset_bwd_reduce_kernel(const float* __restrict__ partial, int nblk, int npass, float* __restrict__ dw,
-                                             float* __restrict__ db, Dims d) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  int per = 32 * d.C + 32;
-  if (idx >= npass * per) return;
-  int pass = idx / per, e = idx - pass * per;
+// fixed-order sum of the per-block partials: CTA = 32 outputs x 8 interleaved slices of the block list
+__global__ void __launch_bounds__(256) dys_offset_bwd_reduce_kernel(const float* __restrict__ partial, int nblk, int npass,
+                                                                    float* __restrict__ dw, float* __restrict__ db, Dims d) {
+  __shared__ float red[8][33];
+  const int o = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 32 + o;
+  const int per = 32 * d.C + 32;
   float s = 0.f;
-  for (int k = 0; k < nblk; ++k) s += partial[((size_t)pass * nblk + k) * per + e];
-  if (e < 32 * d.C) {
-    int j = pass * 32 + e / d.C, c = e % d.C;
-    if (j < d.NOFF) dw[(size_t)j * d.C + c] = s;
-  } else {
-    int j = pass * 32 + (e - 32 * d.C);
-    if (j < d.NOFF) db[j] = s;
+  int pass = 0, e = 0;
+  if (idx < npass * per) {
+    pass = idx / per;
+    e = idx - pass * per;
+    for (int k = sl; k < nblk; k += 8) s += partial[((size_t)pass * nblk + k) * per + e];
+  }
+  red[sl][o] = s;
+  __syncthreads();
+  if (sl == 0 && idx < npass * per) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += red[q][o];
+    if (e < 32 * d.C) {
+      int j = pass * 32 + e / d.C, c = e % d.C;
+      if (j < d.NOFF) dw[(size_t)j * d.C + c] = t;
+    } else {
+      int j = pass * 32 + (e - 32 * d.C);
+      if (j < d.NOFF) db[j] = t;
+    }
   }
 }
 
@@ -313,12 +311,11 @@ static int check(const kmu_dysample_desc* d, const char* who) {
 }
 
 static int launch_sample_fwd(const Dims& d, const float* x, const float* offset, float* out, cudaStream_t st) {
-  // total below = threads: one per (b, group, output row, VEC output columns)
   if (d.OW % 4 == 0) {
-    long long total = (long long)d.B * d.G * d.OH * (d.OW / 4);
+    long long total = (long long)d.B * d.C * d.OH * (d.OW / 4);
     dys_sample_fwd_kernel<4><<<cdiv(total, 256), 256, 0, st>>>(x, offset, out, d);
   } else {
-    long long total = (long long)d.B * d.G * d.OH * d.OW;
+    long long total = (long long)d.B * d.C * d.OH * d.OW;
     dys_sample_fwd_kernel<1><<<cdiv(total, 256), 256, 0, st>>>(x, offset, out, d);
   }
   KMU_LAUNCH_CHECK("dys_sample_fwd");
@@ -409,7 +406,7 @@ int kmu_dysample_bwd(const kmu_dysample_bwd_args* a, kmu_stream stream) {
   dys_offset_bwd_kernel<<<dim3(nblk, npass), 128, smem, st>>>(a->x, a->w_offset, doff, a->dx, partial, d);
   KMU_LAUNCH_CHECK("dys_offset_bwd");
   int n = npass * (32 * d.C + 32);
-  dys_offset_bwd_reduce_kernel<<<cdiv(n, 128), 128, 0, st>>>(partial, nblk, npass, a->d_w_offset, a->d_b_offset, d);
+  dys_offset_bwd_reduce_kernel<<<cdiv(n, 32), 256, 0, st>>>(partial, nblk, npass, a->d_w_offset, a->d_b_offset, d);
   KMU_LAUNCH_CHECK("dys_offset_bwd_reduce");
   return KMU_OK;
 }

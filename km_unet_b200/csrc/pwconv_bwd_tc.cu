@@ -243,6 +243,148 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_bwd_fused_kernel(const __grid_
   }
 }
 
+// ------------------------------------------------------------------------------------------------ forward (same pipeline)
+// y[b, o, p] = bias[o] + sum_c W[o, c] x[b, c, p]: TMA box [Cin][128] fp32 -> converter warps -> bf16 planes -> Cin/16 MMAs of
+// M = 128 pixels x N = Cout -> epilogue warps store NCHW rows (128 B per warp and channel).  Also the input gradient of the pairs
+// the fused backward does not take (called with the transposed weights).
+struct FwdPlan {
+  int Cin, Cout, HW, B;
+  int NST;               // raw stages
+  int raw_stage, plane_buf, wbytes, tmem_cols;
+  int tiles_per_img, ntiles, ctas;
+  size_t smem;
+};
+
+__global__ void __launch_bounds__(NTHREADS) pw_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_x,
+                                                              const __nv_bfloat16* __restrict__ wpack, const float* __restrict__ bias,
+                                                              float* __restrict__ y, const FwdPlan pl) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* pl_base = smem;                                                 // [2][Cin/8][128][16 B]
+  uint8_t* raw_base = pl_base + (size_t)2 * pl.plane_buf;                  // [NST][Cin][128] fp32
+  uint8_t* w_base = raw_base + (size_t)pl.NST * pl.raw_stage;              // [Cin/16][2][Cout][16 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_base + pl.wbytes);
+  uint64_t* raw_full = bars;                 // [MAXST]
+  uint64_t* raw_empty = bars + MAXST;        // [MAXST]
+  uint64_t* pl_full = bars + 2 * MAXST;      // [2]
+  uint64_t* pl_empty = pl_full + 2;          // [2]
+  uint64_t* acc_full = pl_empty + 2;         // [2]
+  uint64_t* acc_empty = acc_full + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Cin = pl.Cin, Cout = pl.Cout, HW = pl.HW;
+
+  for (int i = tid; i < pl.wbytes / 16; i += NTHREADS) reinterpret_cast<uint4*>(w_base)[i] = __ldg(reinterpret_cast<const uint4*>(wpack) + i);
+  if (tid == 0) {
+    for (int i = 0; i < MAXST; ++i) {
+      mbar_init(smem_u32(&raw_full[i]), 1);
+      mbar_init(smem_u32(&raw_empty[i]), NCONV);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&pl_full[i]), NCONV);
+      mbar_init(smem_u32(&pl_empty[i]), 1);
+      mbar_init(smem_u32(&acc_full[i]), 1);
+      mbar_init(smem_u32(&acc_empty[i]), NCONV);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)pl.tmem_cols);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < pl.ntiles; tile += gridDim.x, ++it) {
+        const int b = tile / pl.tiles_per_img, p0 = (tile - b * pl.tiles_per_img) * TPX;
+        const uint32_t s = it % (uint32_t)pl.NST;
+        mbar_wait(smem_u32(&raw_empty[s]), ((it / (uint32_t)pl.NST) & 1u) ^ 1u);
+        const uint32_t bar = smem_u32(&raw_full[s]);
+        mbar_expect_tx(bar, (uint32_t)pl.raw_stage);
+        tma_load_2d(smem_u32(raw_base + (size_t)s * pl.raw_stage), &map_x, p0, b * Cin, bar);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, Cout);
+      const uint64_t wdesc0 = make_smem_desc(smem_u32(w_base), (uint32_t)(Cout * 16), 128);
+      const int KS = Cin / 16;
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < pl.ntiles; tile += gridDim.x, ++it) {
+        const uint32_t pb = it & 1u, ph = (it >> 1) & 1u;
+        mbar_wait_hot(smem_u32(&acc_empty[pb]), ph ^ 1u);
+        mbar_wait_hot(smem_u32(&pl_full[pb]), ph);
+        tc_fence_after();
+        const uint64_t adesc0 = make_smem_desc(smem_u32(pl_base + (size_t)pb * pl.plane_buf), PLANE, 128);
+        const uint32_t d_acc = tmem_base + pb * (uint32_t)Cout;
+        for (int ks = 0; ks < KS; ++ks)
+          umma_bf16(d_acc, desc_advance(adesc0, (uint32_t)(ks * 2 * PLANE)), desc_advance(wdesc0, (uint32_t)(ks * 2 * Cout * 16)), idesc,
+                    ks > 0 ? 1u : 0u);
+        umma_commit(smem_u32(&pl_empty[pb]));
+        umma_commit(smem_u32(&acc_full[pb]));
+      }
+    }
+  } else {
+    const int cw = warp - 2, q = warp & 3, chalf = cw >> 2;
+    const int ct = cw * 32 + lane, px = ct & 127, gpar = ct >> 7;
+    const int gx = Cin / 8;
+    auto epilogue = [&](uint32_t jt, int tile) {
+      const int b = tile / pl.tiles_per_img, p0 = (tile - b * pl.tiles_per_img) * TPX;
+      const uint32_t a = jt & 1u;
+      mbar_wait(smem_u32(&acc_full[a]), (jt >> 1) & 1u);
+      tc_fence_after();
+      const int p = p0 + q * 32 + lane;
+      const int ncol = Cout / 2, c_lo = chalf * ncol;
+      float* op = y + ((size_t)b * Cout + c_lo) * HW + p;
+      for (int c0 = 0; c0 < ncol; c0 += 8) {
+        uint32_t v[8];
+        tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + a * (uint32_t)Cout + (uint32_t)(c_lo + c0), v);
+        tmem_ld_wait();
+        if (p < HW) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) op[(size_t)(c0 + e) * HW] = __uint_as_float(v[e]) + (bias ? __ldg(bias + c_lo + c0 + e) : 0.f);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&acc_empty[a]));
+    };
+    uint32_t it = 0;
+    int prev_tile = -1;
+    for (int tile = blockIdx.x; tile < pl.ntiles; tile += gridDim.x, ++it) {
+      const uint32_t s = it % (uint32_t)pl.NST, pb = it & 1u;
+      mbar_wait(smem_u32(&raw_full[s]), (it / (uint32_t)pl.NST) & 1u);
+      mbar_wait(smem_u32(&pl_empty[pb]), ((it >> 1) & 1u) ^ 1u);
+      const float* rx = reinterpret_cast<const float*>(raw_base + (size_t)s * pl.raw_stage) + px;
+      uint8_t* pa = pl_base + (size_t)pb * pl.plane_buf + (size_t)px * 16;
+      for (int g = gpar; g < gx; g += 2) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = rx[(g * 8 + e) * TPX];
+        *reinterpret_cast<uint4*>(pa + (size_t)g * PLANE) =
+            make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&pl_full[pb]));
+        mbar_arrive(smem_u32(&raw_empty[s]));
+      }
+      if (prev_tile >= 0) epilogue(it - 1, prev_tile);
+      prev_tile = tile;
+    }
+    if (prev_tile >= 0) epilogue(it - 1, prev_tile);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)pl.tmem_cols);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -327,6 +469,34 @@ static Ws ws_layout(const kmu_pwconv_desc& d, const Plan& p) {
   return w;
 }
 
+static bool make_fwd_plan(const kmu_pwconv_desc& d, FwdPlan* out) {
+  if (d.Cin % 16 || d.Cout % 16 || d.Cin < 16 || d.Cout < 16 || d.Cin > 256 || d.Cout > 256) return false;
+  if (d.HW % 4 || d.HW < TPX || d.B <= 0) return false;
+  FwdPlan p;
+  p.Cin = d.Cin; p.Cout = d.Cout; p.HW = d.HW; p.B = d.B;
+  p.raw_stage = d.Cin * 512;
+  p.plane_buf = (d.Cin / 8) * PLANE;
+  p.wbytes = d.Cin * d.Cout * 2;
+  p.tmem_cols = pow2_cols(2 * d.Cout);
+  // two CTAs per SM when shared memory and TMEM allow it: the store-heavy epilogue of one overlaps the other's loads
+  int per_sm = p.tmem_cols <= 256 ? 2 : 1;
+  int budget = (per_sm == 2 ? 108 : 220) * 1024 - 2 * p.plane_buf - p.wbytes - 512;
+  p.NST = budget / p.raw_stage;
+  if (p.NST < 2 && per_sm == 2) {   // wide inputs: one CTA per SM with the whole shared memory
+    per_sm = 1;
+    budget = 220 * 1024 - 2 * p.plane_buf - p.wbytes - 512;
+    p.NST = budget / p.raw_stage;
+  }
+  if (p.NST < 2) return false;
+  if (p.NST > MAXST) p.NST = MAXST;
+  p.tiles_per_img = cdiv(d.HW, TPX);
+  p.ntiles = d.B * p.tiles_per_img;
+  p.ctas = p.ntiles < 148 * per_sm ? p.ntiles : 148 * per_sm;
+  p.smem = (size_t)p.NST * p.raw_stage + (size_t)2 * p.plane_buf + p.wbytes + 256;
+  *out = p;
+  return true;
+}
+
 }  // namespace fused
 }  // namespace pwtc
 }  // namespace kmu
@@ -336,6 +506,38 @@ using namespace kmu::pwtc;
 using namespace kmu::pwtc::fused;
 
 extern "C" {
+
+int kmu_pwconv_tma_fwd_supported(const kmu_pwconv_desc* d) {
+  FwdPlan p;
+  return (d && make_fwd_plan(*d, &p)) ? 1 : 0;
+}
+
+size_t kmu_pwconv_tma_fwd_workspace_bytes(const kmu_pwconv_desc* d) {
+  FwdPlan p;
+  if (!d || !make_fwd_plan(*d, &p)) return 0;
+  return align_up((size_t)p.wbytes, 256);
+}
+
+int kmu_pwconv_tma_fwd(const kmu_pwconv_desc* d, const float* x, const float* w, const float* bias, float* y, void* workspace,
+                       size_t workspace_bytes, kmu_stream stream) {
+  FwdPlan p;
+  KMU_REQUIRE(d && make_fwd_plan(*d, &p) && d->B <= 65535, KMU_ERR_UNSUPPORTED, "pwconv_tma_fwd: unsupported shape");
+  KMU_REQUIRE(x && w && y, KMU_ERR_BAD_ARG, "pwconv_tma_fwd: null tensor");
+  KMU_REQUIRE(((uintptr_t)x & 15) == 0, KMU_ERR_BAD_ARG, "pwconv_tma_fwd: x must be 16-byte aligned");
+  KMU_REQUIRE(workspace && workspace_bytes >= align_up((size_t)p.wbytes, 256), KMU_ERR_WORKSPACE, "pwconv_tma_fwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* wpack = (__nv_bfloat16*)workspace;
+  CUtensorMap map_x;
+  int rc = make_row_map(&map_x, x, (long long)d->B * d->Cin, d->HW, d->Cin);
+  if (rc != KMU_OK) return rc;
+  launch_pack(w, wpack, d->Cin, d->Cout, d->Cout, 0, st);   // wpack[ks][gi][n][e] = W[n][ks*16 + gi*8 + e]
+  KMU_LAUNCH_CHECK("pw_tc_pack");
+  cudaError_t e = cudaFuncSetAttribute(pw_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+  KMU_REQUIRE(e == cudaSuccess, KMU_ERR_LAUNCH, "pwconv_tma_fwd: cannot opt in to %zu B shared memory: %s", p.smem, cudaGetErrorString(e));
+  pw_fwd_tma_kernel<<<p.ctas, NTHREADS, p.smem, st>>>(map_x, wpack, bias, y, p);
+  KMU_LAUNCH_CHECK("pw_fwd_tma");
+  return KMU_OK;
+}
 
 int kmu_pwconv_fused_bwd_supported(const kmu_pwconv_desc* d) {
   Plan p;

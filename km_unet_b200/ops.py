@@ -500,7 +500,13 @@ class _PwConvFn(torch.autograd.Function):
         b = None if bias is None else bias.contiguous()
         y = torch.empty((B, Cout) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
         tc = precision == KMU_PREC_BF16 and bool(lib.kmu_pwconv_tc_supported(C.byref(desc)))
-        if tc:
+        from . import config
+        if config.conv_fwd == "tma" and x.data_ptr() % 16 == 0 and bool(lib.kmu_pwconv_tma_fwd_supported(C.byref(desc))):
+            tc = False
+            ws = _workspace(lib.kmu_pwconv_tma_fwd_workspace_bytes(C.byref(desc)), x.device)
+            check(_call("kmu_pwconv_tma_fwd", (B, Cin, Cout, HW), lib.kmu_pwconv_tma_fwd, C.byref(desc), ptr(x), ptr(w), ptr(b), ptr(y),
+                        ws.data_ptr(), ws.numel(), stream_ptr()), "kmu_pwconv_tma_fwd")
+        elif tc:
             ws = _workspace(lib.kmu_pwconv_tc_workspace_bytes(C.byref(desc)), x.device)
             check(_call("kmu_pwconv_tc_fwd", (B, Cin, Cout, HW), lib.kmu_pwconv_tc_fwd, C.byref(desc), ptr(x), ptr(w), ptr(b), ptr(y),
                         ws.data_ptr(), ws.numel(), stream_ptr()), "kmu_pwconv_tc_fwd")

@@ -56,13 +56,13 @@ def test_full_model_eval_bf16_tensor_core_path_within_2e2():
     m.load_state_dict(g.sd())
     m = m.cuda().eval()
     K.config.kan_precision = K.config.hsm_precision = K.config.conv_precision = "bf16"
-    K.config.conv_bwd = "fused"
+    K.config.conv_bwd, K.config.conv_fwd = "fused", "tma"
     try:
         with torch.no_grad():
             y = m(g.t("in0", "cuda"))
     finally:
         K.config.kan_precision = K.config.hsm_precision = K.config.conv_precision = "fp32"
-        K.config.conv_bwd = "split"
+        K.config.conv_bwd, K.config.conv_fwd = "split", "simt"
     assert rel_err(y, g.t("out0")) < 2e-2
 
 
@@ -72,7 +72,7 @@ def test_training_step_runs_and_all_live_parameters_get_finite_grads(variant, cl
     torch.manual_seed(1234)
     m = K.KM_UNetV3(num_classes=classes, variant=variant).cuda().train()
     K.config.kan_precision = K.config.hsm_precision = K.config.conv_precision = "bf16"
-    K.config.conv_bwd = "fused"
+    K.config.conv_bwd, K.config.conv_fwd = "fused", "tma"
     try:
         x = torch.rand(2, 5, 64, 64, device="cuda")
         t = torch.rand(2, classes, 64, 64, device="cuda")
@@ -80,7 +80,7 @@ def test_training_step_runs_and_all_live_parameters_get_finite_grads(variant, cl
         loss.backward()
     finally:
         K.config.kan_precision = K.config.hsm_precision = K.config.conv_precision = "fp32"
-        K.config.conv_bwd = "split"
+        K.config.conv_bwd, K.config.conv_fwd = "split", "simt"
     assert torch.isfinite(loss)
     dead = ("branches.", ".attn.1.", "dt_proj.", "high_freq_conv.")
     for k, p in m.named_parameters():

@@ -272,3 +272,27 @@ def test_pwconv_fused_backward_within_2e2(B, Cin, Cout, H, W, bias):
     assert rel_err(wc.grad, wd.grad) < 2e-2
     if bias:
         assert rel_err(bc.grad, bd.grad) < 2e-2
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W,bias", [(2, 16, 64, 32, 32, True), (3, 64, 16, 16, 20, False), (2, 16, 48, 16, 16, True),
+                                                (2, 32, 128, 24, 24, True), (2, 128, 32, 16, 16, True), (2, 64, 256, 16, 16, True),
+                                                (8, 16, 64, 128, 128, True), (2, 32, 32, 13, 12, False), (2, 64, 192, 32, 32, True)])
+def test_pwconv_tma_forward_within_2e2(B, Cin, Cout, H, W, bias):
+    """config.conv_fwd = "tma": forward on the persistent TMA -> tcgen05 pipeline (bf16 operands, fp32 accumulation), incl. ragged
+    last tiles and the widest accumulators (2 x 256 TMEM columns)."""
+    import km_unet_b200 as K
+    from km_unet_b200 import _lib, ops
+    import ctypes as C
+    assert _lib.lib().kmu_pwconv_tma_fwd_supported(C.byref(ops.PwDesc(B, Cin, Cout, H * W)))
+    torch.manual_seed(Cin + Cout + H)
+    x = torch.randn(B, Cin, H, W)
+    w = torch.randn(Cout, Cin, 1, 1) / Cin ** 0.5
+    bv = torch.randn(Cout) if bias else None
+    want = F.conv2d(x.double(), w.double(), bv.double() if bias else None)
+    old = K.config.conv_fwd
+    K.config.conv_fwd = "tma"
+    try:
+        y = ops.pwconv(x.cuda(), w.cuda(), bv.cuda() if bias else None)
+    finally:
+        K.config.conv_fwd = old
+    assert rel_err(y, want) < 2e-2

@@ -4,10 +4,15 @@ import subprocess
 import sys
 
 rep, title = sys.argv[1], (sys.argv[2] if len(sys.argv) > 2 else "")
-out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+if rep.endswith(".csv"):           # `ncu -i rep --page raw --csv` already run on the GPU box (the .ncu-rep stays there)
+    with open(rep) as f:
+        out = f.read()
+else:
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units = rows[0], rows[1]
 COLS = [("gpu__time_duration.sum", "time"), ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor pipe %"),
+        ("sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_elapsed", "TC unit busy %"),
         ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue active %"),
         ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem LSU %"),
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM %"), ("dram__bytes_read.sum", "DRAM read"),

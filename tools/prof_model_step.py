@@ -13,6 +13,7 @@ B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 K.config.kan_precision = "bf16"
 K.config.hsm_precision = "bf16"
 K.config.conv_bwd = "fused"
+K.config.conv_fwd = "tma"
 torch.backends.cudnn.benchmark = os.environ.get("KMU_CUDNN_BENCHMARK", "1") == "1"   # train_shanghai.py:331
 torch.manual_seed(1234)
 m = K.KM_UNetV3_SH(num_classes=20).cuda().train()
