@@ -497,6 +497,7 @@ def run_model(h, args):
         launches = graphed_launches            # replays do not pass through the host-side counter: count of the captured step
     clocks = sampler.stop() if sampler else None
     value = world * B * args.steps / (total_ms / 1e3)
+    last_loss = float(step_resident().detach().float().cpu())     # sanity: a diverged / corrupted run must not pass as a number
     e2e_ms = h.timed(step_e2e, args.steps, args.warmup)
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
 
@@ -569,7 +570,7 @@ def run_model(h, args):
                        "grad_allreduce": (f"bucketed NCCL, {nlive * 4 / 1e6:.1f} MB" if world > 1 else "none (1 GPU)")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": batch_host.numel() * 4, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "kan_microbench": kan,
+            "gpu_launches": int(launches), "loss_after_timed_steps": last_loss, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "kan_microbench": kan,
         }
         print(json.dumps(line), flush=True)
 

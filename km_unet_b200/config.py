@@ -23,3 +23,6 @@ def precision_code(name=None):
     if name not in ("fp32", "bf16"):
         raise ValueError(f"unknown KAN precision {name!r} (expected 'fp32' or 'bf16')")
     return KMU_PREC_BF16 if name == "bf16" else KMU_PREC_FP32
+# pairs the TMA pipelines do not take (Cin + Cout too wide for the tile ring): "tc" = per-tile tcgen05 kernels of pwconv_tc.cu,
+# "simt" = fp32 streaming kernels
+conv_wide = os.environ.get("KMU_CONV_WIDE", "tc")

@@ -499,8 +499,9 @@ class _PwConvFn(torch.autograd.Function):
         w = weight.reshape(Cout, Cin).contiguous()
         b = None if bias is None else bias.contiguous()
         y = torch.empty((B, Cout) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
-        tc = precision == KMU_PREC_BF16 and bool(lib.kmu_pwconv_tc_supported(C.byref(desc)))
         from . import config
+        wide_tc = config.conv_wide == "tc"
+        tc = (precision == KMU_PREC_BF16 or (config.conv_fwd == "tma" and wide_tc)) and bool(lib.kmu_pwconv_tc_supported(C.byref(desc)))
         if config.conv_fwd == "tma" and x.data_ptr() % 16 == 0 and bool(lib.kmu_pwconv_tma_fwd_supported(C.byref(desc))):
             tc = False
             ws = _workspace(lib.kmu_pwconv_tma_fwd_workspace_bytes(C.byref(desc)), x.device)
@@ -514,7 +515,8 @@ class _PwConvFn(torch.autograd.Function):
             check(_call("kmu_pwconv_fwd", (B, Cin, Cout, HW), lib.kmu_pwconv_fwd, C.byref(desc), ptr(x), ptr(w), ptr(b), ptr(y),
                         stream_ptr()), "kmu_pwconv_fwd")
         ctx.save_for_backward(x, w)
-        ctx.desc, ctx.has_bias, ctx.wshape, ctx.tc = desc, bias is not None, weight.shape, tc
+        ctx.desc, ctx.has_bias, ctx.wshape = desc, bias is not None, weight.shape
+        ctx.tc = tc or (config.conv_bwd == "fused" and wide_tc and bool(lib.kmu_pwconv_tc_supported(C.byref(desc))))
         return y
 
     @staticmethod
