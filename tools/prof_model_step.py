@@ -32,9 +32,14 @@ def step():
     return loss
 
 
-for _ in range(steps):
+for i in range(steps):
+    if i == steps - 1 and os.environ.get("KMU_PROFILE_LAST_STEP"):   # ncu --profile-from-start off: only the last step is profiled
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     loss = step()
 torch.cuda.synchronize()
+if os.environ.get("KMU_PROFILE_LAST_STEP"):
+    torch.cuda.profiler.stop()
 if os.environ.get("KMU_ATEN_PROFILE"):
     # ATen-level attribution of the non-libkmunet part of the step (torch.profiler, device time per op and input shape)
     from torch.profiler import ProfilerActivity, profile
