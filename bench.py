@@ -270,6 +270,8 @@ class Harness:
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
         if self.world > 1:
+            # NCCL prints its version banner on stdout (NCCL_DEBUG=VERSION/INFO): keep stdout for the one JSON line
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
             dist.init_process_group("nccl", device_id=self.dev)
         self.args = args
 
