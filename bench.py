@@ -31,6 +31,16 @@ import sys
 import threading
 import time
 
+# stdout carries exactly ONE JSON line.  Libraries that write to file descriptor 1 behind Python's back (NCCL prints its version
+# banner there) are sent to stderr: fd 1 is re-pointed at fd 2 and the JSON line goes to a private duplicate of the real stdout.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -252,7 +262,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -270,8 +280,6 @@ class Harness:
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
         if self.world > 1:
-            # NCCL prints its version banner on stdout (NCCL_DEBUG=VERSION/INFO): keep stdout for the one JSON line
-            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
             dist.init_process_group("nccl", device_id=self.dev)
         self.args = args
 
@@ -393,7 +401,7 @@ def run_kan(h, args):
             "roofline": {"kernel": dom, "bound": "tensor", "achieved": fam[dom]["achieved"], "peak": mb["peak"], "unit": "TFLOP/s",
                          "frac": fam[dom]["frac"], "traffic": traffic, "peak_source": mb["peak_source"], "families": fam},
             "cpu_baseline": cpu, "tflops_fwd_bwd": mb["tflops_fwd_bwd"]}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_model(h, args):
@@ -574,7 +582,7 @@ def run_model(h, args):
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches), "loss_after_timed_steps": last_loss, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "kan_microbench": kan,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
 
 
 def main():
