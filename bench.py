@@ -126,6 +126,9 @@ def op_work(name, key):
     if name.startswith("kmu_hsmssd"):
         B, C, L = key
         return ("hbm", (8.0 if name.endswith("fwd") else 16.0) * B * C * L, "byte")
+    if name.startswith("kmu_combine3"):
+        B, n = key                           # fwd: read x, f0..f2, write out; bwd: read dy, f0..f2, write df0..df2
+        return ("hbm", (20.0 if name.endswith("fwd") else 28.0) * B * n, "byte")
     if name.startswith("kmu_layernorm1d"):
         B, C, L = key
         return ("hbm", (8.0 if name.endswith("fwd") else 12.0) * B * C * L, "byte")

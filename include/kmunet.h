@@ -359,6 +359,14 @@ int kmu_dwconv3x3_fwd(const kmu_dwconv3x3_desc* d, const float* x, const float* 
 /* dx, dw (C,9), dbias (C) are overwritten; dx == NULL skips the input gradient, dw == NULL the weight / bias gradients. */
 int kmu_dwconv3x3_bwd(const kmu_dwconv3x3_desc* d, const float* x, const float* dy, const float* w, float* dx, float* dw,
                       float* dbias, void* workspace, size_t workspace_bytes, kmu_stream stream);
+/* The same convolution followed by a per-(b, c) factor: y = scale[b, c] * (conv(x) + bias) -- DirectionAttention's
+ * `self.conv(attn) * weight[:, :, None, None]` (KM_UNetV3_SH.py:130-151) without the broadcast multiply and its three backward
+ * kernels.  scale is (B, C); dscale (B, C) = sum_hw dy * (conv + bias) falls out of the weight-gradient partials. */
+int kmu_dwconv3x3_scaled_fwd(const kmu_dwconv3x3_desc* d, const float* x, const float* w, const float* bias, const float* scale,
+                             float* y, kmu_stream stream);
+int kmu_dwconv3x3_scaled_bwd(const kmu_dwconv3x3_desc* d, const float* x, const float* dy, const float* w, const float* bias,
+                             const float* scale, float* dx, float* dw, float* dbias, float* dscale, void* workspace,
+                             size_t workspace_bytes, kmu_stream stream);
 
 /* Pointwise (1x1) convolution on NCHW: y[b,o,p] = bias[o] + sum_c w[o,c] x[b,c,p]   (vim_utils_init.py:122-130 FFN,
  * KM_UNetV3_SH.py:59,118-122,178,221).  The weight gradient kernel needs Cin a power of two in [16,1024] and
@@ -425,6 +433,16 @@ int kmu_triplenorm_fwd(const kmu_triplenorm_fwd_args* a, kmu_stream stream);
 int kmu_triplenorm_bwd(const kmu_triplenorm_bwd_args* a, kmu_stream stream);
 int kmu_qkv_gate_fwd(const float* qkv, float* out, int32_t B, int32_t C, int32_t HW, kmu_stream stream);
 int kmu_qkv_gate_bwd(const float* qkv, const float* dout, float* dqkv, int32_t B, int32_t C, int32_t HW, kmu_stream stream);
+
+/* kmu_combine3: EnhancedViMBlock.forward, KM_UNetV3_SH.py:349-368: x + DropPath(g0 f0 + g1 f1 + g2 f2) as ONE pass,
+ *     out[b] = x[b] + sum_i coef[b][i] f_i[b],   coef (B,3) = softmax gate weight x per-sample DropPath factor (built by the caller);
+ * backward: df_i = coef[b][i] dy, dcoef[b][i] = sum dy . f_i (per-CTA partials reduced in fixed order); dx = dy is the caller's.
+ * n_per_b = C*H*W elements per sample, a multiple of 4. */
+size_t kmu_combine3_bwd_workspace_bytes(int32_t B, int64_t n_per_b);
+int kmu_combine3_fwd(const float* x, const float* f0, const float* f1, const float* f2, const float* coef, float* out, int32_t B,
+                     int64_t n_per_b, kmu_stream stream);
+int kmu_combine3_bwd(const float* dy, const float* f0, const float* f1, const float* f2, const float* coef, float* df0, float* df1,
+                     float* df2, float* dcoef, int32_t B, int64_t n_per_b, void* workspace, size_t workspace_bytes, kmu_stream stream);
 
 /* Dense "same" convolution with at most 9 taps (1x1, 1x3, 3x1, 3x3; stride 1, zero padding k/2) on NCHW:
  * DirectionViM.proj (KM_UNetV3_SH.py:172-176), the decoder / fusion 3x3 convs (:292,299,427,437,439).

@@ -157,6 +157,9 @@ SYMBOLS = {
     "kmu_dwconv3x3_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(DwDesc)]),
     "kmu_dwconv3x3_fwd": (C.c_int, [C.POINTER(DwDesc), _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
     "kmu_dwconv3x3_bwd": (C.c_int, [C.POINTER(DwDesc), _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kmu_dwconv3x3_scaled_fwd": (C.c_int, [C.POINTER(DwDesc), _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
+    "kmu_dwconv3x3_scaled_bwd": (C.c_int, [C.POINTER(DwDesc), _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p,
+                                           C.c_size_t, C.c_void_p]),
     "kmu_pwconv_wgrad_supported": (C.c_int, [C.POINTER(PwDesc)]),
     "kmu_pwconv_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(PwDesc)]),
     "kmu_pwconv_fwd": (C.c_int, [C.POINTER(PwDesc), _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
@@ -166,6 +169,10 @@ SYMBOLS = {
     "kmu_triplenorm_bwd": (C.c_int, [C.POINTER(TnBwdArgs), C.c_void_p]),
     "kmu_qkv_gate_fwd": (C.c_int, [_f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "kmu_qkv_gate_bwd": (C.c_int, [_f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "kmu_combine3_bwd_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64]),
+    "kmu_combine3_fwd": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int32, C.c_int64, C.c_void_p]),
+    "kmu_combine3_bwd": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int32, C.c_int64, C.c_void_p,
+                                   C.c_size_t, C.c_void_p]),
     "kmu_smallconv_supported": (C.c_int, [C.POINTER(ScDesc)]),
     "kmu_smallconv_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(ScDesc)]),
     "kmu_smallconv_fwd": (C.c_int, [C.POINTER(ScDesc), _f32p, _f32p, _f32p, _f32p, C.c_void_p]),

@@ -492,6 +492,82 @@ static int tn_check(const kmu_triplenorm_desc* d, const char* who) {
 }  // namespace glue
 }  // namespace kmu
 
+namespace kmu {
+namespace glue {
+
+// ---------------------------------------------------------------------------------------------- combine3
+// EnhancedViMBlock.forward (KM_UNetV3_SH.py:349-368): x + DropPath(g0 f0 + g1 f1 + g2 f2) with per-sample gate weights g (softmax
+// of the fusion gate) and the per-sample DropPath factor folded into coef[b][i]:   out = x + sum_i coef[b][i] f_i.
+// One pass over five tensors instead of three broadcast multiplies, a mask multiply and three adds.
+__global__ void __launch_bounds__(256) combine3_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ f0,
+                                                           const float4* __restrict__ f1, const float4* __restrict__ f2,
+                                                           const float* __restrict__ coef, float4* __restrict__ out, long long n4_per_b,
+                                                           long long total4) {
+  long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total4) return;
+  const int b = (int)(i / n4_per_b);
+  const float c0 = __ldg(coef + b * 3), c1 = __ldg(coef + b * 3 + 1), c2 = __ldg(coef + b * 3 + 2);
+  const float4 xv = __ldg(x + i), a = __ldg(f0 + i), bb = __ldg(f1 + i), c = __ldg(f2 + i);
+  float4 o;
+  o.x = xv.x + c0 * a.x + c1 * bb.x + c2 * c.x;
+  o.y = xv.y + c0 * a.y + c1 * bb.y + c2 * c.y;
+  o.z = xv.z + c0 * a.z + c1 * bb.z + c2 * c.z;
+  o.w = xv.w + c0 * a.w + c1 * bb.w + c2 * c.w;
+  out[i] = o;
+}
+
+// df_i = coef[b][i] dy ; dcoef partials: part[b][chunk][i] = sum over the chunk of dy . f_i.   grid (chunks, B), 256 threads.
+__global__ void __launch_bounds__(256) combine3_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ f0,
+                                                           const float4* __restrict__ f1, const float4* __restrict__ f2,
+                                                           const float* __restrict__ coef, float4* __restrict__ df0,
+                                                           float4* __restrict__ df1, float4* __restrict__ df2, float* __restrict__ part,
+                                                           long long n4_per_b, int per_cta) {
+  __shared__ float red[8];
+  const int b = blockIdx.y;
+  const float c0 = __ldg(coef + b * 3), c1 = __ldg(coef + b * 3 + 1), c2 = __ldg(coef + b * 3 + 2);
+  const long long base = (long long)b * n4_per_b;
+  const long long lo = (long long)blockIdx.x * per_cta;
+  long long hi = lo + per_cta;
+  if (hi > n4_per_b) hi = n4_per_b;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  for (long long j = lo + threadIdx.x; j < hi; j += 256) {
+    const long long i = base + j;
+    const float4 g = __ldg(dy + i), a = __ldg(f0 + i), bb = __ldg(f1 + i), c = __ldg(f2 + i);
+    s0 += g.x * a.x + g.y * a.y + g.z * a.z + g.w * a.w;
+    s1 += g.x * bb.x + g.y * bb.y + g.z * bb.z + g.w * bb.w;
+    s2 += g.x * c.x + g.y * c.y + g.z * c.z + g.w * c.w;
+    df0[i] = make_float4(c0 * g.x, c0 * g.y, c0 * g.z, c0 * g.w);
+    df1[i] = make_float4(c1 * g.x, c1 * g.y, c1 * g.z, c1 * g.w);
+    df2[i] = make_float4(c2 * g.x, c2 * g.y, c2 * g.z, c2 * g.w);
+  }
+  s0 = block_sum256(s0, red);
+  s1 = block_sum256(s1, red);
+  s2 = block_sum256(s2, red);
+  if (threadIdx.x == 0) {
+    float* p = part + ((size_t)b * gridDim.x + blockIdx.x) * 3;
+    p[0] = s0; p[1] = s1; p[2] = s2;
+  }
+}
+
+__global__ void combine3_reduce_kernel(const float* __restrict__ part, int chunks, float* __restrict__ dcoef, int n) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // (b, i)
+  if (idx >= n) return;
+  const int b = idx / 3, i = idx - b * 3;
+  float s = 0.f;
+  for (int k = 0; k < chunks; ++k) s += part[((size_t)b * chunks + k) * 3 + i];
+  dcoef[idx] = s;
+}
+
+static int combine3_chunks(int B, long long n4_per_b) {
+  int chunks = (148 * 8 + B - 1) / B;
+  const long long maxc = (n4_per_b + 1023) / 1024;
+  if (chunks > maxc) chunks = (int)maxc;
+  return chunks < 1 ? 1 : chunks;
+}
+
+}  // namespace glue
+}  // namespace kmu
+
 using namespace kmu;
 using namespace kmu::glue;
 
@@ -614,6 +690,39 @@ int kmu_qkv_gate_bwd(const float* qkv, const float* dout, float* dqkv, int32_t B
   if ((HW & 3) == 0) gate_bwd_kernel<true><<<cdiv(total / 4, 256), 256, 0, (cudaStream_t)stream>>>(qkv, dout, dqkv, C, HW, total);
   else gate_bwd_kernel<false><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(qkv, dout, dqkv, C, HW, total);
   KMU_LAUNCH_CHECK("qkv_gate_bwd");
+  return KMU_OK;
+}
+
+size_t kmu_combine3_bwd_workspace_bytes(int32_t B, int64_t n_per_b) {
+  if (B <= 0 || n_per_b <= 0 || (n_per_b & 3)) return 0;
+  return align_up((size_t)B * kmu::glue::combine3_chunks(B, n_per_b / 4) * 3 * 4, 256);
+}
+
+int kmu_combine3_fwd(const float* x, const float* f0, const float* f1, const float* f2, const float* coef, float* out, int32_t B,
+                     int64_t n_per_b, kmu_stream stream) {
+  KMU_REQUIRE(x && f0 && f1 && f2 && coef && out && B > 0 && n_per_b > 0, KMU_ERR_BAD_ARG, "combine3_fwd: bad argument");
+  KMU_REQUIRE((n_per_b & 3) == 0, KMU_ERR_UNSUPPORTED, "combine3_fwd: elements per sample (%lld) must be a multiple of 4", (long long)n_per_b);
+  const long long n4 = n_per_b / 4, total4 = n4 * B;
+  kmu::glue::combine3_fwd_kernel<<<(unsigned)cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)x, (const float4*)f0, (const float4*)f1, (const float4*)f2, coef, (float4*)out, n4, total4);
+  KMU_LAUNCH_CHECK("combine3_fwd");
+  return KMU_OK;
+}
+
+int kmu_combine3_bwd(const float* dy, const float* f0, const float* f1, const float* f2, const float* coef, float* df0, float* df1,
+                     float* df2, float* dcoef, int32_t B, int64_t n_per_b, void* workspace, size_t workspace_bytes, kmu_stream stream) {
+  KMU_REQUIRE(dy && f0 && f1 && f2 && coef && df0 && df1 && df2 && dcoef && B > 0 && n_per_b > 0, KMU_ERR_BAD_ARG, "combine3_bwd: bad argument");
+  KMU_REQUIRE((n_per_b & 3) == 0 && B <= 65535, KMU_ERR_UNSUPPORTED, "combine3_bwd: unsupported shape");
+  KMU_REQUIRE(workspace && workspace_bytes >= kmu_combine3_bwd_workspace_bytes(B, n_per_b), KMU_ERR_WORKSPACE, "combine3_bwd: workspace too small");
+  const long long n4 = n_per_b / 4;
+  const int chunks = kmu::glue::combine3_chunks(B, n4);
+  const int per_cta = (int)cdiv(n4, chunks);
+  cudaStream_t st = (cudaStream_t)stream;
+  kmu::glue::combine3_bwd_kernel<<<dim3(chunks, B), 256, 0, st>>>((const float4*)dy, (const float4*)f0, (const float4*)f1, (const float4*)f2,
+                                                                 coef, (float4*)df0, (float4*)df1, (float4*)df2, (float*)workspace, n4, per_cta);
+  KMU_LAUNCH_CHECK("combine3_bwd");
+  kmu::glue::combine3_reduce_kernel<<<cdiv(B * 3, 128), 128, 0, st>>>((const float*)workspace, chunks, dcoef, B * 3);
+  KMU_LAUNCH_CHECK("combine3_reduce");
   return KMU_OK;
 }
 

@@ -272,9 +272,11 @@ struct DwDims {
 
 // y[b,c,h,w] = bias[c] + sum_{ky,kx} w[c][ky*3+kx] x[b,c,h+ky-1,w+kx-1] (zero padding).  FLIP: correlate with the flipped
 // kernel (= the input gradient of the same convolution).  Thread = 4 consecutive output columns of one row.
+// scale (optional, one factor per (b, c) plane) multiplies the result: y = scale * (conv + bias) forward, dx = scale * conv^T(dy).
 template <bool FLIP>
 __global__ void __launch_bounds__(256) dw3x3_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                    const float* __restrict__ bias, float* __restrict__ y, DwDims d) {
+                                                    const float* __restrict__ bias, const float* __restrict__ scale,
+                                                    float* __restrict__ y, DwDims d) {
   const int wq = (d.W + 3) >> 2;
   long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   long long total = (long long)d.B * d.C * d.H * wq;
@@ -310,6 +312,11 @@ __global__ void __launch_bounds__(256) dw3x3_kernel(const float* __restrict__ x,
 #pragma unroll
     for (int e = 0; e < 4; ++e)
       acc[e] = fmaf(k[ky * 3], v[e], fmaf(k[ky * 3 + 1], v[e + 1], fmaf(k[ky * 3 + 2], v[e + 2], acc[e])));
+  }
+  if (scale) {
+    const float sc = __ldg(scale + plane);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[e] *= sc;
   }
   float* yp = y + (size_t)plane * d.H * d.W + (size_t)h * d.W + w0;
   if (vec) {
@@ -366,9 +373,10 @@ __global__ void __launch_bounds__(256) dw3x3_wgrad_kernel(const float* __restric
   }
 }
 
-// dw[c][t] = sum over b and row slices; warp = (c, t), lanes stride over the B * RS partials, fixed-order tree (deterministic)
-__global__ void __launch_bounds__(128) dw3x3_wreduce_kernel(const float* __restrict__ part, int B, int C, int RS,
-                                                            float* __restrict__ dw, float* __restrict__ dbias) {
+// dw[c][t] = sum over b and row slices; warp = (c, t), lanes stride over the B * RS partials, fixed-order tree (deterministic).
+// With a per-plane scale (y = scale * (conv + bias)) every plane's partial is weighted by its scale.
+__global__ void __launch_bounds__(128) dw3x3_wreduce_kernel(const float* __restrict__ part, const float* __restrict__ scale, int B, int C,
+                                                            int RS, float* __restrict__ dw, float* __restrict__ dbias) {
   const int idx = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (idx >= C * 10) return;
   const int c = idx / 10, t = idx - c * 10;
@@ -376,7 +384,8 @@ __global__ void __launch_bounds__(128) dw3x3_wreduce_kernel(const float* __restr
   const int n = B * RS;
   for (int i = lane; i < n; i += 32) {
     const int b = i / RS, r = i - b * RS;
-    s += (double)part[(((size_t)b * C + c) * RS + r) * 10 + t];
+    const float sc = scale ? __ldg(scale + (size_t)b * C + c) : 1.f;
+    s += (double)(sc * part[(((size_t)b * C + c) * RS + r) * 10 + t]);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -384,6 +393,25 @@ __global__ void __launch_bounds__(128) dw3x3_wreduce_kernel(const float* __restr
     if (t < 9) dw[c * 9 + t] = (float)s;
     else if (dbias) dbias[c] = (float)s;
   }
+}
+
+// dscale[b, c] = sum_p dy * (conv + bias) = sum_t w[c][t] part[b, c][t] + bias[c] part[b, c][9]: free from the same partials
+__global__ void __launch_bounds__(256) dw3x3_dscale_kernel(const float* __restrict__ part, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, int planes, int C, int RS,
+                                                           float* __restrict__ dscale) {
+  const int plane = blockIdx.x * 256 + threadIdx.x;
+  if (plane >= planes) return;
+  const int c = plane % C;
+  float a[10];
+#pragma unroll
+  for (int t = 0; t < 10; ++t) a[t] = 0.f;
+  for (int r = 0; r < RS; ++r)
+#pragma unroll
+    for (int t = 0; t < 10; ++t) a[t] += part[((size_t)plane * RS + r) * 10 + t];
+  float s = bias ? __ldg(bias + c) * a[9] : 0.f;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) s = fmaf(__ldg(w + c * 9 + t), a[t], s);
+  dscale[plane] = s;
 }
 
 static int dw_check(const kmu_dwconv3x3_desc* d, const char* who) {
@@ -479,19 +507,20 @@ size_t kmu_dwconv3x3_bwd_workspace_bytes(const kmu_dwconv3x3_desc* dd) {
   return align_up((size_t)dd->B * dd->C * dw_row_slices(*dd) * 10 * 4, 256);
 }
 
-int kmu_dwconv3x3_fwd(const kmu_dwconv3x3_desc* dd, const float* x, const float* w, const float* bias, float* y, kmu_stream stream) {
+static int dw_fwd(const kmu_dwconv3x3_desc* dd, const float* x, const float* w, const float* bias, const float* scale, float* y,
+                  kmu_stream stream) {
   int rc = dw_check(dd, "dwconv3x3_fwd");
   if (rc != KMU_OK) return rc;
   KMU_REQUIRE(x && w && y, KMU_ERR_BAD_ARG, "dwconv3x3_fwd: null tensor");
   DwDims d{dd->B, dd->C, dd->H, dd->W};
   long long total = (long long)d.B * d.C * d.H * ((d.W + 3) / 4);
-  dw3x3_kernel<false><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, d);
+  dw3x3_kernel<false><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, w, bias, scale, y, d);
   KMU_LAUNCH_CHECK("dw3x3_fwd");
   return KMU_OK;
 }
 
-int kmu_dwconv3x3_bwd(const kmu_dwconv3x3_desc* dd, const float* x, const float* dy, const float* w, float* dx, float* dw, float* dbias,
-                      void* workspace, size_t workspace_bytes, kmu_stream stream) {
+static int dw_bwd(const kmu_dwconv3x3_desc* dd, const float* x, const float* dy, const float* w, const float* bias, const float* scale,
+                  float* dx, float* dw, float* dbias, float* dscale, void* workspace, size_t workspace_bytes, kmu_stream stream) {
   int rc = dw_check(dd, "dwconv3x3_bwd");
   if (rc != KMU_OK) return rc;
   KMU_REQUIRE(x && dy && w, KMU_ERR_BAD_ARG, "dwconv3x3_bwd: null tensor");
@@ -499,20 +528,48 @@ int kmu_dwconv3x3_bwd(const kmu_dwconv3x3_desc* dd, const float* x, const float*
   cudaStream_t st = (cudaStream_t)stream;
   if (dx) {
     long long total = (long long)d.B * d.C * d.H * ((d.W + 3) / 4);
-    dw3x3_kernel<true><<<cdiv(total, 256), 256, 0, st>>>(dy, w, nullptr, dx, d);
+    dw3x3_kernel<true><<<cdiv(total, 256), 256, 0, st>>>(dy, w, nullptr, scale, dx, d);
     KMU_LAUNCH_CHECK("dw3x3_bwd_dx");
   }
-  if (dw) {
+  if (dw || dscale) {
     KMU_REQUIRE(workspace && workspace_bytes >= kmu_dwconv3x3_bwd_workspace_bytes(dd), KMU_ERR_WORKSPACE, "dwconv3x3_bwd: workspace too small");
     const int rs = dw_row_slices(*dd);
     const int rows = cdiv(d.H, rs);
     const int rs2 = cdiv(d.H, rows);
     dw3x3_wgrad_kernel<<<dim3(rs2, d.B * d.C), 256, 0, st>>>(x, dy, (float*)workspace, d, rows);
     KMU_LAUNCH_CHECK("dw3x3_wgrad");
-    dw3x3_wreduce_kernel<<<cdiv(d.C * 10, 4), 128, 0, st>>>((const float*)workspace, d.B, d.C, rs2, dw, dbias);
-    KMU_LAUNCH_CHECK("dw3x3_wreduce");
+    if (dw) {
+      dw3x3_wreduce_kernel<<<cdiv(d.C * 10, 4), 128, 0, st>>>((const float*)workspace, scale, d.B, d.C, rs2, dw, dbias);
+      KMU_LAUNCH_CHECK("dw3x3_wreduce");
+    }
+    if (dscale) {
+      dw3x3_dscale_kernel<<<cdiv(d.B * d.C, 256), 256, 0, st>>>((const float*)workspace, w, bias, d.B * d.C, d.C, rs2, dscale);
+      KMU_LAUNCH_CHECK("dw3x3_dscale");
+    }
   }
   return KMU_OK;
+}
+
+int kmu_dwconv3x3_fwd(const kmu_dwconv3x3_desc* dd, const float* x, const float* w, const float* bias, float* y, kmu_stream stream) {
+  return dw_fwd(dd, x, w, bias, nullptr, y, stream);
+}
+
+int kmu_dwconv3x3_bwd(const kmu_dwconv3x3_desc* dd, const float* x, const float* dy, const float* w, float* dx, float* dw, float* dbias,
+                      void* workspace, size_t workspace_bytes, kmu_stream stream) {
+  return dw_bwd(dd, x, dy, w, nullptr, nullptr, dx, dw, dbias, nullptr, workspace, workspace_bytes, stream);
+}
+
+int kmu_dwconv3x3_scaled_fwd(const kmu_dwconv3x3_desc* dd, const float* x, const float* w, const float* bias, const float* scale,
+                             float* y, kmu_stream stream) {
+  KMU_REQUIRE(scale != nullptr, KMU_ERR_BAD_ARG, "dwconv3x3_scaled_fwd: null scale");
+  return dw_fwd(dd, x, w, bias, scale, y, stream);
+}
+
+int kmu_dwconv3x3_scaled_bwd(const kmu_dwconv3x3_desc* dd, const float* x, const float* dy, const float* w, const float* bias,
+                             const float* scale, float* dx, float* dw, float* dbias, float* dscale, void* workspace,
+                             size_t workspace_bytes, kmu_stream stream) {
+  KMU_REQUIRE(scale != nullptr, KMU_ERR_BAD_ARG, "dwconv3x3_scaled_bwd: null scale");
+  return dw_bwd(dd, x, dy, w, bias, scale, dx, dw, dbias, dscale, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -86,7 +86,7 @@ class DirectionAttention(nn.Module):
         # the three pooling modes of the reference (mean over W then H, over H then W, or both) are the same global mean
         weight = self.fc(x.mean(dim=(2, 3)))
         attn = ops.qkv_gate(conv1x1(x, self.qkv.weight, self.qkv.bias))          # sigmoid(q k) v
-        return ops.dwconv3x3(attn, self.conv.weight, self.conv.bias) * weight[:, :, None, None]
+        return ops.dwconv3x3(attn, self.conv.weight, self.conv.bias, scale=weight)   # conv(attn) * weight[:, :, None, None]
 
 
 class DirectionViM(nn.Module):
@@ -140,7 +140,14 @@ class EnhancedViMBlock(nn.Module):
     def forward(self, x):
         feats = [self.height_block(x), self.width_block(x), self.channel_block(x)]
         g = self.fusion_gate(torch.cat(feats, dim=1))
-        x = x + self.drop_path(g[:, 0:1] * feats[0] + g[:, 1:2] * feats[1] + g[:, 2:3] * feats[2])
+        if ops.combine3_supported(x):
+            # x + DropPath(g0 f0 + g1 f1 + g2 f2) in one pass: the per-sample DropPath factor is folded into the gate weights
+            coef = g.reshape(g.shape[0], 3)
+            if isinstance(self.drop_path, DropPath):
+                coef = self.drop_path(coef)            # same bernoulli(keep) / keep per sample, applied to the (B,3) coefficients
+            x = ops.combine3(x, feats[0], feats[1], feats[2], coef)
+        else:
+            x = x + self.drop_path(g[:, 0:1] * feats[0] + g[:, 1:2] * feats[1] + g[:, 2:3] * feats[2])
         h = F.gelu(conv1x1(self.norm(x), self.ffn[0].weight, self.ffn[0].bias))
         return x + self.drop_path(conv1x1(h, self.ffn[2].weight, self.ffn[2].bias))
 

@@ -12,7 +12,7 @@ from . import _lib
 from ._lib import (ScDesc, TnBwdArgs, TnDesc, TnFwdArgs, PwDesc, BnMixBwdArgs, BnMixDesc, BnMixFwdArgs, DwDesc, DagemBn, DagemBwdArgs, DagemDesc, DagemFwdArgs, DysBwdArgs, DysDesc, DysFwdArgs, HsmBwdArgs, HsmDesc, HsmFwdArgs, KanBwdArgs, KanDesc, KanFwdArgs,
                    KMU_PREC_BF16, KMU_PREC_FP32, check, ptr, stream_ptr)
 
-__all__ = ["kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dysample_sample", "dagem_gate", "bnmix", "dwconv3x3", "pwconv", "pwconv_supported", "triplenorm", "qkv_gate", "smallconv", "smallconv_supported", "iwp", "iwp_supported", "KMU_PREC_FP32", "KMU_PREC_BF16"]
+__all__ = ["kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dysample_sample", "dagem_gate", "bnmix", "dwconv3x3", "pwconv", "pwconv_supported", "triplenorm", "qkv_gate", "smallconv", "smallconv_supported", "iwp", "iwp_supported", "combine3", "combine3_supported", "KMU_PREC_FP32", "KMU_PREC_BF16"]
 
 
 # ------------------------------------------------------------------------------------------------------ op-level timing
@@ -479,10 +479,51 @@ class _DwConv3x3Fn(torch.autograd.Function):
         return dx, None if dw is None else dw.reshape(ctx.wshape), db
 
 
-def dwconv3x3(x, weight, bias=None):
-    """Depthwise 3x3 convolution, stride 1, zero padding 1: weight (C,1,3,3), optional bias (C)."""
+class _DwConv3x3ScaledFn(torch.autograd.Function):
+    """y = scale[b, c] * (dwconv3x3(x) + bias): the convolution of DirectionAttention with its squeeze-excite factor folded in."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, weight, bias, scale):
+        lib = _lib.lib()
+        x = x.contiguous()
+        B, Cc, H, W = x.shape
+        desc = DwDesc(B, Cc, H, W)
+        w = weight.reshape(Cc, 9).contiguous()
+        b = None if bias is None else bias.contiguous()
+        sc = scale.reshape(B, Cc).contiguous()
+        y = torch.empty_like(x)
+        check(_call("kmu_dwconv3x3_fwd", (B, Cc, H, W), lib.kmu_dwconv3x3_scaled_fwd, C.byref(desc), ptr(x), ptr(w), ptr(b), ptr(sc),
+                    ptr(y), stream_ptr()), "kmu_dwconv3x3_scaled_fwd")
+        ctx.save_for_backward(x, w, sc, b if b is not None else w.new_zeros(0))
+        ctx.desc, ctx.has_bias, ctx.wshape, ctx.sshape = desc, bias is not None, weight.shape, scale.shape
+        return y
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        lib = _lib.lib()
+        x, w, sc, b = ctx.saved_tensors
+        desc = ctx.desc
+        dy = dy.to(torch.float32).contiguous()
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w)
+        db = torch.empty(desc.C, dtype=torch.float32, device=x.device) if ctx.has_bias else None
+        dsc = torch.empty_like(sc)
+        ws = _workspace(lib.kmu_dwconv3x3_bwd_workspace_bytes(C.byref(desc)), x.device)
+        check(_call("kmu_dwconv3x3_bwd", (desc.B, desc.C, desc.H, desc.W), lib.kmu_dwconv3x3_scaled_bwd, C.byref(desc), ptr(x), ptr(dy),
+                    ptr(w), ptr(b) if ctx.has_bias else None, ptr(sc), ptr(dx), ptr(dw), ptr(db), ptr(dsc), ws.data_ptr(), ws.numel(),
+                    stream_ptr()), "kmu_dwconv3x3_scaled_bwd")
+        return dx, dw.reshape(ctx.wshape), db, dsc.reshape(ctx.sshape)
+
+
+def dwconv3x3(x, weight, bias=None, scale=None):
+    """Depthwise 3x3 convolution, stride 1, zero padding 1: weight (C,1,3,3), optional bias (C).  scale (B,C) multiplies the
+    result per plane (y = scale * (conv + bias)) inside the same kernels."""
     if not x.is_cuda:
         raise RuntimeError("km_unet_b200.dwconv3x3: CUDA tensors only (no CPU fallback)")
+    if scale is not None:
+        return _DwConv3x3ScaledFn.apply(x, weight, bias, scale)
     return _DwConv3x3Fn.apply(x, weight, bias)
 
 
@@ -653,6 +694,48 @@ def qkv_gate(qkv):
     if not qkv.is_cuda:
         raise RuntimeError("km_unet_b200.qkv_gate: CUDA tensors only (no CPU fallback)")
     return _QkvGateFn.apply(qkv)
+
+
+class _Combine3Fn(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, f0, f1, f2, coef):
+        lib = _lib.lib()
+        x, f0, f1, f2 = x.contiguous(), f0.contiguous(), f1.contiguous(), f2.contiguous()
+        B = x.shape[0]
+        n = x.numel() // B
+        coef = coef.reshape(B, 3).contiguous()
+        out = torch.empty_like(x)
+        check(_call("kmu_combine3_fwd", (B, n), lib.kmu_combine3_fwd, ptr(x), ptr(f0), ptr(f1), ptr(f2), ptr(coef), ptr(out), B, n,
+                    stream_ptr()), "kmu_combine3_fwd")
+        ctx.save_for_backward(f0, f1, f2, coef)
+        ctx.dims = (B, n)
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        lib = _lib.lib()
+        f0, f1, f2, coef = ctx.saved_tensors
+        B, n = ctx.dims
+        dy = dy.to(torch.float32).contiguous()
+        df0, df1, df2 = torch.empty_like(f0), torch.empty_like(f1), torch.empty_like(f2)
+        dcoef = torch.empty_like(coef)
+        ws = _workspace(lib.kmu_combine3_bwd_workspace_bytes(B, n), dy.device)
+        check(_call("kmu_combine3_bwd", (B, n), lib.kmu_combine3_bwd, ptr(dy), ptr(f0), ptr(f1), ptr(f2), ptr(coef), ptr(df0), ptr(df1),
+                    ptr(df2), ptr(dcoef), B, n, ws.data_ptr(), ws.numel(), stream_ptr()), "kmu_combine3_bwd")
+        return dy, df0, df1, df2, dcoef
+
+
+def combine3_supported(x):
+    return x.is_cuda and (x.numel() // x.shape[0]) % 4 == 0
+
+
+def combine3(x, f0, f1, f2, coef):
+    """x + sum_i coef[:, i] * f_i with per-sample coefficients coef (B,3): EnhancedViMBlock's gated fusion + DropPath + residual."""
+    if not x.is_cuda:
+        raise RuntimeError("km_unet_b200.combine3: CUDA tensors only (no CPU fallback)")
+    return _Combine3Fn.apply(x, f0, f1, f2, coef)
 
 
 class _SmallConvFn(torch.autograd.Function):

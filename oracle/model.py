@@ -47,9 +47,15 @@ def _bnmix(x, weight, bias, running_mean, running_var, training, momentum=0.1, e
     return y
 
 
-def _dwconv3x3(x, weight, bias=None):
+def _dwconv3x3(x, weight, bias=None, scale=None):
     import torch.nn.functional as F
-    return F.conv2d(x, weight, bias, stride=1, padding=1, groups=x.shape[1])
+    y = F.conv2d(x, weight, bias, stride=1, padding=1, groups=x.shape[1])
+    return y if scale is None else y * scale[:, :, None, None]      # DirectionAttention: self.conv(attn) * weight (KM_UNetV3_SH.py:130-151)
+
+
+def _combine3(x, f0, f1, f2, coef):
+    c = coef.reshape(coef.shape[0], 3, 1, 1, 1)                      # KM_UNetV3_SH.py:361-364: x + drop_path(sum_i g_i f_i)
+    return x + c[:, 0] * f0 + c[:, 1] * f1 + c[:, 2] * f2
 
 
 def _pwconv(x, weight, bias=None, precision=0):
@@ -108,11 +114,13 @@ def _gate(x, deformed, linears, bns, training, momentum=0.1, eps=1e-5):
 def cpu_ops():
     from km_unet_b200 import ops
     saved = {n: getattr(ops, n) for n in ("kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dagem_gate", "bnmix",
-                                          "dwconv3x3", "pwconv", "triplenorm", "qkv_gate", "smallconv", "iwp")}
+                                          "dwconv3x3", "pwconv", "triplenorm", "qkv_gate", "smallconv", "iwp", "combine3",
+                                          "combine3_supported")}
     ops.kanconv2d, ops.kanlinear, ops.layernorm1d = _kanconv2d, _kanlinear, _hsmssd.layernorm1d
     ops.hsmssd, ops.dysample, ops.dagem_gate = _hsm, _dys, _gate
     ops.bnmix, ops.dwconv3x3, ops.pwconv = _bnmix, _dwconv3x3, _pwconv
     ops.triplenorm, ops.qkv_gate, ops.smallconv, ops.iwp = _triplenorm, _qkv_gate, _smallconv, _iwp
+    ops.combine3, ops.combine3_supported = _combine3, (lambda x: True)
     try:
         yield
     finally:

@@ -296,3 +296,51 @@ def test_pwconv_tma_forward_within_2e2(B, Cin, Cout, H, W, bias):
     finally:
         K.config.conv_fwd = old
     assert rel_err(y, want) < 2e-2
+
+
+@pytest.mark.parametrize("B,C,H,W,bias", [(2, 16, 32, 32, True), (3, 32, 17, 20, True), (2, 64, 8, 8, False), (4, 16, 128, 128, True)])
+def test_dwconv3x3_with_plane_scale_vs_torch(B, C, H, W, bias):
+    """y = scale[b, c] * (dwconv3x3(x) + bias) in one kernel; gradients of x, weight, bias and scale (fp32, 1e-4)."""
+    from km_unet_b200 import ops
+    torch.manual_seed(H * W + C)
+    x = torch.randn(B, C, H, W)
+    w = torch.randn(C, 1, 3, 3) * 0.4
+    bv = torch.randn(C) if bias else None
+    sc = torch.rand(B, C) + 0.25
+    gout = torch.randn(B, C, H, W)
+    xd, wd, sd = x.double().requires_grad_(True), w.double().requires_grad_(True), sc.double().requires_grad_(True)
+    bd = bv.double().requires_grad_(True) if bias else None
+    want = F.conv2d(xd, wd, bd, padding=1, groups=C) * sd[:, :, None, None]
+    want.backward(gout.double())
+    xc, wc, scc = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True), sc.cuda().requires_grad_(True)
+    bc = bv.cuda().requires_grad_(True) if bias else None
+    y = ops.dwconv3x3(xc, wc, bc, scale=scc)
+    assert rel_err(y, want) < TOL
+    y.backward(gout.cuda())
+    assert rel_err(xc.grad, xd.grad) < TOL
+    assert rel_err(wc.grad, wd.grad) < TOL
+    assert rel_err(scc.grad, sd.grad) < TOL
+    if bias:
+        assert rel_err(bc.grad, bd.grad) < TOL
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 16, 32, 32), (5, 32, 12, 10), (32, 16, 64, 64)])
+def test_combine3_vs_torch(B, C, H, W):
+    """x + sum_i coef[b, i] f_i (EnhancedViMBlock's gated fusion + DropPath + residual) and its gradients (fp32, 1e-4)."""
+    from km_unet_b200 import ops
+    torch.manual_seed(B + C + H)
+    t = [torch.randn(B, C, H, W) for _ in range(4)]
+    coef = torch.rand(B, 3)
+    gout = torch.randn(B, C, H, W)
+    td = [v.double().requires_grad_(True) for v in t]
+    cd = coef.double().requires_grad_(True)
+    want = td[0] + sum(cd[:, i].reshape(B, 1, 1, 1) * td[i + 1] for i in range(3))
+    want.backward(gout.double())
+    tc = [v.cuda().requires_grad_(True) for v in t]
+    cc = coef.cuda().requires_grad_(True)
+    y = ops.combine3(tc[0], tc[1], tc[2], tc[3], cc)
+    assert rel_err(y, want) < TOL
+    y.backward(gout.cuda())
+    for a, b in zip(tc, td):
+        assert rel_err(a.grad, b.grad) < TOL
+    assert rel_err(cc.grad, cd.grad) < TOL
