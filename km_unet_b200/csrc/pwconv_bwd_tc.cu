@@ -42,6 +42,22 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                : "memory");
 }
 
+// weights fp32 -> the bf16 K-major B-operand image [ks][gi][n][8] straight into shared memory (every CTA converts its own copy:
+// at most 64 K values from L2, cheaper than a separate pack launch per call).  transposed: element (k, n) = w[k * NJ + n] (dgrad of
+// W (Cout, Cin) with K = Cout), else w[n * NI + k] (forward, K = Cin).
+__device__ __forceinline__ void pack_weights_smem(const float* __restrict__ w, uint8_t* w_base, int NI, int NJ, bool transposed) {
+  const int total = NI * NJ / 8;                      // 16-byte units: (ks, gi, n)
+  for (int u = threadIdx.x; u < total; u += blockDim.x) {
+    const int n = u % NJ, r = u / NJ;                 // r = ks * 2 + gi
+    const int k0 = r * 8;
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = transposed ? __ldg(w + (size_t)(k0 + e) * NJ + n) : __ldg(w + (size_t)n * NI + k0 + e);
+    *reinterpret_cast<uint4*>(w_base + (size_t)u * 16) =
+        make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  }
+}
+
 struct Plan {
   int Cin, Cout, HW, B;
   int MH, Np;            // 128-row halves of Cout; UMMA N of the wgrad GEMM (Cin + ones group + zero group)
@@ -57,7 +73,7 @@ struct Plan {
 
 __global__ void __launch_bounds__(NTHREADS, 1) pw_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_x,
                                                                    const __grid_constant__ CUtensorMap map_dy,
-                                                                   const __nv_bfloat16* __restrict__ wpack, float* __restrict__ dx,
+                                                                   const float* __restrict__ w, float* __restrict__ dx,
                                                                    float* __restrict__ partial, const Plan pl) {
   extern __shared__ __align__(128) uint8_t smem[];
   // The wgrad A descriptor always spans 16 channel groups per 128-row half; groups >= Cout/8 are whatever follows the dy planes
@@ -80,7 +96,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_bwd_fused_kernel(const __grid_
 
   // zero the plane buffers once: the zero group of B (columns Cin + 8 .. Cin + 15 of the wgrad GEMM) stays zero
   for (int i = tid; i < pl.NPL * pl.plane_buf / 16; i += NTHREADS) reinterpret_cast<uint4*>(pl_base)[i] = make_uint4(0u, 0u, 0u, 0u);
-  for (int i = tid; i < pl.wbytes / 16; i += NTHREADS) reinterpret_cast<uint4*>(w_base)[i] = __ldg(reinterpret_cast<const uint4*>(wpack) + i);
+  pack_weights_smem(w, w_base, pl.Cout, pl.Cin, true);      // dgrad: K = Cout, N = Cin
   if (tid == 0) {
     for (int i = 0; i < MAXST; ++i) {
       mbar_init(smem_u32(&raw_full[i]), 1);
@@ -256,7 +272,7 @@ struct FwdPlan {
 };
 
 __global__ void __launch_bounds__(NTHREADS) pw_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_x,
-                                                              const __nv_bfloat16* __restrict__ wpack, const float* __restrict__ bias,
+                                                              const float* __restrict__ w, const float* __restrict__ bias,
                                                               float* __restrict__ y, const FwdPlan pl) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* pl_base = smem;                                                 // [2][Cin/8][128][16 B]
@@ -273,7 +289,7 @@ __global__ void __launch_bounds__(NTHREADS) pw_fwd_tma_kernel(const __grid_const
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Cin = pl.Cin, Cout = pl.Cout, HW = pl.HW;
 
-  for (int i = tid; i < pl.wbytes / 16; i += NTHREADS) reinterpret_cast<uint4*>(w_base)[i] = __ldg(reinterpret_cast<const uint4*>(wpack) + i);
+  pack_weights_smem(w, w_base, pl.Cin, pl.Cout, false);     // forward: K = Cin, N = Cout
   if (tid == 0) {
     for (int i = 0; i < MAXST; ++i) {
       mbar_init(smem_u32(&raw_full[i]), 1);
@@ -530,11 +546,9 @@ int kmu_pwconv_tma_fwd(const kmu_pwconv_desc* d, const float* x, const float* w,
   CUtensorMap map_x;
   int rc = make_row_map(&map_x, x, (long long)d->B * d->Cin, d->HW, d->Cin);
   if (rc != KMU_OK) return rc;
-  launch_pack(w, wpack, d->Cin, d->Cout, d->Cout, 0, st);   // wpack[ks][gi][n][e] = W[n][ks*16 + gi*8 + e]
-  KMU_LAUNCH_CHECK("pw_tc_pack");
   cudaError_t e = cudaFuncSetAttribute(pw_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
   KMU_REQUIRE(e == cudaSuccess, KMU_ERR_LAUNCH, "pwconv_tma_fwd: cannot opt in to %zu B shared memory: %s", p.smem, cudaGetErrorString(e));
-  pw_fwd_tma_kernel<<<p.ctas, NTHREADS, p.smem, st>>>(map_x, wpack, bias, y, p);
+  pw_fwd_tma_kernel<<<p.ctas, NTHREADS, p.smem, st>>>(map_x, w, bias, y, p);
   KMU_LAUNCH_CHECK("pw_fwd_tma");
   return KMU_OK;
 }
@@ -566,13 +580,10 @@ int kmu_pwconv_fused_bwd(const kmu_pwconv_desc* d, const float* x, const float* 
   if (rc != KMU_OK) return rc;
   rc = make_row_map(&map_dy, dy, (long long)d->B * d->Cout, d->HW, d->Cout);
   if (rc != KMU_OK) return rc;
-  // dgrad weights: K = Cout, N = Cin  (wpack[ks][gi][n][e] = W[ks*16 + gi*8 + e][n])
-  launch_pack(w, wpack, d->Cout, d->Cin, d->Cin, 1, st);
-  KMU_LAUNCH_CHECK("pw_tc_pack");
   cudaError_t e = cudaFuncSetAttribute(pw_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
   KMU_REQUIRE(e == cudaSuccess, KMU_ERR_LAUNCH, "pwconv_fused_bwd: cannot opt in to %zu B shared memory: %s", p.smem, cudaGetErrorString(e));
   const int ctas = ctas_for(*d);
-  pw_bwd_fused_kernel<<<ctas, NTHREADS, p.smem, st>>>(map_x, map_dy, wpack, dx, partial, p);
+  pw_bwd_fused_kernel<<<ctas, NTHREADS, p.smem, st>>>(map_x, map_dy, w, dx, partial, p);
   KMU_LAUNCH_CHECK("pw_bwd_fused");
   launch_wreduce(partial, ctas, p.MH, p.Np, d->Cin, d->Cout, dw, dbias, st);
   KMU_LAUNCH_CHECK("pw_wreduce_tc");
