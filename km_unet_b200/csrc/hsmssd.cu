@@ -46,7 +46,9 @@ constexpr int N3 = 192;       // projected channels
 constexpr int TH = 8, TW = 32, HW_ = TW + 2, HH_ = TH + 2, NHALO = HW_ * HH_;  // spatial tile + 1-pixel halo (340)
 constexpr int SUB = 256;      // positions per sub-tile in the over-L sweeps
 constexpr int SUBS_PER_CTA = 2;
-constexpr int GT = 512;      // threads of the per-batch (C,64) gate kernels
+constexpr int GT = 256;      // threads of the per-batch (C,64) gate kernels
+constexpr int GNS = 4;       // ... which split the 64 state columns over GNS CTAs per batch element (the gate is column-wise
+constexpr int GCW = 64 / GNS; //     independent; sums over columns become per-CTA partials): 4x the CTAs on a latency-bound kernel
 
 struct Dims {
   int B, C, L, H;
@@ -250,14 +252,14 @@ __global__ void __launch_bounds__(GT) hsm_combine_gate_kernel(const float* __res
                                                               float* __restrict__ hz_out, float* __restrict__ ho_out, Dims d) {
   extern __shared__ __align__(16) float smem[];
   const int C = d.C;
-  constexpr int CG = GT / 64;
+  constexpr int CG = GT / GCW;
   float* hs_s = smem;                  // [C][64]
   float* hz_s = hs_s + C * 64;         // [2C][64]
   float* v_s = hz_s + 2 * C * 64;      // [C][64]
   float* whz_s = v_s + C * 64;         // [2C][C]
   float* wo_s = whz_s + 2 * C * C;     // [C][C]
   float* sc_s = wo_s + C * C;          // [T][64] exp(m_t - m)
-  const int tid = threadIdx.x, n = tid & 63, cg = tid >> 6, b = blockIdx.x;
+  const int tid = threadIdx.x, n = blockIdx.y * GCW + (tid & (GCW - 1)), cg = tid / GCW, b = blockIdx.x;
   for (int i = tid; i < 2 * C * C; i += GT) whz_s[i] = whz[i];
   for (int i = tid; i < C * C; i += GT) wo_s[i] = wo[i];
   const float* pm = part_m + (size_t)b * d.T * 64 + n;
@@ -383,7 +385,7 @@ __global__ void __launch_bounds__(GT) hsm_gate_bwd_kernel(const float* __restric
                                                           float* __restrict__ wpart, Dims d) {
   extern __shared__ __align__(16) float smem[];
   const int C = d.C;
-  constexpr int CG = GT / 64;
+  constexpr int CG = GT / GCW;
   float* dho_s = smem;               // [C][64]
   float* v_s = dho_s + C * 64;       // [C][64]
   float* hs_s = v_s + C * 64;        // [C][64]
@@ -391,7 +393,7 @@ __global__ void __launch_bounds__(GT) hsm_gate_bwd_kernel(const float* __restric
   float* whz_s = dhz_s + 2 * C * 64; // [2C][C]
   float* wo_s = whz_s + 2 * C * C;   // [C][C]
   float* red_s = wo_s + C * C;       // [GT]
-  const int tid = threadIdx.x, n = tid & 63, cg = tid >> 6, b = blockIdx.x;
+  const int tid = threadIdx.x, nl = tid & (GCW - 1), n0 = blockIdx.y * GCW, n = n0 + nl, cg = tid / GCW, b = blockIdx.x;
   const float Dv = Dp[0];
   for (int i = tid; i < 2 * C * C; i += GT) whz_s[i] = whz[i];
   for (int i = tid; i < C * C; i += GT) wo_s[i] = wo[i];
@@ -434,10 +436,10 @@ __global__ void __launch_bounds__(GT) hsm_gate_bwd_kernel(const float* __restric
   if (cg == 0) {
     float a = 0.f;
 #pragma unroll
-    for (int g = 0; g < CG; ++g) a += red_s[g * 64 + n];
+    for (int g = 0; g < CG; ++g) a += red_s[g * GCW + nl];
     r_out[(size_t)b * 64 + n] = a;
   }
-  float* wb = wpart + (size_t)b * (3 * C * C + 1);
+  float* wb = wpart + ((size_t)b * GNS + blockIdx.y) * (3 * C * C + 1);   // partial over this CTA's GCW columns
   if (tid == 0) wb[3 * C * C] = dD_tot;
   // dWo[dd][c] = sum_n dho[dd][n] v[c][n] ; dWhz[dd][c] = sum_n dhz[dd][n] hs[c][n]
   for (int i = tid; i < 3 * C * C; i += GT) {
@@ -445,8 +447,8 @@ __global__ void __launch_bounds__(GT) hsm_gate_bwd_kernel(const float* __restric
     if (i < C * C) { ar = dho_s + (i / C) * 64; br = v_s + (i % C) * 64; }
     else { int k = i - C * C; ar = dhz_s + (k / C) * 64; br = hs_s + (k % C) * 64; }
     float a = 0.f;
-    for (int k = 0; k < 64; ++k) {
-      int nn = (k + tid) & 63;  // rotate the start so the 32 lanes hit 32 different banks
+    for (int k = 0; k < GCW; ++k) {
+      int nn = n0 + ((k + tid) & (GCW - 1));  // rotate the start so that neighbouring lanes hit different banks
       a = fmaf(ar[nn], br[nn], a);
     }
     wb[i] = a;
@@ -918,7 +920,7 @@ static BwdWs bwd_ws(const Dims& d, int precision) {
   w.part_dho = o; o += align_up((size_t)d.B * d.T * d.C * 64 * 4, 256);
   w.dhs = o; o += align_up((size_t)d.B * d.C * 64 * 4, 256);
   w.r = o; o += align_up((size_t)d.B * 64 * 4, 256);
-  w.wpart = o; o += align_up((size_t)d.B * (3 * d.C * d.C + 1) * 4, 256);
+  w.wpart = o; o += align_up((size_t)d.B * GNS * (3 * d.C * d.C + 1) * 4, 256);
   if (precision == KMU_PREC_BF16) {  // dP as bf16 planes; tpart = the tcgen05 backward's own workspace
     w.dP = o; o += tcb::dpp_bytes(d.B, d.L);
     w.tpart = o; o += tcb::workspace_bytes(d.B, d.C, d.H);
@@ -1007,7 +1009,7 @@ int kmu_hsmssd_fwd(const kmu_hsmssd_fwd_args* a, kmu_stream stream) {
     size_t smem = ((size_t)4 * d.C * 64 + (size_t)3 * d.C * d.C + (size_t)d.T * 64) * 4;
     KMU_REQUIRE(smem <= 220 * 1024, KMU_ERR_UNSUPPORTED, "hsmssd_fwd: L=%d too long for the per-batch combine (T=%d)", d.L, d.T);
     opt_in_smem(hsm_combine_gate_kernel, smem);
-    hsm_combine_gate_kernel<<<d.B, GT, smem, st>>>(part_m, part_s, part_hs, a->w_hz, a->w_out, a->D, a->stats, a->hs, a->hz,
+    hsm_combine_gate_kernel<<<dim3(d.B, GNS), GT, smem, st>>>(part_m, part_s, part_hs, a->w_hz, a->w_out, a->D, a->stats, a->hs, a->hz,
                                                     a->h, d);
     KMU_LAUNCH_CHECK("hsm_combine_gate");
   }
@@ -1067,10 +1069,10 @@ int kmu_hsmssd_bwd(const kmu_hsmssd_bwd_args* a, kmu_stream stream) {
   {
     size_t smem = ((size_t)5 * C * 64 + (size_t)3 * C * C + GT) * 4;
     opt_in_smem(hsm_gate_bwd_kernel, smem);
-    hsm_gate_bwd_kernel<<<d.B, GT, smem, st>>>(part_dho, a->dh, a->hs, a->hz, a->w_hz, a->w_out, a->D, dhs, r, wpart, dg);
+    hsm_gate_bwd_kernel<<<dim3(d.B, GNS), GT, smem, st>>>(part_dho, a->dh, a->hs, a->hz, a->w_hz, a->w_out, a->D, dhs, r, wpart, dg);
     KMU_LAUNCH_CHECK("hsm_gate_bwd");
     int n = 3 * C * C + 1;
-    hsm_wgrad_reduce_kernel<<<cdiv(n, 32), 256, 0, st>>>(wpart, d.B, n, a->d_w_out, C * C, a->d_w_hz, 2 * C * C, a->d_D, 1);
+    hsm_wgrad_reduce_kernel<<<cdiv(n, 32), 256, 0, st>>>(wpart, d.B * GNS, n, a->d_w_out, C * C, a->d_w_hz, 2 * C * C, a->d_D, 1);
     KMU_LAUNCH_CHECK("hsm_wgrad_reduce(gate)");
   }
   {
