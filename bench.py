@@ -126,6 +126,9 @@ def op_work(name, key):
     if name.startswith("kmu_hsmssd"):
         B, C, L = key
         return ("hbm", (8.0 if name.endswith("fwd") else 16.0) * B * C * L, "byte")
+    if name.startswith("kmu_resize_bilinear"):
+        B, C, H, W, OH, OW = key
+        return ("hbm", 4.0 * B * C * (H * W + OH * OW), "byte")
     if name.startswith("kmu_combine3"):
         B, n = key                           # fwd: read x, f0..f2, write out; bwd: read dy, f0..f2, write df0..df2
         return ("hbm", (20.0 if name.endswith("fwd") else 28.0) * B * n, "byte")
@@ -420,6 +423,9 @@ def run_model(h, args):
     K.config.conv_bwd = "fused" if args.precision == "bf16" else "split"
     K.config.conv_fwd = "tma" if args.precision == "bf16" else "simt"
     torch.backends.cudnn.benchmark = True                 # as the reference's training script does (train_shanghai.py:331)
+    # the loss' SSIM filter (two banded GEMMs) and the small nn.Linear layers: TF32 tensor-core GEMMs in the tensor-core precision
+    # class -- the reference computes all of them in fp16 (its loss sits inside autocast, train_shanghai.py:172-174)
+    torch.backends.cuda.matmul.allow_tf32 = args.precision == "bf16"
     _lib.lib()                                            # fail loudly if the extension is missing
     metric, desc, variant, classes, fin, size, default_b, train = WORKLOADS[args.workload]
     B = args.batch or default_b
@@ -576,7 +582,7 @@ def run_model(h, args):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * world, "frames": f"{fin}->{classes}",
-                       "size": size, "precision": (f"KANConv2d, the HSM-SSD projection (forward, dgrad, wgrad) and the 1x1-convolution backward {args.precision} (tcgen05), everything else fp32"
+                       "size": size, "precision": (f"KANConv2d, the HSM-SSD projection (forward, dgrad, wgrad) and the 1x1-convolution backward {args.precision} (tcgen05), torch GEMMs (SSIM filter of the loss, nn.Linear) TF32, everything else fp32"
                                      if args.precision == "bf16" else "fp32 everywhere"),
                        "parallelism": f"dp{world}", "cuda_graph": bool(graphed is not None), "optimizer": "AdamW(lr 1e-3, wd 0.05, fused)" if train else None,
                        "l2": "activations per step (hundreds of %.0f MB tensors) exceed the 126 MB L2" % (B * 16 * size * size * 4 / 1e6),

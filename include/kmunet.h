@@ -438,6 +438,10 @@ int kmu_qkv_gate_bwd(const float* qkv, const float* dout, float* dqkv, int32_t B
  *     out[b] = x[b] + sum_i coef[b][i] f_i[b],   coef (B,3) = softmax gate weight x per-sample DropPath factor (built by the caller);
  * backward: df_i = coef[b][i] dy, dcoef[b][i] = sum dy . f_i (per-CTA partials reduced in fixed order); dx = dy is the caller's.
  * n_per_b = C*H*W elements per sample, a multiple of 4. */
+/* kmu_resize_bilinear_ac: F.interpolate(x, size, mode='bilinear', align_corners=True) of the skip connections
+ * (KM_UNetV3_SH.py:493-512), forward; x (planes, H, W) -> out (planes, OH, OW).  The backward stays ATen's. */
+int kmu_resize_bilinear_ac_fwd(const float* x, float* out, int64_t planes, int32_t H, int32_t W, int32_t OH, int32_t OW,
+                               kmu_stream stream);
 size_t kmu_combine3_bwd_workspace_bytes(int32_t B, int64_t n_per_b);
 int kmu_combine3_fwd(const float* x, const float* f0, const float* f1, const float* f2, const float* coef, float* out, int32_t B,
                      int64_t n_per_b, kmu_stream stream);

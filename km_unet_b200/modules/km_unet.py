@@ -264,8 +264,11 @@ class KM_UNetV3(nn.Module):
 
     @staticmethod
     def _skips(e1, e2, size):
-        r1 = F.interpolate(e1, size=size, mode='bilinear', align_corners=True)
-        r2 = F.interpolate(e2, size=size, mode='bilinear', align_corners=True)
+        if e1.is_cuda:
+            r1, r2 = ops.resize_bilinear_ac(e1, size), ops.resize_bilinear_ac(e2, size)
+        else:                           # CPU oracle runs (oracle/model.py swaps the CUDA entry points, not this torch call)
+            r1 = F.interpolate(e1, size=size, mode='bilinear', align_corners=True)
+            r2 = F.interpolate(e2, size=size, mode='bilinear', align_corners=True)
         return [r1, r2, r2]            # the reference feeds e2 twice (KM_UNetV3_SH.py:495)
 
     def forward(self, x):

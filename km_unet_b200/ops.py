@@ -12,7 +12,7 @@ from . import _lib
 from ._lib import (ScDesc, TnBwdArgs, TnDesc, TnFwdArgs, PwDesc, BnMixBwdArgs, BnMixDesc, BnMixFwdArgs, DwDesc, DagemBn, DagemBwdArgs, DagemDesc, DagemFwdArgs, DysBwdArgs, DysDesc, DysFwdArgs, HsmBwdArgs, HsmDesc, HsmFwdArgs, KanBwdArgs, KanDesc, KanFwdArgs,
                    KMU_PREC_BF16, KMU_PREC_FP32, check, ptr, stream_ptr)
 
-__all__ = ["kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dysample_sample", "dagem_gate", "bnmix", "dwconv3x3", "pwconv", "pwconv_supported", "triplenorm", "qkv_gate", "smallconv", "smallconv_supported", "iwp", "iwp_supported", "combine3", "combine3_supported", "KMU_PREC_FP32", "KMU_PREC_BF16"]
+__all__ = ["kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dysample_sample", "dagem_gate", "bnmix", "dwconv3x3", "pwconv", "pwconv_supported", "triplenorm", "qkv_gate", "smallconv", "smallconv_supported", "iwp", "iwp_supported", "combine3", "combine3_supported", "resize_bilinear_ac", "KMU_PREC_FP32", "KMU_PREC_BF16"]
 
 
 # ------------------------------------------------------------------------------------------------------ op-level timing
@@ -694,6 +694,35 @@ def qkv_gate(qkv):
     if not qkv.is_cuda:
         raise RuntimeError("km_unet_b200.qkv_gate: CUDA tensors only (no CPU fallback)")
     return _QkvGateFn.apply(qkv)
+
+
+class _ResizeBilinearAcFn(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, size):
+        lib = _lib.lib()
+        x = x.contiguous()
+        B, Cc, H, W = x.shape
+        OH, OW = int(size[0]), int(size[1])
+        out = torch.empty(B, Cc, OH, OW, dtype=torch.float32, device=x.device)
+        check(_call("kmu_resize_bilinear_ac_fwd", (B, Cc, H, W, OH, OW), lib.kmu_resize_bilinear_ac_fwd, ptr(x), ptr(out), B * Cc, H, W,
+                    OH, OW, stream_ptr()), "kmu_resize_bilinear_ac_fwd")
+        ctx.in_size, ctx.out_size = (B, Cc, H, W), (OH, OW)
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dout):
+        # the library's own backward kernel (one thread per gradient element) is adequate; only the forward needed replacing
+        dx = torch.ops.aten.upsample_bilinear2d_backward(dout.contiguous(), list(ctx.out_size), list(ctx.in_size), True, None, None)
+        return dx, None
+
+
+def resize_bilinear_ac(x, size):
+    """F.interpolate(x, size=size, mode='bilinear', align_corners=True) (the skip-connection resizes of KM_UNetV3.forward)."""
+    if not x.is_cuda:
+        raise RuntimeError("km_unet_b200.resize_bilinear_ac: CUDA tensors only (no CPU fallback)")
+    return _ResizeBilinearAcFn.apply(x, tuple(size))
 
 
 class _Combine3Fn(torch.autograd.Function):

@@ -344,3 +344,20 @@ def test_combine3_vs_torch(B, C, H, W):
     for a, b in zip(tc, td):
         assert rel_err(a.grad, b.grad) < TOL
     assert rel_err(cc.grad, cd.grad) < TOL
+
+
+@pytest.mark.parametrize("B,C,H,W,OH,OW", [(2, 16, 64, 64, 32, 32), (3, 32, 32, 32, 64, 64), (2, 8, 17, 23, 9, 40), (1, 4, 8, 8, 1, 1)])
+def test_resize_bilinear_align_corners_vs_torch(B, C, H, W, OH, OW):
+    """F.interpolate(bilinear, align_corners=True) forward kernel + gradient (ATen's backward) vs torch on the CPU."""
+    from km_unet_b200 import ops
+    torch.manual_seed(H + OW)
+    x = torch.randn(B, C, H, W)
+    xd = x.double().requires_grad_(True)
+    want = F.interpolate(xd, size=(OH, OW), mode="bilinear", align_corners=True)
+    g = torch.randn(B, C, OH, OW)
+    want.backward(g.double())
+    xc = x.cuda().requires_grad_(True)
+    y = ops.resize_bilinear_ac(xc, (OH, OW))
+    assert rel_err(y, want) < 1e-5
+    y.backward(g.cuda())
+    assert rel_err(xc.grad, xd.grad) < 1e-5

@@ -14,6 +14,7 @@ K.config.kan_precision = "bf16"
 K.config.hsm_precision = "bf16"
 K.config.conv_bwd = "fused"
 K.config.conv_fwd = "tma"
+torch.backends.cuda.matmul.allow_tf32 = True
 torch.backends.cudnn.benchmark = os.environ.get("KMU_CUDNN_BENCHMARK", "1") == "1"   # train_shanghai.py:331
 torch.manual_seed(1234)
 m = K.KM_UNetV3_SH(num_classes=20).cuda().train()
