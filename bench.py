@@ -126,6 +126,9 @@ def op_work(name, key):
     if name.startswith("kmu_hsmssd"):
         B, C, L = key
         return ("hbm", (8.0 if name.endswith("fwd") else 16.0) * B * C * L, "byte")
+    if name.startswith("kmu_groupnorm"):
+        B, C, HW, G = key                    # statistics pass + apply pass: read x twice, write y
+        return ("hbm", 12.0 * B * C * HW, "byte")
     if name.startswith("kmu_resize_bilinear"):
         B, C, H, W, OH, OW = key
         return ("hbm", 4.0 * B * C * (H * W + OH * OW), "byte")

@@ -438,6 +438,12 @@ int kmu_qkv_gate_bwd(const float* qkv, const float* dout, float* dqkv, int32_t B
  *     out[b] = x[b] + sum_i coef[b][i] f_i[b],   coef (B,3) = softmax gate weight x per-sample DropPath factor (built by the caller);
  * backward: df_i = coef[b][i] dy, dcoef[b][i] = sum dy . f_i (per-CTA partials reduced in fixed order); dx = dy is the caller's.
  * n_per_b = C*H*W elements per sample, a multiple of 4. */
+/* kmu_groupnorm_fwd: nn.GroupNorm forward (StableHybridKANConv.pre_norm KM_UNetV3_SH.py:72-94, MultiScaleFusion :292, output norm
+ * :455): y = (x - mean_g) rstd_g gamma_c + beta_c, statistics over (C/G, HW) per sample and group; mean / rstd (B*G) are outputs for
+ * the backward (ATen's native_group_norm_backward takes them).  HW a multiple of 4. */
+size_t kmu_groupnorm_fwd_workspace_bytes(int32_t B, int32_t C, int64_t HW, int32_t G);
+int kmu_groupnorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd, int32_t B, int32_t C,
+                      int64_t HW, int32_t G, float eps, void* workspace, size_t workspace_bytes, kmu_stream stream);
 /* kmu_resize_bilinear_ac: F.interpolate(x, size, mode='bilinear', align_corners=True) of the skip connections
  * (KM_UNetV3_SH.py:493-512), forward; x (planes, H, W) -> out (planes, OH, OW).  The backward stays ATen's. */
 int kmu_resize_bilinear_ac_fwd(const float* x, float* out, int64_t planes, int32_t H, int32_t W, int32_t OH, int32_t OW,

@@ -579,6 +579,71 @@ __global__ void __launch_bounds__(256) resize_bilinear_ac_kernel(const float* __
   out[idx] = lh0 * (lw0 * __ldg(p) + lw1 * __ldg(p + wp)) + lh1 * (lw0 * __ldg(p + hp * W) + lw1 * __ldg(p + hp * W + wp));
 }
 
+// ---------------------------------------------------------------------------------------------- GroupNorm forward
+// nn.GroupNorm of StableHybridKANConv.pre_norm (4 groups), MultiScaleFusion (1 group) and the output norm (KM_UNetV3_SH.py:72-94,
+// 292,455).  ATen's statistics kernel runs ONE CTA per (sample, group) -- 32 CTAs streaming 42 MB at the output norm; here every
+// (sample, group) row is split over GN_SPLIT CTAs, a tiny kernel finishes mean / rstd in double, the apply kernel is float4.
+// mean / rstd are returned so that the caller can hand them to the library's native_group_norm_backward.
+__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, float* __restrict__ part, long long row_len, int split) {
+  __shared__ float red[8];
+  const long long row = blockIdx.y;
+  const long long per = ((row_len / 4 + split - 1) / split) * 4;      // slice length, multiple of 4
+  const long long lo = (long long)blockIdx.x * per;
+  long long hi = lo + per;
+  if (hi > row_len) hi = row_len;
+  const float* p = x + row * row_len;
+  float s = 0.f, q = 0.f;
+  for (long long i = lo + 4 * threadIdx.x; i < hi; i += 1024) {
+    const float4 v = *reinterpret_cast<const float4*>(p + i);
+    s += (v.x + v.y) + (v.z + v.w);
+    q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  s = block_sum256(s, red);
+  q = block_sum256(q, red);
+  if (threadIdx.x == 0) {
+    part[(row * split + blockIdx.x) * 2] = s;
+    part[(row * split + blockIdx.x) * 2 + 1] = q;
+  }
+}
+
+__global__ void gn_fin_kernel(const float* __restrict__ part, float* __restrict__ mean, float* __restrict__ rstd, int rows, int split,
+                              double inv_n, float eps) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < split; ++k) {
+    s += (double)part[((size_t)row * split + k) * 2];
+    q += (double)part[((size_t)row * split + k) * 2 + 1];
+  }
+  const double m = s * inv_n;
+  double var = q * inv_n - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[row] = (float)m;
+  rstd[row] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const float4* __restrict__ x, const float* __restrict__ mean,
+                                                       const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, float4* __restrict__ y, int C, int G, long long hw4,
+                                                       long long total4) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total4) return;
+  const long long plane = i / hw4;                 // b * C + c
+  const int c = (int)(plane % C);
+  const long long row = (plane / C) * G + c / (C / G);
+  const float m = __ldg(mean + row), r = __ldg(rstd + row);
+  const float a = r * (gamma ? __ldg(gamma + c) : 1.f), b = (beta ? __ldg(beta + c) : 0.f) - m * a;
+  const float4 v = __ldg(x + i);
+  y[i] = make_float4(fmaf(v.x, a, b), fmaf(v.y, a, b), fmaf(v.z, a, b), fmaf(v.w, a, b));
+}
+
+static int gn_split(int rows, long long row_len) {
+  int split = (148 * 4 + rows - 1) / rows;
+  const long long maxs = (row_len + 4095) / 4096;
+  if (split > maxs) split = (int)maxs;
+  return split < 1 ? 1 : split;
+}
+
 static int combine3_chunks(int B, long long n4_per_b) {
   int chunks = (148 * 8 + B - 1) / B;
   const long long maxc = (n4_per_b + 1023) / 1024;
@@ -754,6 +819,31 @@ int kmu_resize_bilinear_ac_fwd(const float* x, float* out, int64_t planes, int32
   const long long total = (long long)planes * OH * OW;
   kmu::glue::resize_bilinear_ac_kernel<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, out, planes, H, W, OH, OW, sh, sw);
   KMU_LAUNCH_CHECK("resize_bilinear_ac_fwd");
+  return KMU_OK;
+}
+
+size_t kmu_groupnorm_fwd_workspace_bytes(int32_t B, int32_t C, int64_t HW, int32_t G) {
+  if (B <= 0 || C <= 0 || HW <= 0 || G <= 0 || C % G) return 0;
+  return align_up((size_t)B * G * kmu::glue::gn_split(B * G, (long long)(C / G) * HW) * 2 * 4, 256);
+}
+
+int kmu_groupnorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd, int32_t B, int32_t C,
+                      int64_t HW, int32_t G, float eps, void* workspace, size_t workspace_bytes, kmu_stream stream) {
+  KMU_REQUIRE(x && y && mean && rstd && B > 0 && C > 0 && HW > 0 && G > 0 && C % G == 0, KMU_ERR_BAD_ARG, "groupnorm_fwd: bad argument");
+  KMU_REQUIRE((HW & 3) == 0 && (long long)B * G <= 65535, KMU_ERR_UNSUPPORTED, "groupnorm_fwd: HW must be a multiple of 4, B*G <= 65535");
+  KMU_REQUIRE(workspace && workspace_bytes >= kmu_groupnorm_fwd_workspace_bytes(B, C, HW, G), KMU_ERR_WORKSPACE, "groupnorm_fwd: workspace too small");
+  const int rows = B * G;
+  const long long row_len = (long long)(C / G) * HW;
+  const int split = kmu::glue::gn_split(rows, row_len);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* part = (float*)workspace;
+  kmu::glue::gn_stats_kernel<<<dim3(split, rows), 256, 0, st>>>(x, part, row_len, split);
+  KMU_LAUNCH_CHECK("gn_stats");
+  kmu::glue::gn_fin_kernel<<<cdiv(rows, 128), 128, 0, st>>>(part, mean, rstd, rows, split, 1.0 / (double)row_len, eps);
+  KMU_LAUNCH_CHECK("gn_fin");
+  const long long total4 = (long long)B * C * HW / 4;
+  kmu::glue::gn_apply_kernel<<<(unsigned)cdiv(total4, 256), 256, 0, st>>>((const float4*)x, mean, rstd, gamma, beta, (float4*)y, C, G, HW / 4, total4);
+  KMU_LAUNCH_CHECK("gn_apply");
   return KMU_OK;
 }
 

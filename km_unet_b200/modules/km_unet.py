@@ -25,10 +25,17 @@ from .kan import KANConv2d
 from .vim import EfficientViMBlock, conv1x1, conv_same
 
 
+def group_norm(m, x):
+    """nn.GroupNorm forward through kmu_groupnorm_fwd on the GPU (CPU oracle runs keep the torch module)."""
+    if ops.groupnorm_supported(x):
+        return ops.groupnorm(x, m.weight, m.bias, m.num_groups, m.eps)
+    return m(x)
+
+
 def _run(seq, x):
-    """nn.Sequential forward with the plain convolutions routed through the streaming CUDA kernels where they apply."""
+    """nn.Sequential forward with the plain convolutions / GroupNorms routed through the CUDA kernels where they apply."""
     for m in seq:
-        x = conv_same(m, x) if type(m) is nn.Conv2d else m(x)
+        x = conv_same(m, x) if type(m) is nn.Conv2d else (group_norm(m, x) if type(m) is nn.GroupNorm else m(x))
     return x
 
 
@@ -67,7 +74,7 @@ class StableHybridKANConv(nn.Module):
                     nn.init.zeros_(m.bias)
 
     def forward(self, x):
-        x = self.pre_norm(x)
+        x = group_norm(self.pre_norm, x)
         identity = x if isinstance(self.residual, nn.Identity) else conv1x1(x, self.residual.weight, self.residual.bias)
         return self.post_act(identity + self.kanconv2d(x))
 
@@ -282,7 +289,7 @@ class KM_UNetV3(nn.Module):
         d1 = torch.cat([d1, self.attention1(self._skips(e1, e2, d1.shape[2:]))], dim=1)
         d2 = _run(self.dec2, d1)
         d2 = torch.cat([d2, self.attention2(self._skips(e1, e2, d2.shape[2:]))], dim=1)
-        return self.activation(self.output_norm(_run(self.dec3, d2)))
+        return self.activation(group_norm(self.output_norm, _run(self.dec3, d2)))
 
 
 def KM_UNetV3_SH(num_classes=3, embed_dims=(16, 32, 64)):

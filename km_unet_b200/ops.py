@@ -12,7 +12,7 @@ from . import _lib
 from ._lib import (ScDesc, TnBwdArgs, TnDesc, TnFwdArgs, PwDesc, BnMixBwdArgs, BnMixDesc, BnMixFwdArgs, DwDesc, DagemBn, DagemBwdArgs, DagemDesc, DagemFwdArgs, DysBwdArgs, DysDesc, DysFwdArgs, HsmBwdArgs, HsmDesc, HsmFwdArgs, KanBwdArgs, KanDesc, KanFwdArgs,
                    KMU_PREC_BF16, KMU_PREC_FP32, check, ptr, stream_ptr)
 
-__all__ = ["kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dysample_sample", "dagem_gate", "bnmix", "dwconv3x3", "pwconv", "pwconv_supported", "triplenorm", "qkv_gate", "smallconv", "smallconv_supported", "iwp", "iwp_supported", "combine3", "combine3_supported", "resize_bilinear_ac", "KMU_PREC_FP32", "KMU_PREC_BF16"]
+__all__ = ["kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dysample_sample", "dagem_gate", "bnmix", "dwconv3x3", "pwconv", "pwconv_supported", "triplenorm", "qkv_gate", "smallconv", "smallconv_supported", "iwp", "iwp_supported", "combine3", "combine3_supported", "resize_bilinear_ac", "groupnorm", "groupnorm_supported", "KMU_PREC_FP32", "KMU_PREC_BF16"]
 
 
 # ------------------------------------------------------------------------------------------------------ op-level timing
@@ -694,6 +694,47 @@ def qkv_gate(qkv):
     if not qkv.is_cuda:
         raise RuntimeError("km_unet_b200.qkv_gate: CUDA tensors only (no CPU fallback)")
     return _QkvGateFn.apply(qkv)
+
+
+class _GroupNormFn(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, weight, bias, groups, eps):
+        lib = _lib.lib()
+        x = x.contiguous()
+        B, Cc = x.shape[0], x.shape[1]
+        HW = x.numel() // (B * Cc)
+        y = torch.empty_like(x)
+        mean = torch.empty(B, groups, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(B, groups, dtype=torch.float32, device=x.device)
+        ws = _workspace(lib.kmu_groupnorm_fwd_workspace_bytes(B, Cc, HW, groups), x.device)
+        w = None if weight is None else weight.contiguous()
+        b = None if bias is None else bias.contiguous()
+        check(_call("kmu_groupnorm_fwd", (B, Cc, HW, groups), lib.kmu_groupnorm_fwd, ptr(x), ptr(w), ptr(b), ptr(y), ptr(mean), ptr(rstd),
+                    B, Cc, HW, groups, float(eps), ws.data_ptr(), ws.numel(), stream_ptr()), "kmu_groupnorm_fwd")
+        ctx.save_for_backward(x, w, mean, rstd)
+        ctx.dims = (B, Cc, HW, groups)
+        return y
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        x, w, mean, rstd = ctx.saved_tensors
+        B, Cc, HW, groups = ctx.dims
+        mask = [ctx.needs_input_grad[0], w is not None and ctx.needs_input_grad[1], w is not None and ctx.needs_input_grad[2]]
+        dx, dw, db = torch.ops.aten.native_group_norm_backward(dy.contiguous(), x, mean, rstd, w, B, Cc, HW, groups, mask)
+        return dx, dw, db, None, None
+
+
+def groupnorm_supported(x):
+    return x.is_cuda and x.dim() >= 3 and (x.numel() // (x.shape[0] * x.shape[1])) % 4 == 0
+
+
+def groupnorm(x, weight, bias, groups, eps=1e-5):
+    """nn.GroupNorm forward with split statistics CTAs; backward = the library's native_group_norm_backward on the saved mean / rstd."""
+    if not x.is_cuda:
+        raise RuntimeError("km_unet_b200.groupnorm: CUDA tensors only (no CPU fallback)")
+    return _GroupNormFn.apply(x, weight, bias, int(groups), float(eps))
 
 
 class _ResizeBilinearAcFn(torch.autograd.Function):

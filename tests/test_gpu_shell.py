@@ -361,3 +361,23 @@ def test_resize_bilinear_align_corners_vs_torch(B, C, H, W, OH, OW):
     assert rel_err(y, want) < 1e-5
     y.backward(g.cuda())
     assert rel_err(xc.grad, xd.grad) < 1e-5
+
+
+@pytest.mark.parametrize("B,C,H,W,G", [(2, 16, 32, 32, 4), (3, 32, 12, 10, 1), (32, 20, 128, 128, 1), (4, 64, 16, 16, 4)])
+def test_groupnorm_vs_torch(B, C, H, W, G):
+    """kmu_groupnorm_fwd (split statistics) + the library backward on its mean / rstd vs torch.nn.functional.group_norm in fp64."""
+    from km_unet_b200 import ops
+    torch.manual_seed(B + C + H)
+    x = torch.randn(B, C, H, W) * 1.7 + 0.6
+    w, b = torch.randn(C), torch.randn(C)
+    g = torch.randn(B, C, H, W)
+    xd, wd, bd = x.double().requires_grad_(True), w.double().requires_grad_(True), b.double().requires_grad_(True)
+    want = F.group_norm(xd, G, wd, bd, 1e-5)
+    want.backward(g.double())
+    xc, wc, bc = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    y = ops.groupnorm(xc, wc, bc, G, 1e-5)
+    assert rel_err(y, want) < TOL
+    y.backward(g.cuda())
+    assert rel_err(xc.grad, xd.grad) < TOL
+    assert rel_err(wc.grad, wd.grad) < TOL
+    assert rel_err(bc.grad, bd.grad) < TOL
