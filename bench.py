@@ -126,6 +126,13 @@ def op_work(name, key):
     if name.startswith("kmu_hsmssd"):
         B, C, L = key
         return ("hbm", (8.0 if name.endswith("fwd") else 16.0) * B * C * L, "byte")
+    if name.startswith("kmu_hybridloss"):
+        n = 1
+        for v in key:
+            n *= v                           # stats: read p, t; stack: + write 5 maps; ssim: 5 + 3 filtered maps; bwd: p, t, 3 maps, dp
+        per = {"kmu_hybridloss_stats": 8.0, "kmu_hybridloss_stack": 28.0, "kmu_hybridloss_ssim": 32.0 * (118.0 / 128.0) ** 2,
+               "kmu_hybridloss_bwd": 24.0}[name]
+        return ("hbm", per * n, "byte")
     if name.startswith("kmu_groupnorm"):
         B, C, HW, G = key                    # statistics pass + apply pass: read x twice, write y
         return ("hbm", 12.0 * B * C * HW, "byte")

@@ -438,6 +438,19 @@ int kmu_qkv_gate_bwd(const float* qkv, const float* dout, float* dqkv, int32_t B
  *     out[b] = x[b] + sum_i coef[b][i] f_i[b],   coef (B,3) = softmax gate weight x per-sample DropPath factor (built by the caller);
  * backward: df_i = coef[b][i] dy, dcoef[b][i] = sum dy . f_i (per-CTA partials reduced in fixed order); dx = dy is the caller's.
  * n_per_b = C*H*W elements per sample, a multiple of 4. */
+/* HybridLoss (train_shanghai.py:298-326, train_LAPS.py:347-375) as four streaming passes around the two
+ * banded GEMMs of the SSIM filter (which the caller runs): stats -> scal[8] (sums, minima, 1/range), stack -> the five maps
+ * (p_n, t_n, p_n^2, t_n^2, p_n t_n), ssim -> loss value + the three derivative maps that reach the prediction (d/dmu_p, d/dE[pp],
+ * d/dE[pt], already scaled by -(1 - alpha)/n_valid), bwd -> dpred from the back-filtered maps and grad_out (device scalar).
+ * n = elements of pred (multiple of 4), n_valid = elements of one filtered map. */
+size_t kmu_hybridloss_workspace_bytes(void);
+int kmu_hybridloss_stats(const float* pred, const float* target, int64_t n, float* scal, void* workspace, size_t workspace_bytes,
+                         kmu_stream stream);
+int kmu_hybridloss_stack(const float* pred, const float* target, const float* scal, float* stack5, int64_t n, kmu_stream stream);
+int kmu_hybridloss_ssim(const float* filtered5, const float* scal, float* gm3, float* loss_out, int64_t n_valid, int64_t n_full,
+                        float alpha, float c1, float c2, void* workspace, size_t workspace_bytes, kmu_stream stream);
+int kmu_hybridloss_bwd(const float* pred, const float* target, const float* scal, const float* dstack3, const float* grad_out,
+                       float* dpred, int64_t n, float alpha, kmu_stream stream);
 /* kmu_groupnorm_fwd: nn.GroupNorm forward (StableHybridKANConv.pre_norm KM_UNetV3_SH.py:72-94, MultiScaleFusion :292, output norm
  * :455): y = (x - mean_g) rstd_g gamma_c + beta_c, statistics over (C/G, HW) per sample and group; mean / rstd (B*G) are outputs for
  * the backward (ATen's native_group_norm_backward takes them).  HW a multiple of 4. */

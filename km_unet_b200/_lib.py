@@ -169,6 +169,12 @@ SYMBOLS = {
     "kmu_triplenorm_bwd": (C.c_int, [C.POINTER(TnBwdArgs), C.c_void_p]),
     "kmu_qkv_gate_fwd": (C.c_int, [_f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "kmu_qkv_gate_bwd": (C.c_int, [_f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "kmu_hybridloss_workspace_bytes": (C.c_size_t, []),
+    "kmu_hybridloss_stats": (C.c_int, [_f32p, _f32p, C.c_int64, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kmu_hybridloss_stack": (C.c_int, [_f32p, _f32p, _f32p, _f32p, C.c_int64, C.c_void_p]),
+    "kmu_hybridloss_ssim": (C.c_int, [_f32p, _f32p, _f32p, _f32p, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_void_p,
+                                      C.c_size_t, C.c_void_p]),
+    "kmu_hybridloss_bwd": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int64, C.c_float, C.c_void_p]),
     "kmu_groupnorm_fwd_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int64, C.c_int32]),
     "kmu_groupnorm_fwd": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_float,
                                     C.c_void_p, C.c_size_t, C.c_void_p]),
