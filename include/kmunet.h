@@ -359,6 +359,11 @@ int kmu_dwconv3x3_fwd(const kmu_dwconv3x3_desc* d, const float* x, const float* 
 /* dx, dw (C,9), dbias (C) are overwritten; dx == NULL skips the input gradient, dw == NULL the weight / bias gradients. */
 int kmu_dwconv3x3_bwd(const kmu_dwconv3x3_desc* d, const float* x, const float* dy, const float* w, float* dx, float* dw,
                       float* dbias, void* workspace, size_t workspace_bytes, kmu_stream stream);
+/* Backward with a residual gradient folded in: dx = conv^T(dy) + dx_add (dx may alias dx_add).  EfficientViMBlock feeds the same
+ * tensor to the depthwise convolution and to the layer-scale mix behind it (efficient_vim_init.py:85,93): the mix's d(res) joins the
+ * convolution's input gradient here instead of in a separate add kernel. */
+int kmu_dwconv3x3_bwd_add(const kmu_dwconv3x3_desc* d, const float* x, const float* dy, const float* w, const float* dx_add, float* dx,
+                          float* dw, float* dbias, void* workspace, size_t workspace_bytes, kmu_stream stream);
 /* The same convolution followed by a per-(b, c) factor: y = scale[b, c] * (conv(x) + bias) -- DirectionAttention's
  * `self.conv(attn) * weight[:, :, None, None]` (KM_UNetV3_SH.py:130-151) without the broadcast multiply and its three backward
  * kernels.  scale is (B, C); dscale (B, C) = sum_hw dy * (conv + bias) falls out of the weight-gradient partials. */

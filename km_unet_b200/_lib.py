@@ -157,6 +157,8 @@ SYMBOLS = {
     "kmu_dwconv3x3_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(DwDesc)]),
     "kmu_dwconv3x3_fwd": (C.c_int, [C.POINTER(DwDesc), _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
     "kmu_dwconv3x3_bwd": (C.c_int, [C.POINTER(DwDesc), _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kmu_dwconv3x3_bwd_add": (C.c_int, [C.POINTER(DwDesc), _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p, C.c_size_t,
+                                        C.c_void_p]),
     "kmu_dwconv3x3_scaled_fwd": (C.c_int, [C.POINTER(DwDesc), _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
     "kmu_dwconv3x3_scaled_bwd": (C.c_int, [C.POINTER(DwDesc), _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p,
                                            C.c_size_t, C.c_void_p]),

@@ -273,10 +273,11 @@ struct DwDims {
 // y[b,c,h,w] = bias[c] + sum_{ky,kx} w[c][ky*3+kx] x[b,c,h+ky-1,w+kx-1] (zero padding).  FLIP: correlate with the flipped
 // kernel (= the input gradient of the same convolution).  Thread = 4 consecutive output columns of one row.
 // scale (optional, one factor per (b, c) plane) multiplies the result: y = scale * (conv + bias) forward, dx = scale * conv^T(dy).
+// add (optional, may alias y) is added to the result: the residual branch's gradient joins dx here instead of in a separate kernel.
 template <bool FLIP>
 __global__ void __launch_bounds__(256) dw3x3_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                     const float* __restrict__ bias, const float* __restrict__ scale,
-                                                    float* __restrict__ y, DwDims d) {
+                                                    const float* add, float* y, DwDims d) {
   const int wq = (d.W + 3) >> 2;
   long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   long long total = (long long)d.B * d.C * d.H * wq;
@@ -319,6 +320,17 @@ __global__ void __launch_bounds__(256) dw3x3_kernel(const float* __restrict__ x,
     for (int e = 0; e < 4; ++e) acc[e] *= sc;
   }
   float* yp = y + (size_t)plane * d.H * d.W + (size_t)h * d.W + w0;
+  if (add) {
+    const float* ap = add + (size_t)plane * d.H * d.W + (size_t)h * d.W + w0;
+    if (vec) {
+      const float4 m = *reinterpret_cast<const float4*>(ap);
+      acc[0] += m.x; acc[1] += m.y; acc[2] += m.z; acc[3] += m.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (w0 + e < d.W) acc[e] += ap[e];
+    }
+  }
   if (vec) {
     *reinterpret_cast<float4*>(yp) = make_float4(acc[0], acc[1], acc[2], acc[3]);
   } else {
@@ -514,13 +526,14 @@ static int dw_fwd(const kmu_dwconv3x3_desc* dd, const float* x, const float* w, 
   KMU_REQUIRE(x && w && y, KMU_ERR_BAD_ARG, "dwconv3x3_fwd: null tensor");
   DwDims d{dd->B, dd->C, dd->H, dd->W};
   long long total = (long long)d.B * d.C * d.H * ((d.W + 3) / 4);
-  dw3x3_kernel<false><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, w, bias, scale, y, d);
+  dw3x3_kernel<false><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, w, bias, scale, nullptr, y, d);
   KMU_LAUNCH_CHECK("dw3x3_fwd");
   return KMU_OK;
 }
 
 static int dw_bwd(const kmu_dwconv3x3_desc* dd, const float* x, const float* dy, const float* w, const float* bias, const float* scale,
-                  float* dx, float* dw, float* dbias, float* dscale, void* workspace, size_t workspace_bytes, kmu_stream stream) {
+                  const float* dx_add, float* dx, float* dw, float* dbias, float* dscale, void* workspace, size_t workspace_bytes,
+                  kmu_stream stream) {
   int rc = dw_check(dd, "dwconv3x3_bwd");
   if (rc != KMU_OK) return rc;
   KMU_REQUIRE(x && dy && w, KMU_ERR_BAD_ARG, "dwconv3x3_bwd: null tensor");
@@ -528,7 +541,7 @@ static int dw_bwd(const kmu_dwconv3x3_desc* dd, const float* x, const float* dy,
   cudaStream_t st = (cudaStream_t)stream;
   if (dx) {
     long long total = (long long)d.B * d.C * d.H * ((d.W + 3) / 4);
-    dw3x3_kernel<true><<<cdiv(total, 256), 256, 0, st>>>(dy, w, nullptr, scale, dx, d);
+    dw3x3_kernel<true><<<cdiv(total, 256), 256, 0, st>>>(dy, w, nullptr, scale, dx_add, dx, d);
     KMU_LAUNCH_CHECK("dw3x3_bwd_dx");
   }
   if (dw || dscale) {
@@ -556,7 +569,13 @@ int kmu_dwconv3x3_fwd(const kmu_dwconv3x3_desc* dd, const float* x, const float*
 
 int kmu_dwconv3x3_bwd(const kmu_dwconv3x3_desc* dd, const float* x, const float* dy, const float* w, float* dx, float* dw, float* dbias,
                       void* workspace, size_t workspace_bytes, kmu_stream stream) {
-  return dw_bwd(dd, x, dy, w, nullptr, nullptr, dx, dw, dbias, nullptr, workspace, workspace_bytes, stream);
+  return dw_bwd(dd, x, dy, w, nullptr, nullptr, nullptr, dx, dw, dbias, nullptr, workspace, workspace_bytes, stream);
+}
+
+int kmu_dwconv3x3_bwd_add(const kmu_dwconv3x3_desc* dd, const float* x, const float* dy, const float* w, const float* dx_add, float* dx,
+                          float* dw, float* dbias, void* workspace, size_t workspace_bytes, kmu_stream stream) {
+  KMU_REQUIRE(dx_add != nullptr && dx != nullptr, KMU_ERR_BAD_ARG, "dwconv3x3_bwd_add: null dx_add / dx");
+  return dw_bwd(dd, x, dy, w, nullptr, nullptr, dx_add, dx, dw, dbias, nullptr, workspace, workspace_bytes, stream);
 }
 
 int kmu_dwconv3x3_scaled_fwd(const kmu_dwconv3x3_desc* dd, const float* x, const float* w, const float* bias, const float* scale,
@@ -569,7 +588,7 @@ int kmu_dwconv3x3_scaled_bwd(const kmu_dwconv3x3_desc* dd, const float* x, const
                              const float* scale, float* dx, float* dw, float* dbias, float* dscale, void* workspace,
                              size_t workspace_bytes, kmu_stream stream) {
   KMU_REQUIRE(scale != nullptr, KMU_ERR_BAD_ARG, "dwconv3x3_scaled_bwd: null scale");
-  return dw_bwd(dd, x, dy, w, bias, scale, dx, dw, dbias, dscale, workspace, workspace_bytes, stream);
+  return dw_bwd(dd, x, dy, w, bias, scale, nullptr, dx, dw, dbias, dscale, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -118,9 +118,19 @@ class ConvLayer2D(_ConvLayer):
 
     def forward(self, x, res=None, alpha=None):
         """conv -> norm -> act; with res/alpha the block's layer-scale mix is fused into the normalisation."""
-        x = self.conv_out(x)
         fusable = isinstance(self.norm, nn.BatchNorm2d) and (self.act is None or isinstance(self.act, nn.ReLU)) \
             and self.norm.affine and self.norm.momentum is not None
+        if (fusable and self._dw3 and res is x and self.act is None and x.is_cuda and self.conv.bias is None
+                and getattr(ops, "dwconv_bnmix_enabled", True)):
+            # the depthwise branches of EfficientViMBlock: conv, BatchNorm and the layer-scale mix with the conv's own input as one
+            # autograd node (the residual gradient is added inside the convolution's dx kernel)
+            bn = self.norm
+            y = ops.dwconv_bnmix(x, self.conv.weight, bn.weight, bn.bias, alpha, bn.running_mean, bn.running_var,
+                                 bn.training or bn.running_mean is None, bn.momentum, bn.eps)
+            if bn.training and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+            return y
+        x = self.conv_out(x)
         if fusable:
             return _bn2d(self.norm, x, relu=self.act is not None, res=res, alpha=alpha)
         if self.norm:

@@ -12,7 +12,7 @@ from . import _lib
 from ._lib import (ScDesc, TnBwdArgs, TnDesc, TnFwdArgs, PwDesc, BnMixBwdArgs, BnMixDesc, BnMixFwdArgs, DwDesc, DagemBn, DagemBwdArgs, DagemDesc, DagemFwdArgs, DysBwdArgs, DysDesc, DysFwdArgs, HsmBwdArgs, HsmDesc, HsmFwdArgs, KanBwdArgs, KanDesc, KanFwdArgs,
                    KMU_PREC_BF16, KMU_PREC_FP32, check, ptr, stream_ptr)
 
-__all__ = ["kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dysample_sample", "dagem_gate", "bnmix", "dwconv3x3", "pwconv", "pwconv_supported", "triplenorm", "qkv_gate", "smallconv", "smallconv_supported", "iwp", "iwp_supported", "combine3", "combine3_supported", "resize_bilinear_ac", "groupnorm", "groupnorm_supported", "KMU_PREC_FP32", "KMU_PREC_BF16"]
+__all__ = ["kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dysample_sample", "dagem_gate", "bnmix", "dwconv3x3", "pwconv", "pwconv_supported", "triplenorm", "qkv_gate", "smallconv", "smallconv_supported", "iwp", "iwp_supported", "combine3", "combine3_supported", "resize_bilinear_ac", "groupnorm", "groupnorm_supported", "dwconv_bnmix", "KMU_PREC_FP32", "KMU_PREC_BF16"]
 
 
 # ------------------------------------------------------------------------------------------------------ op-level timing
@@ -442,6 +442,64 @@ def bnmix(x, weight, bias, running_mean, running_var, training, momentum=0.1, ep
     if (res is None) != (alpha is None):
         raise ValueError("bnmix: res and alpha go together")
     return _BnMixFn.apply(x, weight, bias, res, alpha, running_mean, running_var, bool(training), momentum, eps, bool(relu))
+
+
+class _DwBnMixFn(torch.autograd.Function):
+    """y = (1 - sigmoid(alpha)) x + sigmoid(alpha) BN(dwconv3x3(x)): EfficientViMBlock's depthwise branches
+    (vim_block_init/efficient_vim_init.py:85,93) as ONE autograd node, so that the mix's d(res) is added to the convolution's input
+    gradient inside the dx kernel (kmu_dwconv3x3_bwd_add) instead of by an autograd accumulation kernel."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, conv_w, weight, bias, alpha, running_mean, running_var, training, momentum, eps):
+        lib = _lib.lib()
+        x = x.contiguous()
+        B, Cc, H, W = x.shape
+        HW = H * W
+        ddesc = DwDesc(B, Cc, H, W)
+        cw = conv_w.reshape(Cc, 9).contiguous()
+        t = torch.empty_like(x)
+        check(_call("kmu_dwconv3x3_fwd", (B, Cc, H, W), lib.kmu_dwconv3x3_fwd, C.byref(ddesc), ptr(x), ptr(cw), None, ptr(t), stream_ptr()),
+              "kmu_dwconv3x3_fwd")
+        desc = BnMixDesc(B, Cc, HW, 1 if training else 0, 0, 1, float(momentum), float(eps))
+        w, b, al = weight.contiguous(), bias.contiguous(), alpha.contiguous()
+        y = torch.empty_like(x)
+        stat = torch.empty(Cc, 2, dtype=torch.float32, device=x.device)
+        ws = _workspace(lib.kmu_bnmix_workspace_bytes(C.byref(desc)), x.device)
+        args = BnMixFwdArgs(desc, ptr(t), ptr(w), ptr(b), ptr(running_mean), ptr(running_var), ptr(x), ptr(al), ptr(y), ptr(stat),
+                            ws.data_ptr(), ws.numel())
+        check(_call("kmu_bnmix_fwd", (B, Cc, HW), lib.kmu_bnmix_fwd, C.byref(args), stream_ptr()), "kmu_bnmix_fwd")
+        ctx.save_for_backward(x, cw, t, w, b, stat, al)
+        ctx.desc, ctx.ddesc, ctx.cwshape = desc, ddesc, conv_w.shape
+        return y
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        lib = _lib.lib()
+        x, cw, t, w, b, stat, al = ctx.saved_tensors
+        desc, ddesc = ctx.desc, ctx.ddesc
+        dy = dy.to(torch.float32).contiguous()
+        dt = torch.empty_like(x)
+        dres = torch.empty_like(x)
+        dw, db, dal = torch.empty_like(w), torch.empty_like(b), torch.empty_like(al)
+        ws = _workspace(lib.kmu_bnmix_workspace_bytes(C.byref(desc)), x.device)
+        args = BnMixBwdArgs(desc, ptr(t), ptr(dy), ptr(w), ptr(b), ptr(stat), ptr(x), ptr(al), ptr(dt), ptr(dw), ptr(db), ptr(dres),
+                            ptr(dal), ws.data_ptr(), ws.numel())
+        check(_call("kmu_bnmix_bwd", (desc.B, desc.C, desc.HW), lib.kmu_bnmix_bwd, C.byref(args), stream_ptr()), "kmu_bnmix_bwd")
+        dcw = torch.empty_like(cw)
+        ws2 = _workspace(lib.kmu_dwconv3x3_bwd_workspace_bytes(C.byref(ddesc)), x.device)
+        # dx = conv^T(dt) + dres, written over dres
+        check(_call("kmu_dwconv3x3_bwd", (ddesc.B, ddesc.C, ddesc.H, ddesc.W), lib.kmu_dwconv3x3_bwd_add, C.byref(ddesc), ptr(x), ptr(dt),
+                    ptr(cw), ptr(dres), ptr(dres), ptr(dcw), None, ws2.data_ptr(), ws2.numel(), stream_ptr()), "kmu_dwconv3x3_bwd_add")
+        return dres, dcw.reshape(ctx.cwshape), dw, db, dal, None, None, None, None, None
+
+
+def dwconv_bnmix(x, conv_weight, bn_weight, bn_bias, alpha, running_mean, running_var, training, momentum=0.1, eps=1e-5):
+    """(1 - sigmoid(alpha)) x + sigmoid(alpha) BatchNorm2d(dwconv3x3(x)) with x feeding both the convolution and the mix."""
+    if not x.is_cuda:
+        raise RuntimeError("km_unet_b200.dwconv_bnmix: CUDA tensors only (no CPU fallback)")
+    return _DwBnMixFn.apply(x, conv_weight, bn_weight, bn_bias, alpha, running_mean, running_var, bool(training), momentum, eps)
 
 
 class _DwConv3x3Fn(torch.autograd.Function):
