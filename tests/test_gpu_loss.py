@@ -24,7 +24,7 @@ def test_hybrid_loss_value_and_gradient(shape):
         (got * 3.0).backward()
     finally:
         torch.backends.cuda.matmul.allow_tf32 = old
-    assert abs(float(got) - float(want)) < 1e-5 * abs(float(want))
+    assert abs(float(got.detach()) - float(want.detach())) < 1e-5 * abs(float(want.detach()))
     assert rel_err(pc.grad, 3.0 * pd.grad) < 1e-4
 
 
