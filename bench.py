@@ -139,6 +139,9 @@ def op_work(name, key):
     if name.startswith("kmu_resize_bilinear"):
         B, C, H, W, OH, OW = key
         return ("hbm", 4.0 * B * C * (H * W + OH * OW), "byte")
+    if name.startswith("kmu_lerpmix"):
+        B, C, HW = key                       # fwd: read x, m, write y; bwd: read x, m, dy, write dx, dm
+        return ("hbm", (12.0 if name.endswith("fwd") else 20.0) * B * C * HW, "byte")
     if name.startswith("kmu_combine3"):
         B, n = key                           # fwd: read x, f0..f2, write out; bwd: read dy, f0..f2, write df0..df2
         return ("hbm", (20.0 if name.endswith("fwd") else 28.0) * B * n, "byte")

@@ -443,6 +443,12 @@ int kmu_qkv_gate_bwd(const float* qkv, const float* dout, float* dqkv, int32_t B
  *     out[b] = x[b] + sum_i coef[b][i] f_i[b],   coef (B,3) = softmax gate weight x per-sample DropPath factor (built by the caller);
  * backward: df_i = coef[b][i] dy, dcoef[b][i] = sum dy . f_i (per-CTA partials reduced in fixed order); dx = dy is the caller's.
  * n_per_b = C*H*W elements per sample, a multiple of 4. */
+/* kmu_lerpmix: EfficientViMBlock.forward, vim_block_init/efficient_vim_init.py:89-90:
+ *     y = (1 - sigmoid(alpha_c)) x + sigmoid(alpha_c) m,  alpha (C) raw;  backward: dx, dm, dalpha (fixed-order reduction).  HW % 4 == 0. */
+size_t kmu_lerpmix_bwd_workspace_bytes(int32_t B, int32_t C, int64_t HW);
+int kmu_lerpmix_fwd(const float* x, const float* m, const float* alpha, float* y, int32_t B, int32_t C, int64_t HW, kmu_stream stream);
+int kmu_lerpmix_bwd(const float* x, const float* m, const float* dy, const float* alpha, float* dx, float* dm, float* dalpha, int32_t B,
+                    int32_t C, int64_t HW, void* workspace, size_t workspace_bytes, kmu_stream stream);
 /* HybridLoss (train_shanghai.py:298-326, train_LAPS.py:347-375) as four streaming passes around the two
  * banded GEMMs of the SSIM filter (which the caller runs): stats -> scal[8] (sums, minima, 1/range), stack -> the five maps
  * (p_n, t_n, p_n^2, t_n^2, p_n t_n), ssim -> loss value + the three derivative maps that reach the prediction (d/dmu_p, d/dE[pp],

@@ -171,6 +171,10 @@ SYMBOLS = {
     "kmu_triplenorm_bwd": (C.c_int, [C.POINTER(TnBwdArgs), C.c_void_p]),
     "kmu_qkv_gate_fwd": (C.c_int, [_f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "kmu_qkv_gate_bwd": (C.c_int, [_f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "kmu_lerpmix_bwd_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int64]),
+    "kmu_lerpmix_fwd": (C.c_int, [_f32p, _f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p]),
+    "kmu_lerpmix_bwd": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p,
+                                  C.c_size_t, C.c_void_p]),
     "kmu_hybridloss_workspace_bytes": (C.c_size_t, []),
     "kmu_hybridloss_stats": (C.c_int, [_f32p, _f32p, C.c_int64, _f32p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kmu_hybridloss_stack": (C.c_int, [_f32p, _f32p, _f32p, _f32p, C.c_int64, C.c_void_p]),

@@ -26,3 +26,5 @@ def precision_code(name=None):
 # pairs the TMA pipelines do not take (Cin + Cout too wide for the tile ring): "tc" = per-tile tcgen05 kernels of pwconv_tc.cu,
 # "simt" = fp32 streaming kernels
 conv_wide = os.environ.get("KMU_CONV_WIDE", "tc")
+# EfficientViMBlock's mixer layer-scale (torch.lerp with a broadcast weight) through kmu_lerpmix (one pass per direction)
+fused_lerp = os.environ.get("KMU_FUSED_LERP", "0") == "1"

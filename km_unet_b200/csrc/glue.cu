@@ -644,6 +644,70 @@ static int gn_split(int rows, long long row_len) {
   return split < 1 ? 1 : split;
 }
 
+// ---------------------------------------------------------------------------------------------- layer-scale mix (lerp)
+// EfficientViMBlock.forward (vim_block_init/efficient_vim_init.py:89-90): x <- (1 - sigmoid(alpha_c)) x + sigmoid(alpha_c) mixer(x).
+// torch.lerp with a broadcast tensor weight costs one forward and ~6 backward kernels (two products, the weight gradient, its
+// reduction to (1,C,1,1), the sigmoid backward); here one float4 pass per direction plus a fixed-order reduction of d(alpha).
+__global__ void __launch_bounds__(256) lerpmix_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ m,
+                                                          const float* __restrict__ alpha, float4* __restrict__ y, int C, long long hw4,
+                                                          long long total4) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total4) return;
+  const int c = (int)((i / hw4) % C);
+  const float s = 1.f / (1.f + __expf(-__ldg(alpha + c)));
+  const float4 a = __ldg(x + i), b = __ldg(m + i);
+  y[i] = make_float4(a.x + s * (b.x - a.x), a.y + s * (b.y - a.y), a.z + s * (b.z - a.z), a.w + s * (b.w - a.w));
+}
+
+// grid (chunks, B * C): dx = (1 - s) dy, dm = s dy, part[plane][chunk] = sum dy (m - x)
+__global__ void __launch_bounds__(256) lerpmix_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ m,
+                                                          const float4* __restrict__ dy, const float* __restrict__ alpha,
+                                                          float4* __restrict__ dx, float4* __restrict__ dm, float* __restrict__ part,
+                                                          int C, long long hw4, int per_cta) {
+  __shared__ float red[8];
+  const long long plane = blockIdx.y;
+  const int c = (int)(plane % C);
+  const float s = 1.f / (1.f + __expf(-__ldg(alpha + c))), r = 1.f - s;
+  const long long lo = (long long)blockIdx.x * per_cta;
+  long long hi = lo + per_cta;
+  if (hi > hw4) hi = hw4;
+  float acc = 0.f;
+  for (long long j = lo + threadIdx.x; j < hi; j += 256) {
+    const long long i = plane * hw4 + j;
+    const float4 a = __ldg(x + i), b = __ldg(m + i), g = __ldg(dy + i);
+    acc += g.x * (b.x - a.x) + g.y * (b.y - a.y) + g.z * (b.z - a.z) + g.w * (b.w - a.w);
+    dx[i] = make_float4(r * g.x, r * g.y, r * g.z, r * g.w);
+    dm[i] = make_float4(s * g.x, s * g.y, s * g.z, s * g.w);
+  }
+  acc = block_sum256(acc, red);
+  if (threadIdx.x == 0) part[plane * gridDim.x + blockIdx.x] = acc;
+}
+
+// dalpha[c] = s (1 - s) sum over b and chunks; one warp per channel, fixed order
+__global__ void __launch_bounds__(128) lerpmix_reduce_kernel(const float* __restrict__ part, const float* __restrict__ alpha, int B, int C,
+                                                             int chunks, float* __restrict__ dalpha) {
+  const int c = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (c >= C) return;
+  float acc = 0.f;
+  const int n = B * chunks;
+  for (int i = lane; i < n; i += 32) {
+    const int b = i / chunks, k = i - b * chunks;
+    acc += part[((size_t)b * C + c) * chunks + k];
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    const float s = 1.f / (1.f + __expf(-alpha[c]));
+    dalpha[c] = s * (1.f - s) * acc;
+  }
+}
+
+static int lerpmix_chunks(int planes, long long hw4) {
+  int chunks = (148 * 8 + planes - 1) / planes;
+  const long long maxc = (hw4 + 255) / 256;
+  if (chunks > maxc) chunks = (int)maxc;
+  return chunks < 1 ? 1 : chunks;
+}
+
 static int combine3_chunks(int B, long long n4_per_b) {
   int chunks = (148 * 8 + B - 1) / B;
   const long long maxc = (n4_per_b + 1023) / 1024;
@@ -844,6 +908,37 @@ int kmu_groupnorm_fwd(const float* x, const float* gamma, const float* beta, flo
   const long long total4 = (long long)B * C * HW / 4;
   kmu::glue::gn_apply_kernel<<<(unsigned)cdiv(total4, 256), 256, 0, st>>>((const float4*)x, mean, rstd, gamma, beta, (float4*)y, C, G, HW / 4, total4);
   KMU_LAUNCH_CHECK("gn_apply");
+  return KMU_OK;
+}
+
+size_t kmu_lerpmix_bwd_workspace_bytes(int32_t B, int32_t C, int64_t HW) {
+  if (B <= 0 || C <= 0 || HW <= 0 || (HW & 3)) return 0;
+  return align_up((size_t)B * C * kmu::glue::lerpmix_chunks(B * C, HW / 4) * 4, 256);
+}
+
+int kmu_lerpmix_fwd(const float* x, const float* m, const float* alpha, float* y, int32_t B, int32_t C, int64_t HW, kmu_stream stream) {
+  KMU_REQUIRE(x && m && alpha && y && B > 0 && C > 0 && HW > 0 && (HW & 3) == 0, KMU_ERR_BAD_ARG, "lerpmix_fwd: bad argument (HW multiple of 4)");
+  const long long hw4 = HW / 4, total4 = hw4 * B * C;
+  kmu::glue::lerpmix_fwd_kernel<<<(unsigned)cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)x, (const float4*)m, alpha,
+                                                                                           (float4*)y, C, hw4, total4);
+  KMU_LAUNCH_CHECK("lerpmix_fwd");
+  return KMU_OK;
+}
+
+int kmu_lerpmix_bwd(const float* x, const float* m, const float* dy, const float* alpha, float* dx, float* dm, float* dalpha, int32_t B,
+                    int32_t C, int64_t HW, void* workspace, size_t workspace_bytes, kmu_stream stream) {
+  KMU_REQUIRE(x && m && dy && alpha && dx && dm && dalpha && B > 0 && C > 0 && HW > 0 && (HW & 3) == 0, KMU_ERR_BAD_ARG, "lerpmix_bwd: bad argument");
+  KMU_REQUIRE((long long)B * C <= 65535, KMU_ERR_UNSUPPORTED, "lerpmix_bwd: B*C > 65535");
+  KMU_REQUIRE(workspace && workspace_bytes >= kmu_lerpmix_bwd_workspace_bytes(B, C, HW), KMU_ERR_WORKSPACE, "lerpmix_bwd: workspace too small");
+  const long long hw4 = HW / 4;
+  const int chunks = kmu::glue::lerpmix_chunks(B * C, hw4);
+  const int per_cta = (int)cdiv(hw4, chunks);
+  cudaStream_t st = (cudaStream_t)stream;
+  kmu::glue::lerpmix_bwd_kernel<<<dim3(chunks, B * C), 256, 0, st>>>((const float4*)x, (const float4*)m, (const float4*)dy, alpha, (float4*)dx,
+                                                                   (float4*)dm, (float*)workspace, C, hw4, per_cta);
+  KMU_LAUNCH_CHECK("lerpmix_bwd");
+  kmu::glue::lerpmix_reduce_kernel<<<cdiv(C, 4), 128, 0, st>>>((const float*)workspace, alpha, B, C, chunks, dalpha);
+  KMU_LAUNCH_CHECK("lerpmix_reduce");
   return KMU_OK;
 }
 

@@ -204,6 +204,10 @@ class EfficientViMBlock(nn.Module):
         # their BatchNorm kernel; the mixer's is one lerp
         x = self.dwconv1(x, res=x, alpha=self.alpha[0])
         mixed, _ = self.mixer(self.norm(x.flatten(2)))
-        x = torch.lerp(x, mixed, torch.sigmoid(self.alpha[1]).view(1, -1, 1, 1))
+        from .. import config
+        if config.fused_lerp and ops.lerpmix_supported(x):
+            x = ops.lerpmix(x, mixed, self.alpha[1])
+        else:
+            x = torch.lerp(x, mixed, torch.sigmoid(self.alpha[1]).view(1, -1, 1, 1))
         x = self.dwconv2(x, res=x, alpha=self.alpha[2])
         return self.ffn(x, res=x, alpha=self.alpha[3])

@@ -12,7 +12,7 @@ from . import _lib
 from ._lib import (ScDesc, TnBwdArgs, TnDesc, TnFwdArgs, PwDesc, BnMixBwdArgs, BnMixDesc, BnMixFwdArgs, DwDesc, DagemBn, DagemBwdArgs, DagemDesc, DagemFwdArgs, DysBwdArgs, DysDesc, DysFwdArgs, HsmBwdArgs, HsmDesc, HsmFwdArgs, KanBwdArgs, KanDesc, KanFwdArgs,
                    KMU_PREC_BF16, KMU_PREC_FP32, check, ptr, stream_ptr)
 
-__all__ = ["kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dysample_sample", "dagem_gate", "bnmix", "dwconv3x3", "pwconv", "pwconv_supported", "triplenorm", "qkv_gate", "smallconv", "smallconv_supported", "iwp", "iwp_supported", "combine3", "combine3_supported", "resize_bilinear_ac", "groupnorm", "groupnorm_supported", "dwconv_bnmix", "KMU_PREC_FP32", "KMU_PREC_BF16"]
+__all__ = ["kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dysample_sample", "dagem_gate", "bnmix", "dwconv3x3", "pwconv", "pwconv_supported", "triplenorm", "qkv_gate", "smallconv", "smallconv_supported", "iwp", "iwp_supported", "combine3", "combine3_supported", "resize_bilinear_ac", "groupnorm", "groupnorm_supported", "dwconv_bnmix", "lerpmix", "lerpmix_supported", "KMU_PREC_FP32", "KMU_PREC_BF16"]
 
 
 # ------------------------------------------------------------------------------------------------------ op-level timing
@@ -752,6 +752,46 @@ def qkv_gate(qkv):
     if not qkv.is_cuda:
         raise RuntimeError("km_unet_b200.qkv_gate: CUDA tensors only (no CPU fallback)")
     return _QkvGateFn.apply(qkv)
+
+
+class _LerpMixFn(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, m, alpha):
+        lib = _lib.lib()
+        x, m, al = x.contiguous(), m.contiguous(), alpha.contiguous()
+        B, Cc = x.shape[0], x.shape[1]
+        HW = x.numel() // (B * Cc)
+        y = torch.empty_like(x)
+        check(_call("kmu_lerpmix_fwd", (B, Cc, HW), lib.kmu_lerpmix_fwd, ptr(x), ptr(m), ptr(al), ptr(y), B, Cc, HW, stream_ptr()),
+              "kmu_lerpmix_fwd")
+        ctx.save_for_backward(x, m, al)
+        ctx.dims = (B, Cc, HW)
+        return y
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        lib = _lib.lib()
+        x, m, al = ctx.saved_tensors
+        B, Cc, HW = ctx.dims
+        dy = dy.to(torch.float32).contiguous()
+        dx, dm, dal = torch.empty_like(x), torch.empty_like(m), torch.empty_like(al)
+        ws = _workspace(lib.kmu_lerpmix_bwd_workspace_bytes(B, Cc, HW), x.device)
+        check(_call("kmu_lerpmix_bwd", (B, Cc, HW), lib.kmu_lerpmix_bwd, ptr(x), ptr(m), ptr(dy), ptr(al), ptr(dx), ptr(dm), ptr(dal), B, Cc,
+                    HW, ws.data_ptr(), ws.numel(), stream_ptr()), "kmu_lerpmix_bwd")
+        return dx, dm, dal
+
+
+def lerpmix_supported(x):
+    return x.is_cuda and x.dim() >= 3 and (x.numel() // (x.shape[0] * x.shape[1])) % 4 == 0
+
+
+def lerpmix(x, m, alpha):
+    """(1 - sigmoid(alpha_c)) x + sigmoid(alpha_c) m with a raw per-channel alpha (C,): EfficientViMBlock's mixer layer-scale."""
+    if not x.is_cuda:
+        raise RuntimeError("km_unet_b200.lerpmix: CUDA tensors only (no CPU fallback)")
+    return _LerpMixFn.apply(x, m.reshape(x.shape), alpha)
 
 
 class _GroupNormFn(torch.autograd.Function):

@@ -381,3 +381,21 @@ def test_groupnorm_vs_torch(B, C, H, W, G):
     assert rel_err(xc.grad, xd.grad) < TOL
     assert rel_err(wc.grad, wd.grad) < TOL
     assert rel_err(bc.grad, bd.grad) < TOL
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 16, 32, 32), (3, 32, 10, 12), (32, 64, 32, 32)])
+def test_lerpmix_vs_torch(B, C, H, W):
+    """(1 - sigmoid(alpha_c)) x + sigmoid(alpha_c) m and the gradients of x, m, alpha vs torch.lerp in fp64."""
+    from km_unet_b200 import ops
+    torch.manual_seed(B + C + H)
+    x, m, al, g = torch.randn(B, C, H, W), torch.randn(B, C, H, W), torch.randn(C), torch.randn(B, C, H, W)
+    xd, md, ad = x.double().requires_grad_(True), m.double().requires_grad_(True), al.double().requires_grad_(True)
+    want = torch.lerp(xd, md, torch.sigmoid(ad).view(1, -1, 1, 1))
+    want.backward(g.double())
+    xc, mc, ac = x.cuda().requires_grad_(True), m.cuda().requires_grad_(True), al.cuda().requires_grad_(True)
+    y = ops.lerpmix(xc, mc, ac)
+    assert rel_err(y, want) < TOL
+    y.backward(g.cuda())
+    assert rel_err(xc.grad, xd.grad) < TOL
+    assert rel_err(mc.grad, md.grad) < TOL
+    assert rel_err(ac.grad, ad.grad) < TOL
