@@ -27,4 +27,4 @@ def precision_code(name=None):
 # "simt" = fp32 streaming kernels
 conv_wide = os.environ.get("KMU_CONV_WIDE", "tc")
 # EfficientViMBlock's mixer layer-scale (torch.lerp with a broadcast weight) through kmu_lerpmix (one pass per direction)
-fused_lerp = os.environ.get("KMU_FUSED_LERP", "0") == "1"
+fused_lerp = os.environ.get("KMU_FUSED_LERP", "1") == "1"
