@@ -18,9 +18,12 @@ One JSON line on stdout (rank 0).  `value` = whole-job samples/s with the batch 
 metric through the public module API with the batch in pinned host memory (H2D of the 25-frame batch and D2H of the
 loss inside the timed region); `roofline` = the C-ABI entry point with the largest share of the step (CUDA events on
 the launching stream around every libkmunet call during a profiling pass of the same workload) against the roofline
-that bounds it; `cpu_baseline` = the full-model CPU oracle (oracle/model.py) on the box's host cores, bounded sample.
-`--impl reference` times that CPU oracle alone (the reference is pure PyTorch: its own CPU path is the same
-arithmetic; the reference tree itself cannot travel to the GPU box).
+that bounds it (`roofline.kan` = the KANConv2d microbench fractions of the tensor peak); `cpu_baseline` = the UNMODIFIED
+reference model (byte-for-byte mirror oracle/_ref/, recipe oracle/make_ref.py; kind "reference") on the box's host cores,
+bounded sample -- or, when the mirror is absent, the CPU oracle port (oracle/model.py; kind "port");
+`gpu_eager_reference` = the same unmodified reference run eagerly on the B200 under fp16 autocast + GradScaler exactly as
+train_shanghai.py:159-181 does, at the largest batch that fits.
+`--impl reference` times the reference's CPU path alone; that arm never imports km_unet_b200.
 """
 import argparse
 import json
@@ -238,17 +241,129 @@ def cpu_oracle_kan_step_factory(batch):
     return step
 
 
+def reference_mirror_available():
+    from oracle import ref_loader
+    return ref_loader.available()
+
+
+def reference_model_step_factory(workload, batch, device="cpu", fp16_autocast=False):
+    """The UNMODIFIED reference (oracle/_ref mirror or /root/reference; imported through oracle/ref_loader.py with the timm /
+    fvcore / pywt stand-ins of oracle/shims.py) running train_shanghai.py's train() body (:159-181): zero_grad, forward, loss,
+    backward, AdamW(lr 1e-3, wd 0.05) (:342).  HybridLoss = oracle/loss.py (train_shanghai.py:298-326; torchmetrics is absent).
+    Nothing of km_unet_b200 is imported."""
+    import warnings
+    import torch
+    from oracle import loss as OL
+    from oracle import ref_loader
+    _, _, variant, classes, fin, size, _, train = WORKLOADS[workload]
+    R = ref_loader.load_models(dropin=False, autocast=True)            # decorators as shipped (inert on CPU tensors)
+    torch.manual_seed(1234)
+    model = (R.KM_UNetV3_SH if variant == "SH" else R.KM_UNetV3_LAPS)(num_classes=classes).to(device)
+    model.train(train)
+    g = torch.Generator().manual_seed(20240518)
+    data = torch.rand(batch, fin + classes, size, size, generator=g).to(device)
+    x, target = data[:, :fin].contiguous(), data[:, fin:].contiguous()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.05)
+    scaler = torch.amp.GradScaler("cuda") if fp16_autocast else None
+
+    def step():
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            if not train:
+                with torch.no_grad():
+                    return float(model(x).float().mean())
+            opt.zero_grad()
+            if fp16_autocast:
+                with torch.autocast("cuda", dtype=torch.float16):
+                    loss = OL.hybrid_loss(model(x), target)
+                scaler.scale(loss).backward()
+                scaler.step(opt)
+                scaler.update()
+            else:
+                loss = OL.hybrid_loss(model(x), target)
+                loss.backward()
+                opt.step()
+            return loss
+    return step
+
+
+def reference_kan_step_factory(batch):
+    import torch
+    from oracle import ref_loader
+    R = ref_loader.load(with_models=False)
+    CIN, COUT, KS, S = KAN["CIN"], KAN["COUT"], KAN["KS"], KAN["S"]
+    torch.manual_seed(1234)
+    layer = R.KANConv2d(CIN, COUT, KS, padding=1)
+    g = torch.Generator().manual_seed(20240518)
+    x = torch.randn(batch, CIN, S, S, generator=g).requires_grad_(True)
+    gout = torch.randn(batch, COUT, S, S, generator=g)
+
+    def step():
+        layer.zero_grad()
+        x.grad = None
+        layer(x).backward(gout)
+        return float(layer.kanlayer.base_weight.grad[0, 0])
+    return step
+
+
 def time_cpu_oracle(workload, batch, steps, warmup):
+    """-> (samples/s, ms per step, threads, kind): the reference itself when its mirror is present, else the oracle port."""
     import torch
     torch.set_num_threads(os.cpu_count() or 1)
-    step = cpu_oracle_kan_step_factory(batch) if workload == "kan" else cpu_oracle_model_step_factory(workload, batch)
+    if reference_mirror_available():
+        kind = "reference"
+        step = reference_kan_step_factory(batch) if workload == "kan" else reference_model_step_factory(workload, batch)
+    else:
+        kind = "port"
+        step = cpu_oracle_kan_step_factory(batch) if workload == "kan" else cpu_oracle_model_step_factory(workload, batch)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps * 1e3, torch.get_num_threads()
+    return batch * steps / dt, dt / steps * 1e3, torch.get_num_threads(), kind
+
+
+def cpu_sample_text(steps, warmup, sb, kind):
+    what = ("the UNMODIFIED reference model (oracle/_ref mirror) + oracle/loss.py on torch CPU fp32" if kind == "reference"
+            else "oracle/model.py (CPU port) on torch CPU fp32")
+    return f"{steps} steps x {sb} sample(s) of the workload after {warmup} warm-up, {what}"
+
+
+def gpu_eager_reference(workload, dev, steps=3, warmup=2):
+    """The unmodified reference on the B200, eager, fp16 autocast + GradScaler as train_shanghai.py:159-181 -- 'the meaningful GPU
+    baseline' of SURVEY section 8d.  Largest batch of 32 / 16 / 8 / 4 that fits (its B-spline temporaries are GBs each)."""
+    import torch
+    if not reference_mirror_available():
+        return {"unavailable": "no oracle/_ref mirror on this box"}
+    torch.backends.cudnn.benchmark = True                               # train_shanghai.py:330
+    last = None
+    for B in (32, 16, 8, 4):
+        try:
+            step = reference_model_step_factory(workload, B, device=dev, fp16_autocast=WORKLOADS[workload][7])
+            for _ in range(warmup):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                res = step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            peak = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+            return {"value": B / (ms / 1e3), "unit": UNIT, "batch": B, "ms_per_step": ms, "steps": steps, "warmup": warmup,
+                    "precision": "fp16 autocast + GradScaler (train_shanghai.py:172-181), cudnn.benchmark", "mode": "eager",
+                    "loss": float(res) if not isinstance(res, float) else res, "peak_mem_gib": peak,
+                    "what": "unmodified reference model (oracle/_ref) + oracle/loss.py, stock PyTorch kernels, 1 x B200"}
+        except torch.cuda.OutOfMemoryError as e:
+            last = str(e).split("\n")[0]
+            step = None
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+    return {"unavailable": f"out of memory down to B=4: {last}"}
 
 
 def cpu_sample_batch(workload):
@@ -270,14 +385,14 @@ def run_reference(args):
         return 0
     sb = cpu_sample_batch(args.workload)
     steps, warmup = min(args.steps, 3), min(args.warmup, 1)
-    value, ms, cores = time_cpu_oracle(args.workload, sb, steps, warmup)
-    sample = f"{steps} steps x {sb} sample(s) of the workload after {warmup} warm-up, oracle/model.py on torch CPU fp32"
+    value, ms, cores, kind = time_cpu_oracle(args.workload, sb, steps, warmup)
+    sample = cpu_sample_text(steps, warmup, sb, kind)
     line = {
         "impl": "reference", "metric": metric_of(args.workload), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": describe(args.workload) + f"; CPU sample of {sb} sample(s) per step", "batch_per_step": sb},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -407,9 +522,10 @@ def run_kan(h, args):
             traffic = json.load(f).get(dom)
     cpu = None
     if h.world == 1 and not args.no_cpu_baseline:
-        v, ms, cores = time_cpu_oracle("kan", 1, 3, 1)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "3 steps x 1 image of the workload (B=1, 64x128x128) after 1 warm-up, oracle/kan.py on torch CPU fp32"}
+        v, ms, cores, kind = time_cpu_oracle("kan", 1, 3, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": "3 steps x 1 image of the workload (B=1, 64x128x128) after 1 warm-up, " +
+                         ("the reference's KANConv2d (oracle/_ref)" if kind == "reference" else "oracle/kan.py") + " on torch CPU fp32"}
     value = h.world * B / (mb["fwd_bwd_ms"] / 1e3)
     line = {"metric": metric_of("kan"), "value": value, "unit": UNIT, "n_gpus": h.world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": mb["fwd_bwd_ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -468,7 +584,7 @@ def run_model(h, args):
     if train and args.graph:
         from km_unet_b200.train import GraphedTrainStep
         l0 = _lib.launch_count()
-        graphed = GraphedTrainStep(model, crit, opt, x_dev, t_dev, world=world, warmup=3)
+        graphed = GraphedTrainStep(model, crit, opt, x_dev, t_dev, world=world, warmup=3, comm=args.comm)
         graphed_launches = (_lib.launch_count() - l0) // 4          # 3 eager warm-up steps + the captured one
 
     def train_step(x, t):
@@ -532,6 +648,20 @@ def run_model(h, args):
     last_loss = float(step_resident().detach().float().cpu())     # sanity: a diverged / corrupted run must not pass as a number
     e2e_ms = h.timed(step_e2e, args.steps, args.warmup)
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
+    used_graph = graphed is not None
+    if graphed is not None and graphed.reducer is not None:
+        graphed.reducer.remove()       # the captured graph keeps its all-reduces; the eager passes below must not launch more
+
+    # N > 1: what the gradient exchange costs on the critical path = the same step captured WITHOUT the all-reduce, timed the same way
+    comm = None
+    if world > 1 and train and graphed is not None:
+        nocomm = GraphedTrainStep(model, crit, opt, x_dev, t_dev, world=1, warmup=1)
+        nocomm_ms = h.timed(lambda: nocomm(), args.steps, args.warmup)
+        comm = {"mode": args.comm, "graph_launches_per_step": graphed.graph_launches_per_step,
+                "buckets": len(graphed.reducer.buckets), "bytes_per_step": sum(f.numel() * 4 for _, f in graphed.reducer.buckets),
+                "ms_per_step_without_allreduce": nocomm_ms / args.steps,
+                "exposed_comm_ms": (total_ms - nocomm_ms) / args.steps}
+        del nocomm
 
     # op-level profile of the same step: CUDA events on the launching stream around every libkmunet call
     prof_steps = 3
@@ -584,9 +714,18 @@ def run_model(h, args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sb = cpu_sample_batch(args.workload)
-        v, ms, cores = time_cpu_oracle(args.workload, sb, 2, 1)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"2 steps x {sb} sample(s) of the workload after 1 warm-up, oracle/model.py on torch CPU fp32"}
+        v, ms, cores, kind = time_cpu_oracle(args.workload, sb, 2, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": cpu_sample_text(2, 1, sb, kind)}
+    gpu_ref = None
+    if rank == 0 and world == 1 and not args.no_gpu_reference:
+        graphed = None
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats(dev)
+        gpu_ref = gpu_eager_reference(args.workload, dev)
+    if kan is not None:
+        roofline["kan"] = {k: {"ms": v["ms"], "achieved": v["achieved"], "frac": v["frac"]} for k, v in kan["families"].items()}
+        roofline["kan"].update({"unit": "TFLOP/s", "peak": kan["peak"], "peak_source": kan["peak_source"], "workload": kan["workload"],
+                                "batch": kan["batch"]})
 
     if rank == 0:
         nlive = sum(p.numel() for p in opt.param_groups[0]["params"]) if train else 0
@@ -597,13 +736,18 @@ def run_model(h, args):
             "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * world, "frames": f"{fin}->{classes}",
                        "size": size, "precision": (f"KANConv2d, the HSM-SSD projection (forward, dgrad, wgrad) and the 1x1-convolution backward {args.precision} (tcgen05), torch GEMMs (SSIM filter of the loss, nn.Linear) TF32, everything else fp32"
                                      if args.precision == "bf16" else "fp32 everywhere"),
-                       "parallelism": f"dp{world}", "cuda_graph": bool(graphed is not None), "optimizer": "AdamW(lr 1e-3, wd 0.05, fused)" if train else None,
+                       "parallelism": f"dp{world}", "cuda_graph": used_graph, "optimizer": "AdamW(lr 1e-3, wd 0.05, fused)" if train else None,
                        "l2": "activations per step (hundreds of %.0f MB tensors) exceed the 126 MB L2" % (B * 16 * size * size * 4 / 1e6),
-                       "grad_allreduce": (f"bucketed NCCL, {nlive * 4 / 1e6:.1f} MB" if world > 1 else "none (1 GPU)")},
+                       "grad_allreduce": ((f"bucketed NCCL all-reduce of {nlive * 4 / 1e6:.1f} MB launched from grad-ready hooks, captured inside the step graph "
+                                           "(overlaps the rest of backward)" if args.comm == "captured" else
+                                           f"bucketed NCCL all-reduce of {nlive * 4 / 1e6:.1f} MB between two graphs") if world > 1 else "none (1 GPU)")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": batch_host.numel() * 4, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches), "loss_after_timed_steps": last_loss, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "kan_microbench": kan,
+            "gpu_eager_reference": gpu_ref,
         }
+        if comm is not None:
+            line["comm"] = comm
         emit(line)
 
 
@@ -618,6 +762,9 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("KMU_KAN_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kan-microbench", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the eager fp16-autocast run of the unmodified reference on the GPU")
+    ap.add_argument("--comm", default="captured", choices=["captured", "split"], help="N > 1: NCCL all-reduce inside the step graph, "
+                    "overlapped with backward (default), or between two graphs (round-1 scheme)")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="run the training step eagerly instead of as CUDA graphs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 1)

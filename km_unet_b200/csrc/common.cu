@@ -1,4 +1,5 @@
 // common.cu -- error channel, version, device probe, launch accounting.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 
@@ -6,7 +7,8 @@
 
 namespace kmu {
 static thread_local char g_err[512] = "";
-static thread_local uint64_t g_launches = 0;
+// process-wide: PyTorch runs backward nodes on its autograd thread, a thread_local counter would miss every backward launch
+static std::atomic<uint64_t> g_launches{0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -15,10 +17,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-void count_launches(int n) { g_launches += (uint64_t)n; }
+void count_launches(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 int finish_launch(const char* what) {
-  g_launches += 1;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
@@ -31,7 +33,7 @@ int finish_launch(const char* what) {
 extern "C" {
 int kmu_version(void) { return KMU_VERSION; }
 const char* kmu_last_error(void) { return kmu::g_err; }
-uint64_t kmu_launch_count(void) { return kmu::g_launches; }
+uint64_t kmu_launch_count(void) { return kmu::g_launches.load(std::memory_order_relaxed); }
 int kmu_device_supported(void) {
   int dev = 0, major = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;

@@ -5,6 +5,8 @@ The reference is single-process: this is the only collectiv
 independent, BatchNorm statistics stay per replica, so "parity" for N ranks = the all-reduced gradient equals the mean
 of the per-rank gradients.
 """
+import contextlib
+
 import torch
 import torch.distributed as dist
 
@@ -14,8 +16,18 @@ class BucketedGradAllReduce:
 
     Parameters are packed into flat buckets (reverse registration order ~ the order backward produces them).  When the
     last gradient of a bucket has been accumulated, the bucket is copied into its flat buffer and an async all-reduce
-    is issued; `finish()` waits for all buckets and scatters the averaged values back into `.grad`.
-    Parameters that never receive a gradient (KM-UNet has 448k of them) must not be passed in.
+    is issued from the hook -- while the rest of backward is still running; `finish()` waits for all buckets and scatters
+    the averaged values back into `.grad`.  The hooks and `finish()` only enqueue work, so a whole step (backward, the
+    all-reduces on NCCL's stream, the scatter) can be captured into ONE CUDA graph (train.GraphedTrainStep).
+
+    Contract:
+      * exactly one backward() between two finish() calls.  A second backward before finish() would re-launch a bucket whose
+        all-reduce may still be in flight, so it raises; accumulate gradients under `no_sync()` instead (hooks disarmed; the
+        step that follows all-reduces the accumulated sum).
+      * EVERY rank must produce gradients for the same set of parameters in a step, because buckets are collectives: a
+        bucket that did not fill on some rank is launched by finish() on that rank, after its peers launched it mid-backward --
+        the order of collectives stays the same on all ranks only if the set of unfilled buckets is the same everywhere.
+      * parameters that never receive a gradient (KM-UNet has 448k of them) must not be passed in.
     """
 
     def __init__(self, params, bucket_bytes=4 << 20, group=None):
@@ -32,10 +44,9 @@ class BucketedGradAllReduce:
                 cur, cur_bytes = [], 0
         if cur:
             self._close(cur)
-        self._pending = {}
-        self._handles = []
         self._hooks = []
         self._where = {}
+        self._armed = True
         for bi, (ps, _) in enumerate(self.buckets):
             for p in ps:
                 self._where[p] = bi
@@ -48,11 +59,28 @@ class BucketedGradAllReduce:
         self.buckets.append((list(ps), flat))
 
     def reset(self):
-        self._pending = {bi: len(ps) for bi, (ps, _) in enumerate(self.buckets)}
-        self._handles = []
+        """Re-arm every bucket for the next step (finish() does this; call it after an aborted backward)."""
+        self._pending = [len(ps) for ps, _ in self.buckets]
+        self._launched = [False] * len(self.buckets)
+        self._handles = [None] * len(self.buckets)
+        self._order = []
+
+    @contextlib.contextmanager
+    def no_sync(self):
+        """Gradient accumulation: backward passes inside this context do not count towards the buckets."""
+        old, self._armed = self._armed, False
+        try:
+            yield
+        finally:
+            self._armed = old
 
     def _on_grad(self, p):
+        if not self._armed:
+            return
         bi = self._where[p]
+        if self._launched[bi] or self._pending[bi] == 0:
+            raise RuntimeError("BucketedGradAllReduce: a parameter received a second gradient before finish() -- call finish() "
+                               "after every backward(), or accumulate under no_sync()")
         self._pending[bi] -= 1
         if self._pending[bi] == 0:
             self._launch(bi)
@@ -61,22 +89,21 @@ class BucketedGradAllReduce:
         ps, flat = self.buckets[bi]
         torch._foreach_copy_(list(flat.split([p.numel() for p in ps])), [p.grad.reshape(-1) for p in ps])
         if self.world > 1:
-            h = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-            self._handles.append((bi, h))
-        else:
-            self._handles.append((bi, None))
+            self._handles[bi] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._launched[bi] = True
+        self._order.append(bi)
 
     def finish(self):
-        """Wait for every bucket, write averaged gradients back.  Returns the number of bytes all-reduced."""
-        for bi, left in self._pending.items():
-            if left != 0:                      # a parameter got no gradient this step: reduce what we have
-                ps, _ = self.buckets[bi]
+        """Wait for every bucket, write averaged gradients back (once per bucket).  Returns the number of bytes all-reduced."""
+        for bi, (ps, _) in enumerate(self.buckets):
+            if not self._launched[bi]:         # a parameter got no gradient this step (same set on every rank): reduce what we have
                 for p in ps:
                     if p.grad is None:
                         p.grad = torch.zeros_like(p)
                 self._launch(bi)
         total = 0
-        for bi, h in self._handles:
+        for bi in self._order:
+            h = self._handles[bi]
             if h is not None:
                 h.wait()
             ps, flat = self.buckets[bi]

@@ -11,11 +11,17 @@ import torch
 import torch.nn.functional as F
 
 
-def _bn_rows(v, weight, bias, running_mean, running_var, training, eps=1e-5):
-    """BatchNorm1d over the rows of v (R, F)."""
+def _bn_rows(v, weight, bias, running_mean, running_var, training, eps=1e-5, momentum=0.1, update=False):
+    """BatchNorm1d over the rows of v (R, F).  update=True also moves the running statistics as nn.BatchNorm1d does in
+    train mode (momentum 0.1, UNBIASED batch variance; DAGEM_md.py:17,24,31,38,52 build them with the defaults)."""
     if training:
         mu = v.mean(dim=0)
         var = ((v - mu) ** 2).mean(dim=0)
+        if update and running_mean is not None:
+            n = v.shape[0]
+            with torch.no_grad():
+                running_mean.mul_(1 - momentum).add_(momentum * mu.detach().to(running_mean.dtype))
+                running_var.mul_(1 - momentum).add_(momentum * (var.detach() * n / max(n - 1, 1)).to(running_var.dtype))
     else:
         mu, var = running_mean, running_var
     return (v - mu) / torch.sqrt(var + eps) * weight + bias
@@ -86,15 +92,15 @@ def dagem(x, P, training=True):
 def dagem_gate(x, deformed, lin, bns, training=True):
     """The gating + final aggregation alone (DAGEM_md.py:62-92,104-110) with explicit tensors, mirroring the C ABI
     kmu_dagem_fwd: lin = (ea_w, ea_b, vu_w, vu_b, eu_w, eu_b, er_w, er_b, wf); bns = 5 x (weight, bias, running_mean,
-    running_var) in the order edge_aggregation, edge_update, vertex_update, update_edge_reduce, final.  Running statistics
-    are read (eval) but never updated here."""
+    running_var) in the order edge_aggregation, edge_update, vertex_update, update_edge_reduce, final.  In training the
+    running statistics are updated in place, as the reference's BatchNorm modules (and kmu_dagem_fwd) do."""
     ea_w, ea_b, vu_w, vu_b, eu_w, eu_b, er_w, er_b, wf = lin
     B, C, H, W = x.shape
     Ch = C // 2
 
     def bn(i, v):
         w, b, rm, rv = bns[i]
-        return _bn_rows(v, w, b, rm, rv, training)
+        return _bn_rows(v, w, b, rm, rv, training, update=True)
 
     nbrs = torch.stack([torch.roll(x, 1, 2), torch.roll(x, -1, 2), torch.roll(x, 1, 3), torch.roll(x, -1, 3)], dim=-1)
     edge = nbrs * x.unsqueeze(-1)

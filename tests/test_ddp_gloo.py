@@ -68,3 +68,26 @@ def test_single_process_is_identity():
     before = lin.weight.grad.clone()
     red.finish()
     assert torch.equal(lin.weight.grad, before)
+
+
+def test_second_backward_before_finish_raises_and_no_sync_accumulates():
+    """a second backward() before finish() used to re-launch buckets (gradient / world^2, racing all-reduces)."""
+    import pytest
+    from km_unet_b200.ddp import BucketedGradAllReduce
+    lin = torch.nn.Linear(3, 2)
+    red = BucketedGradAllReduce(list(lin.parameters()))
+    x = torch.ones(1, 3)
+    lin(x).sum().backward()
+    with pytest.raises(RuntimeError, match="second gradient"):
+        lin(x).sum().backward()
+    red.reset()
+    lin.zero_grad(set_to_none=True)
+    with red.no_sync():                                 # accumulation step: hooks disarmed
+        lin(x).sum().backward()
+    lin(x).sum().backward()                             # the step that reduces the accumulated sum
+    red.finish()
+    assert torch.allclose(lin.weight.grad, torch.full((2, 3), 2.0))
+    lin.zero_grad(set_to_none=True)                     # re-armed for the next step
+    lin(x).sum().backward()
+    red.finish()
+    assert torch.allclose(lin.weight.grad, torch.ones(2, 3))

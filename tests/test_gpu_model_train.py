@@ -1,0 +1,216 @@
+"""END-TO-END train-mode parity on the GPU: output, loss and the gradient of EVERY live parameter of one training step of
+KM_UNetV3_SH(20) and KM_UNetV3_LAPS(3) at B = 2, 128 x 128 against the unmodified reference run in fp64
+(tests/golden/km_unetv3_{sh,laps}_train_128.npz, generator: tests/golden/make_golden_train.py; reference:
+KM_UNetV3_SH.py:371-517, KM_UNetV3_LAPS.py:366-511, train_shanghai.py:159-195,298-326).
+
+Two precision classes (north_star): fp32 (1e-4) and the exact configuration bench.py times -- bf16 tcgen05 KAN / HSM kernels,
+TMA pointwise forward, fused pointwise backward, dwconv_bnmix, fused lerp, TF32 torch GEMMs, through GraphedTrainStep (2e-2).
+
+How the gates are stated.  Output and loss: max|got - want| / max|want| <= gate.  Gradients: the reference's OWN fp32 run
+deviates from its fp64 run by 8e-5 (median over tensors) up to 4e-2 (tensors whose gradient is a cancellation: HSMSSD.D, or
+that sit behind a ReLU that flips), see `ref32g/*` in the fixture -- no fp32 implementation can be within 1e-4 of fp64 on
+every tensor.  So per tensor  err <= gate + 5 * max(ref32 error of that tensor, median ref32 error)  and, over all live
+gradients taken as one vector, relative L2 error <= gate + 2 * (ref32's).  Every test writes its numbers (worst tensors
+included) to gpurun_out/parity_*.json.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import train_fixture as TF
+from conftest import GOLDEN, ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _golden(tag):
+    return np.load(os.path.join(GOLDEN, f"km_unetv3_{tag}_train_128.npz"))
+
+
+def _thresholded(x):
+    """metrics.py:45-47,106-107: uint16(clip(x,0,1) * 90) >= thr for thr in [20,30,35,40]."""
+    q = (np.clip(x, 0, 1) * 90).astype(np.uint16)
+    return np.stack([q >= t for t in (20, 30, 35, 40)])
+
+
+def _scores(pred, truth):
+    """CSI / POD / FAR / HSS of metrics.py:258-266 from binary masks."""
+    out = []
+    for p, t in zip(pred, truth):
+        tp, fn = float((p & t).sum()), float((~p & t).sum())
+        fp, tn = float((p & ~t).sum()), float((~p & ~t).sum())
+        eps = 1e-6
+        out.append((tp / (tp + fn + fp + eps), tp / (tp + fn + eps), fp / (tp + fp + eps),
+                    2 * (tp * tn - fn * fp) / ((tp + fn) * (fn + tn) + (tp + fp) * (fp + tn) + eps)))
+    return np.array(out)
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def _build(tag):
+    import km_unet_b200 as K
+    variant, classes = TF.VARIANTS[tag]
+    z = _golden(tag)
+    torch.manual_seed(TF.SEED_WEIGHTS)
+    model = K.KM_UNetV3(num_classes=classes, variant=variant)
+    TF.perturb_(model)
+    TF.assert_same_state(model.state_dict(), z)      # the seeded construction on this box == the one the fixture was made from
+    x, t = TF.make_batch(classes)
+    return model.cuda().train(), x.cuda(), t.cuda(), z
+
+
+class _Config:
+    """The two precision classes as bench.py sets them (bench.py:run_model)."""
+
+    def __init__(self, cls):
+        self.cls = cls
+
+    def __enter__(self):
+        import km_unet_b200 as K
+        c = K.config
+        self.saved = (c.kan_precision, c.hsm_precision, c.conv_precision, c.conv_bwd, c.conv_fwd,
+                      torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        if self.cls == "bf16":
+            c.kan_precision = c.hsm_precision = "bf16"
+            c.conv_bwd, c.conv_fwd = "fused", "tma"
+            torch.backends.cuda.matmul.allow_tf32 = True
+        else:
+            c.kan_precision = c.hsm_precision = c.conv_precision = "fp32"
+            c.conv_bwd, c.conv_fwd = "split", "simt"
+            torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        return self
+
+    def __exit__(self, *exc):
+        import km_unet_b200 as K
+        c = K.config
+        (c.kan_precision, c.hsm_precision, c.conv_precision, c.conv_bwd, c.conv_fwd,
+         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32) = self.saved
+        return False
+
+
+def _report(name, z, out, loss, grads, after=None, extra=None):
+    want_out = z["out0"].astype(np.float64)
+    e = TF.grad_errors(grads, z)
+    ref = {k[6:]: z[k] for k in z.files if k.startswith("ref32g/")}
+    ref_med = float(np.median([v[0] for v in ref.values()]))
+    rows = sorted(e.items(), key=lambda kv: -kv[1][0])
+    a, b = _thresholded(out), _thresholded(want_out)
+    truth = _thresholded(TF.make_batch(out.shape[1])[1].numpy())
+    rep = {"out_err": _rel(out, want_out), "loss_err": abs(loss - float(z["loss"])) / abs(float(z["loss"])),
+           "grad_l2": TF.grad_global_l2(grads, z), "grad_l2_ref32": float(z["ref32/grad_l2"]),
+           "grad_err_max": rows[0][1][0], "grad_err_median": float(np.median([v[0] for v in e.values()])),
+           "grad_err_median_ref32": ref_med, "grad_err_max_ref32": float(z["ref32/grad_err"]),
+           "n_live": len(e), "mask_flips": int((a != b).sum()), "mask_cells": int(a.size),
+           "scores_equal": bool(np.array_equal(_scores(a, truth), _scores(b, truth))),
+           "score_max_abs_diff": float(np.abs(_scores(a, truth) - _scores(b, truth)).max()),
+           "worst": [{"param": k, "err": v[0], "norm_err": v[1], "ref32_err": float(ref[k][0])} for k, v in rows[:12]]}
+    if after is not None:
+        rep["running_stat_err"] = max(_rel(after[k[9:]].detach().double().cpu().numpy(), z[k]) for k in z.files if k.startswith("sd_after/"))
+    if extra:
+        rep.update(extra)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", f"parity_{name}.json"), "w") as f:
+        json.dump(rep, f, indent=1)
+    return rep, e, ref, ref_med
+
+
+def _assert_grads(rep, e, ref, ref_med, gate):
+    assert rep["grad_l2"] <= gate + 2 * rep["grad_l2_ref32"], rep
+    bad = {k: (v[0], float(ref[k][0])) for k, v in e.items() if not v[0] <= gate + 5 * max(float(ref[k][0]), ref_med)}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("tag", ["sh", "laps"])
+def test_train_step_fp32_class_matches_reference(tag):
+    from km_unet_b200.loss import HybridLoss
+    from km_unet_b200.modules import km_unet as MM
+    model, x, t, z = _build(tag)
+    with _Config("fp32"), TF.DropPathReplayer(MM.DropPath, list(z["masks"])):
+        out = model(x)
+        loss = HybridLoss()(out, t)
+        loss.backward()
+    torch.cuda.synchronize()
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    rep, e, ref, ref_med = _report(f"{tag}_fp32", z, out.detach().double().cpu().numpy(), loss.item(), grads, after=model.state_dict())
+    assert rep["out_err"] <= 1e-4 and rep["loss_err"] <= 1e-4, rep
+    assert rep["running_stat_err"] <= 1e-4, rep
+    assert rep["mask_flips"] == 0 and rep["scores_equal"], rep          # CSI / POD / FAR / HSS identical on the thresholded masks
+    _assert_grads(rep, e, ref, ref_med, 1e-4)
+
+
+@pytest.mark.parametrize("tag", ["sh", "laps"])
+def test_train_step_bench_configuration_graphed_matches_reference_and_eager(tag):
+    """bf16 class through GraphedTrainStep (what bench.py times): first replay == the reference's step within 2e-2, and the
+    replay == the same step run eagerly."""
+    from km_unet_b200.loss import HybridLoss
+    from km_unet_b200.modules import km_unet as MM
+    from km_unet_b200.train import GraphedTrainStep
+    model, x, t, z = _build(tag)
+    masks = [torch.as_tensor(m, dtype=torch.float32, device="cuda") for m in z["masks"]]      # device-resident: usable under capture
+
+    class Replay(TF.DropPathReplayer):
+        def __enter__(self):
+            rep = super().__enter__()
+            cls, n = self.cls, len(masks)
+
+            def forward(mod, v):
+                if not mod.training or mod.drop_prob == 0.0:
+                    return v
+                m = masks[rep.i % n].reshape((v.shape[0],) + (1,) * (v.dim() - 1)) / (1.0 - mod.drop_prob)
+                rep.i += 1
+                return v * m
+            cls.forward = forward
+            return rep
+
+    crit = HybridLoss()
+    with _Config("bf16"), Replay(MM.DropPath, masks):
+        state0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        crit(model(x), t).backward()                                   # which parameters are live (the dead ones stay out of AdamW)
+        live = [p for p in model.parameters() if p.grad is not None]
+        for p in model.parameters():
+            p.grad = None
+        model.load_state_dict(state0)
+        # eager step from the fixture's state
+        out_e = model(x)
+        loss_e = crit(out_e, t)
+        loss_e.backward()
+        eager = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+        out_e, loss_e = out_e.detach().clone(), loss_e.detach().clone()
+        after_e = {k: v.detach().clone() for k, v in model.state_dict().items() if "running_" in k}
+        model.load_state_dict(state0)
+        for p in model.parameters():
+            p.grad = None
+        opt = torch.optim.AdamW(live, lr=1e-3, weight_decay=0.05, fused=True, capturable=True)
+        step = GraphedTrainStep(model, crit, opt, x, t, world=1, warmup=3)
+        # warm-up must have left no trace: parameters, BatchNorm statistics, optimizer step counters
+        for k, v in model.state_dict().items():
+            assert torch.equal(v, state0[k]), f"GraphedTrainStep warm-up changed {k}"
+        assert all(float(s["step"]) == 0.0 for s in opt.state.values())
+        loss_g = step().detach().clone()
+        torch.cuda.synchronize()
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    after = {k: v for k, v in model.state_dict().items() if "running_" in k}
+    replay_vs_eager = max(_rel(grads[k].double().cpu().numpy(), eager[k].double().cpu().numpy()) for k in eager)
+    extra = {"replay_vs_eager_grad": replay_vs_eager, "replay_vs_eager_out": _rel(step.out.detach().double().cpu().numpy(), out_e.double().cpu().numpy()),
+             "replay_vs_eager_loss": abs(loss_g.item() - loss_e.item()) / abs(loss_e.item()),
+             "replay_vs_eager_running": max(_rel(after[k].double().cpu().numpy(), after_e[k].double().cpu().numpy()) for k in after_e)}
+    rep, e, ref, ref_med = _report(f"{tag}_bf16_graphed", z, step.out.detach().double().cpu().numpy(), loss_g.item(), grads,
+                                   after=model.state_dict(), extra=extra)
+    # graph replay == eager (atomics in DySample's dX scatter reorder fp32 sums: not bitwise)
+    assert extra["replay_vs_eager_out"] <= 1e-6 and extra["replay_vs_eager_loss"] <= 1e-6 and replay_vs_eager <= 1e-4, extra
+    assert extra["replay_vs_eager_running"] <= 1e-6, extra
+    # the optimizer really stepped inside the graph
+    assert all(float(s["step"]) == 1.0 for s in opt.state.values())
+    assert any(not torch.equal(p.detach(), state0[k]) for k, p in model.named_parameters() if p.grad is not None)
+    # vs the reference
+    assert rep["out_err"] <= 2e-2 and rep["loss_err"] <= 2e-2 and rep["running_stat_err"] <= 2e-2, rep
+    _assert_grads(rep, e, ref, ref_med, 2e-2)
+    # thresholded cloud masks under the bf16 class: report the flip count; the scores built from them must agree to 1e-3
+    assert rep["mask_flips"] <= 1e-3 * rep["mask_cells"] and rep["score_max_abs_diff"] <= 1e-3, rep

@@ -58,8 +58,13 @@ def test_wavelet_pooling_matches_matrix_form(C, S):
         assert rel_err(m(x), want) < 1e-6
 
 
-@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not present")
-@pytest.mark.parametrize("name", ["StableHybridKANConv_noKAN", "TripleNorm", "DirectionAttention", "LocalContrastAttention",
+def _ref_available():
+    from oracle import ref_loader
+    return ref_loader.available()
+
+
+@pytest.mark.skipif(not _ref_available(), reason="no reference tree and no oracle/_ref mirror")
+@pytest.mark.parametrize("name", ["StableHybridKANConv", "StableHybridKANConv_residual", "TripleNorm", "DirectionAttention", "LocalContrastAttention",
                                   "MultiScaleFusion", "IntelligentWaveletPoolingModule"])
 def test_glue_blocks_match_live_reference(name):
     from oracle import ref_loader
@@ -78,8 +83,10 @@ def test_glue_blocks_match_live_reference(name):
         x = [torch.randn(2, 16, 8, 8), torch.randn(2, 32, 8, 8), torch.randn(2, 32, 8, 8)]
     elif name == "IntelligentWaveletPoolingModule":
         ref, ours, x = sh.IntelligentWaveletPoolingModule(16), M.IntelligentWaveletPoolingModule(16), torch.randn(2, 16, 8, 8)
-    else:
-        pytest.skip("KAN path needs CUDA")
+    elif name == "StableHybridKANConv":          # K5, identity residual (KM_UNetV3_SH.py:72-94); the KAN op runs as its CPU oracle
+        ref, ours, x = sh.StableHybridKANConv(16, 16), M.StableHybridKANConv(16, 16), torch.randn(2, 16, 8, 8) * 1.5
+    else:                                        # K5 with the 1x1 residual convolution
+        ref, ours, x = sh.StableHybridKANConv(16, 32), M.StableHybridKANConv(16, 32), torch.randn(2, 16, 8, 8) * 1.5
     with torch.no_grad():
         for p in ref.parameters():
             p.add_(torch.randn_like(p) * 0.1)
@@ -102,6 +109,39 @@ def test_full_model_cpu_oracle_matches_reference_golden():
     with OM.cpu_ops(), torch.no_grad():
         y = m(g.t("in0"))
     assert rel_err(y, g.t("out0")) < 1e-5
+
+
+@pytest.mark.parametrize("tag", ["sh", "laps"])
+def test_full_model_train_step_cpu_oracle_matches_reference_fp64_fixture(tag):
+    """TRAIN mode, end to end: the mirror's glue (DropPath folded into the combine3 coefficients, BatchNorm statistics, dead
+    parameters) + the op restatements of oracle/ + oracle/loss.py, in fp64, against output / loss / every live gradient of the
+    unmodified reference's own fp64 step (tests/golden/make_golden_train.py).  Exact to the fixture's fp32 storage."""
+    import train_fixture as TF
+    import km_unet_b200 as K
+    from km_unet_b200.modules import km_unet as MM
+    from oracle import loss as OL
+    from oracle import model as OM
+    variant, classes = TF.VARIANTS[tag]
+    z = np.load(os.path.join(GOLDEN, f"km_unetv3_{tag}_train_128.npz"))
+    torch.manual_seed(TF.SEED_WEIGHTS)
+    m = K.KM_UNetV3(num_classes=classes, variant=variant)
+    TF.perturb_(m)
+    TF.assert_same_state(m.state_dict(), z)
+    m = m.double().train()
+    x, t = TF.make_batch(classes)
+    with OM.cpu_ops(), TF.DropPathReplayer(MM.DropPath, list(z["masks"])):
+        out = m(x.double())
+        loss = OL.hybrid_loss(out, t.double())
+        loss.backward()
+    grads = {k: p.grad for k, p in m.named_parameters()}
+    assert rel_err(out, torch.from_numpy(z["out0"])) < 1e-6
+    assert abs(loss.item() - float(z["loss"])) < 1e-9
+    errs = TF.grad_errors(grads, z)
+    assert max(v[0] for v in errs.values()) < 1e-6, sorted(errs.items(), key=lambda kv: -kv[1][0])[:3]
+    assert TF.grad_global_l2(grads, z) < 1e-6
+    for k in z.files:
+        if k.startswith("sd_after/"):
+            assert rel_err(m.state_dict()[k[9:]], torch.from_numpy(z[k])) < 1e-6, k
 
 
 def test_product_path_raises_on_cpu_outside_the_oracle_context():
