@@ -154,6 +154,9 @@ def op_work(name, key):
     if name.startswith("kmu_dysample"):
         B, C, H, W = key
         return ("hbm", (20.0 if name.endswith("fwd") else 24.0) * B * C * H * W, "byte")
+    if name.startswith("kmu_deformconv3x3"):
+        B, C, H, W = key                     # fwd: read x, offset, write out; bwd: + dout, dx, doffset (latency-bound at the bridge size)
+        return ("hbm", (4.0 * (2 * C + 18) if name.endswith("fwd") else 4.0 * (4 * C + 36)) * B * H * W, "byte")
     if name.startswith("kmu_dagem"):
         B, C, H, W = key
         return ("hbm", (12.0 if name.endswith("fwd") else 20.0) * B * C * H * W, "byte")

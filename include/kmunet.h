@@ -223,6 +223,25 @@ int kmu_dysample_sample_bwd(const kmu_dysample_desc* d, const float* x, const fl
                             kmu_stream stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * G': DAGEM's deformable 3x3 convolution   DAGEM_md.py:46 (DeformConv2d(C, C, kernel_size=3, padding=1)), :98-101
+ *   (offset = offset_conv(x); deformed = deform_conv(x, offset)).  torchvision.ops.deform_conv2d semantics with one offset
+ *   group, stride 1, dilation 1: out[b,o,p] = bias[o] + sum_{c,t} W[o,c,t] bilinear(x[b,c], p + tap_t - 1 + offset[b,2t:2t+2,p]),
+ *   zero outside (-1,H) x (-1,W).  Every kernel runs on the given stream (torchvision's CUDA op uses the legacy default stream
+ *   and is therefore NOT CUDA-graph capturable) and all reductions have a fixed order (no atomics).  H*W <= 4096.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t B, C, H, W, Cout;
+} kmu_deform_desc;
+
+size_t kmu_deformconv3x3_bwd_workspace_bytes(const kmu_deform_desc* d);
+int kmu_deformconv3x3_fwd(const kmu_deform_desc* d, const float* x /* (B,C,H,W) */, const float* offset /* (B,18,H,W): (dy,dx) per tap */,
+                          const float* weight /* (Cout,C,3,3) */, const float* bias /* (Cout) or NULL */, float* out /* (B,Cout,H,W) */,
+                          kmu_stream stream);
+int kmu_deformconv3x3_bwd(const kmu_deform_desc* d, const float* x, const float* offset, const float* weight,
+                          const float* dout /* (B,Cout,H,W) */, float* dx, float* doffset, float* dweight,
+                          float* dbias /* may be NULL */, void* workspace, size_t workspace_bytes, kmu_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * G: DAGEM attention-gated fusion        DAGEM_md.py:62-92 (edge / vertex gating), :104-110 (final aggregation)
  *   s = x . sum_k a_k nb_k + a_b ; agg = ReLU(BN0(s)) ; ue_k = We [x; x . nb_k] + e_b ; uvp = Wv [x; agg] + v_b ;
  *   r = sum_k r_k ReLU(BN1(ue_k)) + r_b ; z = Wf [deformed; ReLU(BN2(uvp)) . ReLU(BN3(r))] ; out = ReLU(BN4(z))

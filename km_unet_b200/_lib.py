@@ -64,6 +64,10 @@ class DysBwdArgs(C.Structure):
                [("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
+class DeformDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B", "C", "H", "W", "Cout")]
+
+
 class DagemDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("B", "C", "H", "W", "training")] + [("momentum", C.c_float), ("eps", C.c_float)]
 
@@ -151,6 +155,10 @@ SYMBOLS = {
     "kmu_dysample_bwd": (C.c_int, [C.POINTER(DysBwdArgs), C.c_void_p]),
     "kmu_dysample_sample_fwd": (C.c_int, [C.POINTER(DysDesc), _f32p, _f32p, _f32p, C.c_void_p]),
     "kmu_dysample_sample_bwd": (C.c_int, [C.POINTER(DysDesc), _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
+    "kmu_deformconv3x3_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(DeformDesc)]),
+    "kmu_deformconv3x3_fwd": (C.c_int, [C.POINTER(DeformDesc), _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
+    "kmu_deformconv3x3_bwd": (C.c_int, [C.POINTER(DeformDesc), _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p,
+                                        C.c_size_t, C.c_void_p]),
     "kmu_bnmix_workspace_bytes": (C.c_size_t, [C.POINTER(BnMixDesc)]),
     "kmu_bnmix_fwd": (C.c_int, [C.POINTER(BnMixFwdArgs), C.c_void_p]),
     "kmu_bnmix_bwd": (C.c_int, [C.POINTER(BnMixBwdArgs), C.c_void_p]),

@@ -56,23 +56,28 @@ __device__ __forceinline__ size_t chan_off(long long v, int c, int C, int HW) {
   return (size_t)((b * C + c) * (long long)HW + (v - b * HW));
 }
 
-// ---- forward statistics: part[(c*nsplit + s)*2 + {0,1}] = sum, sum of squares.  grid (nsplit, C), 256 threads
+// ---- forward statistics: part[(c*nsplit + s)*2 + {0,1}] = sum, sum of squares of (x - k), k = the channel's first element.
+//      The shift keeps var = E[(x-k)^2] - E[x-k]^2 free of the catastrophic cancellation of E[x^2] - mean^2 when |mean| >> std
+//      (k is a sample of the channel, so |E[x-k]| is a few std at most); nn.BatchNorm's Welford has no such problem either.
+//      grid (nsplit, C), 256 threads
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, float* __restrict__ part, BnDims d) {
   __shared__ float red[8];
   const int c = blockIdx.y, s = blockIdx.x;
   const long long v0 = (long long)s * d.len;
   long long v1 = v0 + d.len;
   if (v1 > d.per) v1 = d.per;
+  const float k = __ldg(x + (size_t)c * d.HW);
   float a = 0.f, q = 0.f;
   if ((d.HW & 3) == 0) {
     for (long long v = v0 + 4 * threadIdx.x; v < v1; v += 1024) {
       float4 t = *reinterpret_cast<const float4*>(x + chan_off(v, c, d.C, d.HW));
+      t.x -= k; t.y -= k; t.z -= k; t.w -= k;
       a += (t.x + t.y) + (t.z + t.w);
       q = fmaf(t.x, t.x, fmaf(t.y, t.y, fmaf(t.z, t.z, fmaf(t.w, t.w, q))));
     }
   } else {
     for (long long v = v0 + threadIdx.x; v < v1; v += 256) {
-      float t = x[chan_off(v, c, d.C, d.HW)];
+      float t = x[chan_off(v, c, d.C, d.HW)] - k;
       a += t;
       q = fmaf(t, t, q);
     }
@@ -86,7 +91,7 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
 }
 
 // ---- finalize: stat[c] = (mean, rstd); running statistics as torch.nn.BatchNorm2d (momentum, unbiased variance).  grid C, 32 thr
-__global__ void __launch_bounds__(32) bn_fin_kernel(const float* __restrict__ part, float2* __restrict__ stat,
+__global__ void __launch_bounds__(32) bn_fin_kernel(const float* __restrict__ x, const float* __restrict__ part, float2* __restrict__ stat,
                                                     float* __restrict__ rmean, float* __restrict__ rvar, BnDims d, int training,
                                                     float momentum, float eps) {
   const int c = blockIdx.x;
@@ -102,9 +107,10 @@ __global__ void __launch_bounds__(32) bn_fin_kernel(const float* __restrict__ pa
       s += __shfl_xor_sync(0xffffffffu, s, o);
       q += __shfl_xor_sync(0xffffffffu, q, o);
     }
-    mean = s / (double)d.per;
-    var = q / (double)d.per - mean * mean;
+    const double ms = s / (double)d.per;      // mean of the shifted values
+    var = q / (double)d.per - ms * ms;
     if (var < 0.0) var = 0.0;
+    mean = ms + (double)x[(size_t)c * d.HW];
   } else {
     mean = (double)rmean[c];
     var = (double)rvar[c];
@@ -470,7 +476,7 @@ int kmu_bnmix_fwd(const kmu_bnmix_fwd_args* a, kmu_stream stream) {
     bn_stats_kernel<<<dim3(d.nsplit, d.C), 256, 0, st>>>(a->x, part, d);
     KMU_LAUNCH_CHECK("bn_stats");
   }
-  bn_fin_kernel<<<d.C, 32, 0, st>>>(part, stat, a->running_mean, a->running_var, d, a->d.training, a->d.momentum, a->d.eps);
+  bn_fin_kernel<<<d.C, 32, 0, st>>>(a->x, part, stat, a->running_mean, a->running_var, d, a->d.training, a->d.momentum, a->d.eps);
   KMU_LAUNCH_CHECK("bn_fin");
   const long long total = (long long)d.B * d.C * d.HW;
   const float* res = a->d.mix ? a->res : nullptr;

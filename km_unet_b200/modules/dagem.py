@@ -1,8 +1,10 @@
 """DAGEM with the reference's constructor signature and state_dict layout (DAGEM_md.py:7-111).
 
 The edge / vertex gating MLPs, their five train-mode BatchNorms and the final 1x1 fusion run in libkmunet.so
-(ops.dagem_gate).  The deformable branch (offset conv -> torchvision DeformConv2d, DAGEM_md.py:95-101) is a third-party
-library op in the reference too and stays a library call here.
+(ops.dagem_gate), and so does the deformable 3x3 convolution (ops.deformconv3x3, csrc/deform.cu): torchvision's CUDA op
+launches on the legacy default stream, so it is silently dropped from a CUDA-graph capture, and its backward scatters with
+atomics.  `deform_conv` stays a torchvision DeformConv2d module for its parameters / state_dict keys; it is only CALLED for
+maps larger than the kernel takes (H*W > 4096).  The 3x3 offset convolution (DAGEM_md.py:45,98) is a plain cuDNN convolution.
 """
 import torch.nn as nn
 from torchvision.ops import DeformConv2d
@@ -29,7 +31,11 @@ class DAGEM(nn.Module):
 
     def forward(self, input):
         x = input
-        deformed = self.deform_conv(x, self.offset_conv(x)) + x
+        offset = self.offset_conv(x)
+        if ops.deformconv3x3_supported(x, self.deform_conv.weight):
+            deformed = ops.deformconv3x3(x, offset, self.deform_conv.weight, self.deform_conv.bias) + x
+        else:
+            deformed = self.deform_conv(x, offset) + x
         bns = self._bns()
         training = self.training or any(bn.running_mean is None for bn in bns)
         lin = (self.edge_aggregation_func[0].weight, self.edge_aggregation_func[0].bias,

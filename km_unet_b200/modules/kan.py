@@ -35,6 +35,9 @@ class KANLinear(nn.Module):
         self.grid_eps = grid_eps
         self.precision = None          # None -> km_unet_b200.config.kan_precision
         self.reset_parameters()
+        # load_state_dict rewrites the knot table: refresh the cached knot summary right away (a device -> host read) so that
+        # the next forward -- possibly under CUDA-graph capture, where such a read is illegal -- finds it valid
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._grid_meta() if module.grid.is_cuda else None)
 
     # -- host-side helpers (init / grid adaptation only) -------------------------------------------------------
     def reset_parameters(self):

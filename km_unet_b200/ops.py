@@ -9,7 +9,7 @@ import torch
 from torch.amp import custom_bwd, custom_fwd
 
 from . import _lib
-from ._lib import (ScDesc, TnBwdArgs, TnDesc, TnFwdArgs, PwDesc, BnMixBwdArgs, BnMixDesc, BnMixFwdArgs, DwDesc, DagemBn, DagemBwdArgs, DagemDesc, DagemFwdArgs, DysBwdArgs, DysDesc, DysFwdArgs, HsmBwdArgs, HsmDesc, HsmFwdArgs, KanBwdArgs, KanDesc, KanFwdArgs,
+from ._lib import (ScDesc, TnBwdArgs, TnDesc, TnFwdArgs, PwDesc, BnMixBwdArgs, BnMixDesc, BnMixFwdArgs, DwDesc, DagemBn, DagemBwdArgs, DagemDesc, DagemFwdArgs, DeformDesc, DysBwdArgs, DysDesc, DysFwdArgs, HsmBwdArgs, HsmDesc, HsmFwdArgs, KanBwdArgs, KanDesc, KanFwdArgs,
                    KMU_PREC_BF16, KMU_PREC_FP32, check, ptr, stream_ptr)
 
 __all__ = ["kanconv2d", "kanlinear", "layernorm1d", "hsmssd", "dysample", "dysample_sample", "dagem_gate", "bnmix", "dwconv3x3", "pwconv", "pwconv_supported", "triplenorm", "qkv_gate", "smallconv", "smallconv_supported", "iwp", "iwp_supported", "combine3", "combine3_supported", "resize_bilinear_ac", "groupnorm", "groupnorm_supported", "dwconv_bnmix", "lerpmix", "lerpmix_supported", "KMU_PREC_FP32", "KMU_PREC_BF16"]
@@ -389,6 +389,50 @@ def dagem_gate(x, deformed, linears, bns, training, momentum=0.1, eps=1e-5):
         flat += [w, b]
     running = [(rm, rv) for _, _, rm, rv in bns]
     return _DagemGateFn.apply(x, deformed, *linears, *flat, running, bool(training), momentum, eps)
+
+
+class _DeformConvFn(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, offset, weight, bias):
+        lib = _lib.lib()
+        x, offset, weight = x.contiguous(), offset.contiguous(), weight.contiguous()
+        B, Cc, H, W = x.shape
+        desc = DeformDesc(B, Cc, H, W, weight.shape[0])
+        out = torch.empty(B, weight.shape[0], H, W, dtype=torch.float32, device=x.device)
+        check(_call("kmu_deformconv3x3_fwd", (B, Cc, H, W), lib.kmu_deformconv3x3_fwd, C.byref(desc), ptr(x), ptr(offset), ptr(weight),
+                    ptr(bias.contiguous()) if bias is not None else None, ptr(out), stream_ptr()), "kmu_deformconv3x3_fwd")
+        ctx.save_for_backward(x, offset, weight)
+        ctx.desc, ctx.has_bias = desc, bias is not None
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dout):
+        lib = _lib.lib()
+        x, offset, weight = ctx.saved_tensors
+        desc = ctx.desc
+        dout = dout.to(torch.float32).contiguous()
+        dx, doff, dw = torch.empty_like(x), torch.empty_like(offset), torch.empty_like(weight)
+        db = torch.empty(weight.shape[0], dtype=torch.float32, device=x.device) if ctx.has_bias else None
+        ws = _workspace(lib.kmu_deformconv3x3_bwd_workspace_bytes(C.byref(desc)), x.device)
+        check(_call("kmu_deformconv3x3_bwd", (desc.B, desc.C, desc.H, desc.W), lib.kmu_deformconv3x3_bwd, C.byref(desc), ptr(x), ptr(offset),
+                    ptr(weight), ptr(dout), ptr(dx), ptr(doff), ptr(dw), ptr(db) if db is not None else None, ws.data_ptr(), ws.numel(),
+                    stream_ptr()), "kmu_deformconv3x3_bwd")
+        return dx, doff, dw, db
+
+
+def deformconv3x3_supported(x, weight):
+    return (x.is_cuda and x.dim() == 4 and x.shape[2] * x.shape[3] <= 4096 and tuple(weight.shape[2:]) == (3, 3)
+            and x.shape[1] <= 256 and weight.shape[0] <= 256 and weight.shape[1] == x.shape[1])
+
+
+def deformconv3x3(x, offset, weight, bias=None):
+    """torchvision.ops.deform_conv2d(x, offset, weight, bias, padding=1) for a 3x3 kernel, stride 1, one offset group
+    (DAGEM_md.py:46,98-101) on the caller's stream, deterministic backward."""
+    if not x.is_cuda:
+        raise RuntimeError("km_unet_b200.deformconv3x3: CUDA tensors only (no CPU fallback)")
+    return _DeformConvFn.apply(x, offset, weight, bias)
 
 
 # ------------------------------------------------------------------------------------------------------ EfficientViMBlock shell

@@ -65,7 +65,8 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
         with torch.no_grad():                      # undo the warm-up steps in place (tensor identities are what the graph captures)
             for t, s in zip(list(model.parameters()) + list(model.buffers()), snap_model):
-                t.copy_(s)
+                if not torch.equal(t, s):          # constant buffers (KAN knot tables) keep their version: no cache refresh under capture
+                    t.copy_(s)
             for p in self.params:
                 for k, v in optimizer.state.get(p, {}).items():
                     if torch.is_tensor(v):

@@ -106,3 +106,65 @@ def test_dagem_cpu_tensor_raises():
     m = DAGEM(input_channels=8)
     with pytest.raises(RuntimeError):
         m(torch.randn(1, 8, 4, 4))
+
+
+@pytest.mark.parametrize("B,C,Co,H,W,scale", [(2, 8, 8, 6, 6, 1.0), (2, 64, 64, 16, 16, 0.7), (1, 16, 24, 32, 32, 2.5), (1, 4, 4, 64, 64, 1.5),
+                                               (3, 5, 7, 9, 4, 4.0)])
+def test_deformconv3x3_vs_torchvision_semantics(B, C, Co, H, W, scale):
+    """kmu_deformconv3x3_{fwd,bwd} vs the oracle restatement of torchvision.ops.deform_conv2d (pinned to torchvision's CPU op in
+    tests/test_oracle_dagem.py) in fp64, all four gradients; offsets large enough to leave the image."""
+    from km_unet_b200 import ops
+    from oracle import dagem as OD
+    g = torch.Generator().manual_seed(B * 100 + C + H)
+    x = torch.randn(B, C, H, W, generator=g)
+    off = torch.randn(B, 18, H, W, generator=g) * scale
+    w = torch.randn(Co, C, 3, 3, generator=g) * 0.2
+    bias = torch.randn(Co, generator=g)
+    gout = torch.randn(B, Co, H, W, generator=g)
+    ref = [t.double().requires_grad_(True) for t in (x, off, w, bias)]
+    want = OD.deform_conv2d(*ref, padding=1)
+    want.backward(gout.double())
+    got_in = [t.cuda().requires_grad_(True) for t in (x, off, w, bias)]
+    got = ops.deformconv3x3(*got_in)
+    got.backward(gout.cuda())
+    assert rel_err(got, want) < TOL
+    for a, b, name in zip(got_in, ref, ("dx", "doffset", "dweight", "dbias")):
+        assert rel_err(a.grad, b.grad) < TOL, name
+    # bit-reproducible (fixed-order reductions, no atomics)
+    again = [t.detach().clone().requires_grad_(True) for t in got_in]
+    ops.deformconv3x3(*again).backward(gout.cuda())
+    for a, b in zip(got_in, again):
+        assert torch.equal(a.grad, b.grad)
+
+
+def test_dagem_module_graph_replay_equals_eager():
+    """torchvision's deform_conv2d is dropped from CUDA-graph captures (legacy-stream launches): the module must not depend on it."""
+    from km_unet_b200 import DAGEM
+    torch.manual_seed(0)
+    m = DAGEM(input_channels=64).cuda().train()
+    with torch.no_grad():
+        m.offset_conv.weight.mul_(3.0)
+    x = torch.randn(4, 64, 16, 16, device="cuda")
+    state = {k: v.clone() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        want = m(x).clone()
+        m.load_state_dict(state)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            m(x)
+        torch.cuda.current_stream().wait_stream(s)
+        m.load_state_dict(state)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = m(x)
+        m.load_state_dict(state)
+        x2 = torch.randn(4, 64, 16, 16, device="cuda")
+        keep = x.clone()
+        x.copy_(x2)
+        g.replay()                      # different input: proves the replay recomputes the deformable columns
+        x.copy_(keep)
+        m.load_state_dict(state)
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, want)

@@ -52,6 +52,29 @@ def test_bnmix_vs_torch(B, C, H, W, training, relu, mix):
     assert rel_err(rmc, rm_ref) < TOL and rel_err(rvc, rv_ref) < TOL
 
 
+def test_bnmix_large_channel_offset_does_not_cancel():
+    """mean 100, std 0.1 -- E[x^2] - mean^2 in fp32 loses the variance entirely; the kernel shifts by a sample."""
+    from km_unet_b200 import ops
+    torch.manual_seed(3)
+    B, C, H, W = 4, 16, 32, 32
+    x = torch.randn(B, C, H, W) * 0.1 + 100.0 * (torch.arange(C).float().view(1, C, 1, 1) - 7.5)
+    w, b = torch.rand(C) + 0.5, torch.randn(C) * 0.2
+    rm, rv = torch.zeros(C), torch.ones(C)
+    gout = torch.randn(B, C, H, W)
+    xd, wd, bd = (t.double().requires_grad_(True) for t in (x, w, b))
+    rm_ref, rv_ref = rm.double().clone(), rv.double().clone()
+    want = _ref_bnmix(xd, wd, bd, rm_ref, rv_ref, True, False, None, None)
+    want.backward(gout.double())
+    xc, wc, bc = (t.cuda().requires_grad_(True) for t in (x, w, b))
+    rmc, rvc = rm.cuda(), rv.cuda()
+    y = ops.bnmix(xc, wc, bc, rmc, rvc, True, 0.1, 1e-5, False, None, None)
+    y.backward(gout.cuda())
+    # x itself carries ~1e-7 * 750 / 0.1 = 1e-3 of a standard deviation of fp32 representation error; the statistics must not add to it
+    assert rel_err(rvc, rv_ref) < 1e-4 and rel_err(rmc, rm_ref) < 1e-6
+    assert rel_err(y, want) < 2e-3
+    assert rel_err(wc.grad, wd.grad) < 2e-3 and rel_err(bc.grad, bd.grad) < 1e-4
+
+
 @pytest.mark.parametrize("B,C,H,W,bias", [(2, 16, 32, 32, False), (3, 8, 7, 5, True), (1, 64, 16, 16, True), (4, 16, 128, 128, False),
                                           (2, 4, 1, 1, True)])
 def test_dwconv3x3_vs_torch(B, C, H, W, bias):
