@@ -17,6 +17,8 @@
 //     hsm_proj_dw_bwd  dP -> dx += Wp^T dQ, per-CTA partials of dWp and dWd ; hsm_wgrad_reduce sums them in fixed order.
 // P is materialised in fp32 (B,192,L): with 180 GB of HBM3e that is cheaper than recomputing the projection in the
 // three backward sweeps on CUDA cores.  All reductions are deterministic (no atomics).
+#include <algorithm>
+#include <cstdlib>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -40,6 +42,17 @@ int contract(const float* x, const float* dy, const float* wp, const float* wd, 
 int backward(const float* x, const float* wp, const float* wd, const void* dPp, float* dx, float* dwp, float* dwd, int B, int C, int H,
              void* workspace, int x_packed, cudaStream_t st);
 }  // namespace tcb
+namespace fz {   // hsm_fused.cu: sweeps over L with P = dw3x3(Wp x) kept in TMEM (never written to HBM)
+size_t pack_bytes(int C);
+int tiles_per_image(int H);
+size_t merge_bytes(int B, int C, int H);
+int merge(const float* part_m, const float* part_s, const float* part_hs, int B, int C, int H, void* workspace, float** m1, float** s1,
+          float** hs1, cudaStream_t st);
+int forward_hs(const float* x, const float* wp, const float* wd, float* part_m, float* part_s, float* part_hs, int B, int C, int H,
+               void* workspace, cudaStream_t st);
+int dp(const float* x, const float* dy, const float* wp, const float* wd, const float* stats, const float* dhs, const float* ho,
+       const float* r, void* dPp, float* dx, int B, int C, int H, void* workspace, cudaStream_t st);
+}  // namespace fz
 
 constexpr int N = 64;         // states
 constexpr int N3 = 192;       // projected channels
@@ -901,19 +914,31 @@ static int check(const kmu_hsmssd_desc* d, const char* who) {
   return KMU_OK;
 }
 
-struct FwdWs { size_t part_m, part_s, part_hs, wpack, weff, total; };
+// KMU_HSM_FUSED=0 selects the round-1 tensor-core path (P written to HBM) for A/B measurements
+static bool fused_sweeps() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("KMU_HSM_FUSED");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+struct FwdWs { size_t part_m, part_s, part_hs, wpack, weff, merge, total; };
 static FwdWs fwd_ws(const Dims& d) {
   FwdWs w;
   size_t o = 0;
-  w.wpack = o; o += tc::pack_bytes(d.C);
+  const size_t T = (size_t)std::max(d.T, fz::tiles_per_image(d.H));    // per-tile partials of the fused sweep
+  w.wpack = o; o += std::max(tc::pack_bytes(d.C), fz::pack_bytes(d.C));
   w.weff = o; o += tc::weff_bytes(d.B, d.C);
-  w.part_m = o; o += align_up((size_t)d.B * d.T * 64 * 4, 256);
-  w.part_s = o; o += align_up((size_t)d.B * d.T * 64 * 4, 256);
-  w.part_hs = o; o += align_up((size_t)d.B * d.T * d.C * 64 * 4, 256);
+  w.part_m = o; o += align_up((size_t)d.B * T * 64 * 4, 256);
+  w.part_s = o; o += align_up((size_t)d.B * T * 64 * 4, 256);
+  w.part_hs = o; o += align_up((size_t)d.B * T * d.C * 64 * 4, 256);
+  w.merge = o; o += fz::merge_bytes(d.B, d.C, d.H);
   w.total = o;
   return w;
 }
-struct BwdWs { size_t part_dho, dhs, r, wpart, dP, tpart, total; };
+struct BwdWs { size_t part_dho, dhs, r, wpart, dP, tpart, wpk, total; };
 static BwdWs bwd_ws(const Dims& d, int precision) {
   BwdWs w;
   size_t o = 0;
@@ -924,6 +949,7 @@ static BwdWs bwd_ws(const Dims& d, int precision) {
   if (precision == KMU_PREC_BF16) {  // dP as bf16 planes; tpart = the tcgen05 backward's own workspace
     w.dP = o; o += tcb::dpp_bytes(d.B, d.L);
     w.tpart = o; o += tcb::workspace_bytes(d.B, d.C, d.H);
+    w.wpk = o; o += fz::pack_bytes(d.C);
   } else {
     w.dP = o; o += align_up((size_t)d.B * N3 * d.L * 4, 256);
     w.tpart = o; o += align_up((size_t)d.B * d.tiles_x * d.tiles_y * (N3 * d.C + N3 * 9) * 4, 256);
@@ -958,8 +984,9 @@ int kmu_hsmssd_fwd(const kmu_hsmssd_fwd_args* a, kmu_stream stream) {
   KMU_REQUIRE(a != nullptr, KMU_ERR_BAD_ARG, "hsmssd_fwd: null args");
   int st_ = check(&a->d, "hsmssd_fwd");
   if (st_ != KMU_OK) return st_;
-  KMU_REQUIRE(a->x && a->w_bcdt && a->w_dw && a->w_hz && a->w_out && a->D && a->y && a->h && a->P, KMU_ERR_BAD_ARG,
-              "hsmssd_fwd: null tensor (P scratch is required)");
+  const bool fused = a->d.precision == KMU_PREC_BF16 && fused_sweeps();
+  KMU_REQUIRE(a->x && a->w_bcdt && a->w_dw && a->w_hz && a->w_out && a->D && a->y && a->h && (a->P || fused), KMU_ERR_BAD_ARG,
+              "hsmssd_fwd: null tensor (the P scratch is required outside the fused bf16 path)");
   Dims d = make_dims(a->d);
   FwdWs w = fwd_ws(d);
   KMU_REQUIRE(a->workspace && a->workspace_bytes >= w.total, KMU_ERR_WORKSPACE, "hsmssd_fwd: workspace %zu < %zu",
@@ -969,7 +996,15 @@ int kmu_hsmssd_fwd(const kmu_hsmssd_fwd_args* a, kmu_stream stream) {
   float* part_m = (float*)(ws + w.part_m);
   float* part_s = (float*)(ws + w.part_s);
   float* part_hs = (float*)(ws + w.part_hs);
-  if (a->d.precision == KMU_PREC_BF16) {
+  Dims dc = d;                    // combine: number of partials per batch element
+  if (fused) {
+    // projection, tile-local softmax and the x (e . Bm)^T contraction in ONE kernel; P lives in TMEM only (hsm_fused.cu)
+    int rc = fz::forward_hs(a->x, a->w_bcdt, a->w_dw, part_m, part_s, part_hs, d.B, d.C, d.H, ws + w.wpack, st);
+    if (rc != KMU_OK) return rc;
+    rc = fz::merge(part_m, part_s, part_hs, d.B, d.C, d.H, ws + w.merge, &part_m, &part_s, &part_hs, st);
+    if (rc != KMU_OK) return rc;
+    dc.T = 1;
+  } else if (a->d.precision == KMU_PREC_BF16) {
     // Bm and dt slices only: y = ho Cm is folded into one more convolution of x (tc::out), d(ho) into a correlation (tcb::contract)
     int rc = tc::project(a->x, a->w_bcdt, a->w_dw, a->P, d.B, d.C, d.H, 2, ws + w.wpack, st);
     if (rc != KMU_OK) return rc;
@@ -990,7 +1025,7 @@ int kmu_hsmssd_fwd(const kmu_hsmssd_fwd_args* a, kmu_stream stream) {
 #undef KMU_HSM_PROJ
     KMU_LAUNCH_CHECK("hsm_proj_dw");
   }
-  {
+  if (!fused) {
     size_t smem = ((size_t)SUB * 65 + (size_t)d.C * SUB + 192) * 4;
     dim3 grid(d.T, d.B);
     if (d.C <= 16) {
@@ -1006,11 +1041,11 @@ int kmu_hsmssd_fwd(const kmu_hsmssd_fwd_args* a, kmu_stream stream) {
     KMU_LAUNCH_CHECK("hsm_softmax_hs");
   }
   {
-    size_t smem = ((size_t)4 * d.C * 64 + (size_t)3 * d.C * d.C + (size_t)d.T * 64) * 4;
-    KMU_REQUIRE(smem <= 220 * 1024, KMU_ERR_UNSUPPORTED, "hsmssd_fwd: L=%d too long for the per-batch combine (T=%d)", d.L, d.T);
+    size_t smem = ((size_t)4 * d.C * 64 + (size_t)3 * d.C * d.C + (size_t)dc.T * 64) * 4;
+    KMU_REQUIRE(smem <= 220 * 1024, KMU_ERR_UNSUPPORTED, "hsmssd_fwd: L=%d too long for the per-batch combine (T=%d)", d.L, dc.T);
     opt_in_smem(hsm_combine_gate_kernel, smem);
     hsm_combine_gate_kernel<<<dim3(d.B, GNS), GT, smem, st>>>(part_m, part_s, part_hs, a->w_hz, a->w_out, a->D, a->stats, a->hs, a->hz,
-                                                    a->h, d);
+                                                    a->h, dc);
     KMU_LAUNCH_CHECK("hsm_combine_gate");
   }
   if (a->d.precision == KMU_PREC_BF16) {
@@ -1028,7 +1063,8 @@ int kmu_hsmssd_bwd(const kmu_hsmssd_bwd_args* a, kmu_stream stream) {
   KMU_REQUIRE(a != nullptr, KMU_ERR_BAD_ARG, "hsmssd_bwd: null args");
   int st_ = check(&a->d, "hsmssd_bwd");
   if (st_ != KMU_OK) return st_;
-  KMU_REQUIRE(a->x && a->dy && a->w_bcdt && a->w_dw && a->w_hz && a->w_out && a->D && a->P && a->stats && a->hs && a->hz && a->h,
+  const bool fused = a->d.precision == KMU_PREC_BF16 && fused_sweeps();
+  KMU_REQUIRE(a->x && a->dy && a->w_bcdt && a->w_dw && a->w_hz && a->w_out && a->D && (a->P || fused) && a->stats && a->hs && a->hz && a->h,
               KMU_ERR_BAD_ARG, "hsmssd_bwd: null input tensor");
   KMU_REQUIRE(a->dx && a->d_w_bcdt && a->d_w_dw && a->d_w_hz && a->d_w_out && a->d_D, KMU_ERR_BAD_ARG,
               "hsmssd_bwd: null output tensor");
@@ -1075,7 +1111,11 @@ int kmu_hsmssd_bwd(const kmu_hsmssd_bwd_args* a, kmu_stream stream) {
     hsm_wgrad_reduce_kernel<<<cdiv(n, 32), 256, 0, st>>>(wpart, d.B * GNS, n, a->d_w_out, C * C, a->d_w_hz, 2 * C * C, a->d_D, 1);
     KMU_LAUNCH_CHECK("hsm_wgrad_reduce(gate)");
   }
-  {
+  if (fused) {
+    // P recomputed into TMEM (bit-identical to the forward's), dP planes + the direct part of dx from the same CTA (hsm_fused.cu)
+    int rc = fz::dp(a->x, a->dy, a->w_bcdt, a->w_dw, a->stats, dhs, a->h, r, dP, a->dx, d.B, C, d.H, ws + w.wpk, st);
+    if (rc != KMU_OK) return rc;
+  } else {
     size_t smem = ((size_t)2 * C * 64 + 192) * 4;
     dim3 grid(cdiv(d.L, 256), d.B);
 #define KMU_HSM_DP(CC)                                                                                              \

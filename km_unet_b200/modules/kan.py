@@ -37,7 +37,7 @@ class KANLinear(nn.Module):
         self.reset_parameters()
         # load_state_dict rewrites the knot table: refresh the cached knot summary right away (a device -> host read) so that
         # the next forward -- possibly under CUDA-graph capture, where such a read is illegal -- finds it valid
-        self.register_load_state_dict_post_hook(lambda module, incompatible: module._grid_meta() if module.grid.is_cuda else None)
+        self.register_load_state_dict_post_hook(KANLinear._refresh_grid_meta)
 
     # -- host-side helpers (init / grid adaptation only) -------------------------------------------------------
     def reset_parameters(self):
@@ -84,6 +84,11 @@ class KANLinear(nn.Module):
 
     def _precision(self):
         return config.precision_code(self.precision)
+
+    @staticmethod
+    def _refresh_grid_meta(module, incompatible_keys):
+        if module.grid.is_cuda:
+            module._grid_meta()
 
     def _grid_meta(self):
         """Cached (uniform_and_shared, t0, h) of the knot table, refreshed when the buffer is modified or moved."""

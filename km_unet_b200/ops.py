@@ -4,6 +4,7 @@ PyTorch is used for plumbing only: device memory (the caching allocator owns eve
 autograd bookkeeping.  All arithmetic happens in libkmunet.so.  CPU tensors raise -- there is no fallback.
 """
 import ctypes as C
+import os
 
 import torch
 from torch.amp import custom_bwd, custom_fwd
@@ -198,7 +199,9 @@ class _HsmssdFn(torch.autograd.Function):
         Ac, Dc = A.contiguous(), D.contiguous()
         y = torch.empty(B, Cc, L, dtype=torch.float32, device=dev)
         h = torch.empty(B, Cc, N, dtype=torch.float32, device=dev)
-        P = torch.empty(B, 3 * N, L, dtype=torch.float32, device=dev)
+        # the fused bf16 sweeps (csrc/hsm_fused.cu) keep P = dw3x3(Wp x) in TMEM: nothing to save (402 MB per call at (32,16,16384))
+        fused = int(precision) == KMU_PREC_BF16 and os.environ.get("KMU_HSM_FUSED", "1") != "0"
+        P = None if fused else torch.empty(B, 3 * N, L, dtype=torch.float32, device=dev)
         stats = torch.empty(B, 2, N, dtype=torch.float32, device=dev)
         hs = torch.empty(B, Cc, N, dtype=torch.float32, device=dev)
         hz = torch.empty(B, 2 * Cc, N, dtype=torch.float32, device=dev)

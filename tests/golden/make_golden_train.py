@@ -73,6 +73,8 @@ def main():
         e32 = TF.grad_errors({k: p.grad for k, p in m32.named_parameters()}, _Z(rec))
         worst32 = max(v[0] for v in e32.values())
         rec["ref32/grad_err"] = np.array(worst32)
+        thr = lambda a: np.stack([(np.clip(a, 0, 1) * 90).astype(np.uint16) >= t for t in (20, 30, 35, 40)])   # metrics.py:45-47,106-107
+        rec["ref32/mask_flips"] = np.array(int((thr(out32.detach().numpy()) != thr(out.detach().numpy())).sum()))
         rec["ref32/grad_l2"] = np.array(TF.grad_global_l2({k: p.grad for k, p in m32.named_parameters()}, _Z(rec)))
         for k, v in e32.items():                                     # the reference's own fp32 error per tensor: context for the gates
             rec["ref32g/" + k] = np.array(v)
@@ -82,7 +84,7 @@ def main():
         path = os.path.join(HERE, f"km_unetv3_{tag}_train_128.npz")
         np.savez_compressed(path, **rec)
         print(f"{tag}: {os.path.getsize(path) / 1e6:.2f} MB; {nlive} live parameters ({nelem} elements), {len(masks)} DropPath masks, "
-              f"loss {loss.item():.6f}; the reference's own fp32 vs fp64: out {rec['ref32/out_err']:.2e} loss {rec['ref32/loss_err']:.2e} "
+              f"loss {loss.item():.6f}; the reference's own fp32 vs fp64: out {rec['ref32/out_err']:.2e} ({int(rec['ref32/mask_flips'])} thresholded-mask cells flip) loss {rec['ref32/loss_err']:.2e} "
               f"grad max {worst32:.2e} median {np.median([v[0] for v in e32.values()]):.2e} global L2 {rec['ref32/grad_l2']:.2e}")
 
 
