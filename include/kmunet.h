@@ -175,9 +175,10 @@ int kmu_hsmssd_bwd(const kmu_hsmssd_bwd_args* a, kmu_stream stream);
 /* LayerNorm1D over the channel axis of (B,C,L): y = (x-mean_c)/sqrt(var_c+eps)*w + b  (biased variance). */
 int kmu_layernorm1d_fwd(const float* x, const float* weight, const float* bias, float* y, float* rstd /* (B,L) or NULL */,
                         int32_t B, int32_t C, int32_t L, float eps, kmu_stream stream);
-/* dweight/dbias are ACCUMULATED with atomics into zero-initialised (C) buffers. */
+/* dweight / dbias (C) are OVERWRITTEN; per-CTA partials in the workspace are summed in a fixed order (bit-reproducible). */
+size_t kmu_layernorm1d_bwd_workspace_bytes(int32_t B, int32_t C, int32_t L);
 int kmu_layernorm1d_bwd(const float* x, const float* weight, const float* dy, float* dx, float* dweight, float* dbias,
-                        int32_t B, int32_t C, int32_t L, float eps, kmu_stream stream);
+                        int32_t B, int32_t C, int32_t L, float eps, void* workspace, size_t workspace_bytes, kmu_stream stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * D: DySample ('lp' style, dyscope off)        DySample_md.py:49-68

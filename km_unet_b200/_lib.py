@@ -148,8 +148,9 @@ SYMBOLS = {
     "kmu_hsmssd_bwd": (C.c_int, [C.POINTER(HsmBwdArgs), C.c_void_p]),
     "kmu_layernorm1d_fwd": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                       C.c_void_p]),
+    "kmu_layernorm1d_bwd_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "kmu_layernorm1d_bwd": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
-                                      C.c_void_p]),
+                                      C.c_void_p, C.c_size_t, C.c_void_p]),
     "kmu_dysample_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(DysDesc)]),
     "kmu_dysample_fwd": (C.c_int, [C.POINTER(DysFwdArgs), C.c_void_p]),
     "kmu_dysample_bwd": (C.c_int, [C.POINTER(DysBwdArgs), C.c_void_p]),

@@ -23,8 +23,9 @@ def precision_code(name=None):
     if name not in ("fp32", "bf16"):
         raise ValueError(f"unknown KAN precision {name!r} (expected 'fp32' or 'bf16')")
     return KMU_PREC_BF16 if name == "bf16" else KMU_PREC_FP32
-# pairs the TMA pipelines do not take (Cin + Cout too wide for the tile ring): "tc" = per-tile tcgen05 kernels of pwconv_tc.cu,
-# "simt" = fp32 streaming kernels
-conv_wide = os.environ.get("KMU_CONV_WIDE", "tc")
+# pairs the TMA pipelines do not take (Cin = 256: the tile ring does not fit): "simt" = fp32 streaming kernels (default: these few
+# layers were the largest remaining source of end-to-end error when run with plain bf16 operands, tools/bf16_ablation.py),
+# "tc" = per-tile tcgen05 kernels of pwconv_tc.cu (bf16 operands)
+conv_wide = os.environ.get("KMU_CONV_WIDE", "simt")
 # EfficientViMBlock's mixer layer-scale (torch.lerp with a broadcast weight) through kmu_lerpmix (one pass per direction)
 fused_lerp = os.environ.get("KMU_FUSED_LERP", "1") == "1"

@@ -858,11 +858,8 @@ __global__ void __launch_bounds__(256) ln1d_fwd_kernel(const float* __restrict__
 
 __global__ void __launch_bounds__(256) ln1d_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                        const float* __restrict__ dy, float* __restrict__ dx,
-                                                       float* __restrict__ dw, float* __restrict__ db, int B, int C, int L,
-                                                       float eps) {
-  extern __shared__ float red[];  // [2][C]
-  for (int i = threadIdx.x; i < 2 * C; i += 256) red[i] = 0.f;
-  __syncthreads();
+                                                       float* __restrict__ part, int B, int C, int L, float eps) {
+  extern __shared__ float red[];  // [8 warps][2 C]: per-warp sums, combined in warp order (no atomics: bit-reproducible)
   long long p = (long long)blockIdx.x * 256 + threadIdx.x;
   const bool valid = p < (long long)B * L;
   int b = valid ? (int)(p / L) : 0, l = valid ? (int)(p - (long long)b * L) : 0;
@@ -896,10 +893,34 @@ __global__ void __launch_bounds__(256) ln1d_bwd_kernel(const float* __restrict__
       dx[(size_t)b * C * L + (size_t)c * L + l] = rstd * (gy * w[c] - m1 - xh * m2);
     }
     float sw = warp_sum(gy * xh), sb = warp_sum(gy);
-    if (lane == 0) { atomicAdd(&red[c], sw); atomicAdd(&red[C + c], sb); }
+    if (lane == 0) { red[(threadIdx.x >> 5) * 2 * C + c] = sw; red[(threadIdx.x >> 5) * 2 * C + C + c] = sb; }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += 256) { atomicAdd(dw + i, red[i]); atomicAdd(db + i, red[C + i]); }
+  for (int i = threadIdx.x; i < 2 * C; i += 256) {
+    float a = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) a += red[w8 * 2 * C + i];
+    part[(size_t)blockIdx.x * 2 * C + i] = a;
+  }
+}
+
+// dw[c] = sum over blocks of part[blk][c], db[c] = ... part[blk][C + c]: 32 outputs x 8 interleaved slices of the block list per CTA
+__global__ void __launch_bounds__(256) ln1d_bwd_reduce_kernel(const float* __restrict__ part, int nblk, int C, float* __restrict__ dw,
+                                                              float* __restrict__ db) {
+  __shared__ float red[8][33];
+  const int o = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 32 + o;
+  float s = 0.f;
+  if (idx < 2 * C)
+    for (int k = sl; k < nblk; k += 8) s += part[(size_t)k * 2 * C + idx];
+  red[sl][o] = s;
+  __syncthreads();
+  if (sl == 0 && idx < 2 * C) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += red[q][o];
+    if (idx < C) dw[idx] = t; else db[idx - C] = t;
+  }
 }
 
 static int check(const kmu_hsmssd_desc* d, const char* who) {
@@ -1175,14 +1196,26 @@ int kmu_layernorm1d_fwd(const float* x, const float* weight, const float* bias, 
   return KMU_OK;
 }
 
+size_t kmu_layernorm1d_bwd_workspace_bytes(int32_t B, int32_t C, int32_t L) {
+  if (B <= 0 || C <= 0 || L <= 0) return 0;
+  return align_up((size_t)cdiv((long long)B * L, 256) * 2 * C * 4, 256);
+}
+
 int kmu_layernorm1d_bwd(const float* x, const float* weight, const float* dy, float* dx, float* dweight, float* dbias, int32_t B,
-                        int32_t C, int32_t L, float eps, kmu_stream stream) {
+                        int32_t C, int32_t L, float eps, void* workspace, size_t workspace_bytes, kmu_stream stream) {
   KMU_REQUIRE(x && weight && dy && dx && dweight && dbias && B > 0 && C > 0 && L > 0, KMU_ERR_BAD_ARG,
               "layernorm1d_bwd: bad argument");
-  KMU_REQUIRE(C <= 4096, KMU_ERR_UNSUPPORTED, "layernorm1d_bwd: C=%d > 4096", C);
-  ln1d_bwd_kernel<<<cdiv((long long)B * L, 256), 256, (size_t)2 * C * 4, (cudaStream_t)stream>>>(x, weight, dy, dx, dweight, dbias,
-                                                                                                B, C, L, eps);
+  KMU_REQUIRE(C <= 1024, KMU_ERR_UNSUPPORTED, "layernorm1d_bwd: C=%d > 1024", C);
+  KMU_REQUIRE(workspace && workspace_bytes >= kmu_layernorm1d_bwd_workspace_bytes(B, C, L), KMU_ERR_WORKSPACE,
+              "layernorm1d_bwd: workspace too small");
+  const int nblk = cdiv((long long)B * L, 256);
+  float* part = (float*)workspace;
+  const size_t smem = (size_t)16 * C * 4;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(ln1d_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  ln1d_bwd_kernel<<<nblk, 256, smem, (cudaStream_t)stream>>>(x, weight, dy, dx, part, B, C, L, eps);
   KMU_LAUNCH_CHECK("ln1d_bwd");
+  ln1d_bwd_reduce_kernel<<<cdiv(2 * C, 32), 256, 0, (cudaStream_t)stream>>>(part, nblk, C, dweight, dbias);
+  KMU_LAUNCH_CHECK("ln1d_bwd_reduce");
   return KMU_OK;
 }
 

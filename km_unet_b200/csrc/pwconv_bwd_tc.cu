@@ -58,6 +58,23 @@ __device__ __forceinline__ void pack_weights_smem(const float* __restrict__ w, u
   }
 }
 
+// residual image of the same weights: bf16(w - bf16(w)) -- the low half of the split-bf16 forward (x = hi + lo to ~16 mantissa bits)
+__device__ __forceinline__ void pack_weights_lo_smem(const float* __restrict__ w, uint8_t* w_base, int NI, int NJ) {
+  const int total = NI * NJ / 8;
+  for (int u = threadIdx.x; u < total; u += blockDim.x) {
+    const int n = u % NJ, r = u / NJ;
+    const int k0 = r * 8;
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float v = __ldg(w + (size_t)n * NI + k0 + e);
+      f[e] = v - __bfloat162float(__float2bfloat16_rn(v));
+    }
+    *reinterpret_cast<uint4*>(w_base + (size_t)u * 16) =
+        make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  }
+}
+
 struct Plan {
   int Cin, Cout, HW, B;
   int MH, Np;            // 128-row halves of Cout; UMMA N of the wgrad GEMM (Cin + ones group + zero group)
@@ -266,7 +283,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_bwd_fused_kernel(const __grid_
 struct FwdPlan {
   int Cin, Cout, HW, B;
   int NST;               // raw stages
-  int raw_stage, plane_buf, wbytes, tmem_cols;
+  int raw_stage, plane_buf, wbytes, tmem_cols, NPL;
   int tiles_per_img, ntiles, ctas;
   size_t smem;
 };
@@ -275,9 +292,12 @@ __global__ void __launch_bounds__(NTHREADS) pw_fwd_tma_kernel(const __grid_const
                                                               const float* __restrict__ w, const float* __restrict__ bias,
                                                               float* __restrict__ y, const FwdPlan pl) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* pl_base = smem;                                                 // [2][Cin/8][128][16 B]
-  uint8_t* raw_base = pl_base + (size_t)2 * pl.plane_buf;                  // [NST][Cin][128] fp32
-  uint8_t* w_base = raw_base + (size_t)pl.NST * pl.raw_stage;              // [Cin/16][2][Cout][16 B]
+  // Split-bf16 operands: every fp32 value is fed to the tensor core as hi + lo (hi = bf16(v), lo = bf16(v - hi)) and the product as
+  // hi*hi + lo*hi + hi*lo -- ~16 mantissa bits instead of 8 at three times the MMA work, which is free here (the kernel is HBM-bound).
+  // The bf16-only version was the largest single source of end-to-end error of the tensor-core precision class (tools/bf16_ablation.py).
+  uint8_t* pl_base = smem;                                                 // [2][hi, lo][Cin/8][128][16 B]
+  uint8_t* raw_base = pl_base + (size_t)pl.NPL * pl.plane_buf;                  // [NST][Cin][128] fp32
+  uint8_t* w_base = raw_base + (size_t)pl.NST * pl.raw_stage;              // [hi, lo][Cin/16][2][Cout][16 B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(w_base + pl.wbytes);
   uint64_t* raw_full = bars;                 // [MAXST]
   uint64_t* raw_empty = bars + MAXST;        // [MAXST]
@@ -290,6 +310,7 @@ __global__ void __launch_bounds__(NTHREADS) pw_fwd_tma_kernel(const __grid_const
   const int Cin = pl.Cin, Cout = pl.Cout, HW = pl.HW;
 
   pack_weights_smem(w, w_base, pl.Cin, pl.Cout, false);     // forward: K = Cin, N = Cout
+  pack_weights_lo_smem(w, w_base + pl.wbytes / 2, pl.Cin, pl.Cout);
   if (tid == 0) {
     for (int i = 0; i < MAXST; ++i) {
       mbar_init(smem_u32(&raw_full[i]), 1);
@@ -329,17 +350,22 @@ __global__ void __launch_bounds__(NTHREADS) pw_fwd_tma_kernel(const __grid_const
       const int KS = Cin / 16;
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < pl.ntiles; tile += gridDim.x, ++it) {
-        const uint32_t pb = it & 1u, ph = (it >> 1) & 1u;
-        mbar_wait_hot(smem_u32(&acc_empty[pb]), ph ^ 1u);
+        const uint32_t ab = it & 1u, ah = (it >> 1) & 1u;                               // accumulator buffer / phase
+        const uint32_t pb = it % (uint32_t)pl.NPL, ph = (it / (uint32_t)pl.NPL) & 1u;   // plane buffer / phase
+        mbar_wait_hot(smem_u32(&acc_empty[ab]), ah ^ 1u);
         mbar_wait_hot(smem_u32(&pl_full[pb]), ph);
         tc_fence_after();
         const uint64_t adesc0 = make_smem_desc(smem_u32(pl_base + (size_t)pb * pl.plane_buf), PLANE, 128);
-        const uint32_t d_acc = tmem_base + pb * (uint32_t)Cout;
-        for (int ks = 0; ks < KS; ++ks)
-          umma_bf16(d_acc, desc_advance(adesc0, (uint32_t)(ks * 2 * PLANE)), desc_advance(wdesc0, (uint32_t)(ks * 2 * Cout * 16)), idesc,
-                    ks > 0 ? 1u : 0u);
+        const uint32_t d_acc = tmem_base + ab * (uint32_t)Cout;
+        const uint32_t a_lo = (uint32_t)(pl.plane_buf / 2), w_lo = (uint32_t)(pl.wbytes / 2);
+        for (int ks = 0; ks < KS; ++ks) {
+          const uint32_t ao = (uint32_t)(ks * 2 * PLANE), wo = (uint32_t)(ks * 2 * Cout * 16);
+          umma_bf16(d_acc, desc_advance(adesc0, ao + a_lo), desc_advance(wdesc0, wo), idesc, ks > 0 ? 1u : 0u);   // lo * hi (small terms first)
+          umma_bf16(d_acc, desc_advance(adesc0, ao), desc_advance(wdesc0, wo + w_lo), idesc, 1u);                 // hi * lo
+          umma_bf16(d_acc, desc_advance(adesc0, ao), desc_advance(wdesc0, wo), idesc, 1u);                        // hi * hi
+        }
         umma_commit(smem_u32(&pl_empty[pb]));
-        umma_commit(smem_u32(&acc_full[pb]));
+        umma_commit(smem_u32(&acc_full[ab]));
       }
     }
   } else {
@@ -370,17 +396,22 @@ __global__ void __launch_bounds__(NTHREADS) pw_fwd_tma_kernel(const __grid_const
     uint32_t it = 0;
     int prev_tile = -1;
     for (int tile = blockIdx.x; tile < pl.ntiles; tile += gridDim.x, ++it) {
-      const uint32_t s = it % (uint32_t)pl.NST, pb = it & 1u;
+      const uint32_t s = it % (uint32_t)pl.NST, pb = it % (uint32_t)pl.NPL;
       mbar_wait(smem_u32(&raw_full[s]), (it / (uint32_t)pl.NST) & 1u);
-      mbar_wait(smem_u32(&pl_empty[pb]), ((it >> 1) & 1u) ^ 1u);
+      mbar_wait(smem_u32(&pl_empty[pb]), ((it / (uint32_t)pl.NPL) & 1u) ^ 1u);
       const float* rx = reinterpret_cast<const float*>(raw_base + (size_t)s * pl.raw_stage) + px;
       uint8_t* pa = pl_base + (size_t)pb * pl.plane_buf + (size_t)px * 16;
       for (int g = gpar; g < gx; g += 2) {
-        float f[8];
+        float f[8], l[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = rx[(g * 8 + e) * TPX];
+        for (int e = 0; e < 8; ++e) {
+          f[e] = rx[(g * 8 + e) * TPX];
+          l[e] = f[e] - __bfloat162float(__float2bfloat16_rn(f[e]));
+        }
         *reinterpret_cast<uint4*>(pa + (size_t)g * PLANE) =
             make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+        *reinterpret_cast<uint4*>(pa + (size_t)(pl.plane_buf / 2) + (size_t)g * PLANE) =
+            make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -491,24 +522,27 @@ static bool make_fwd_plan(const kmu_pwconv_desc& d, FwdPlan* out) {
   FwdPlan p;
   p.Cin = d.Cin; p.Cout = d.Cout; p.HW = d.HW; p.B = d.B;
   p.raw_stage = d.Cin * 512;
-  p.plane_buf = (d.Cin / 8) * PLANE;
-  p.wbytes = d.Cin * d.Cout * 2;
+  p.plane_buf = 2 * (d.Cin / 8) * PLANE;       // hi and lo planes
+  p.wbytes = 2 * d.Cin * d.Cout * 2;           // hi and lo weights
   p.tmem_cols = pow2_cols(2 * d.Cout);
   // two CTAs per SM when shared memory and TMEM allow it: the store-heavy epilogue of one overlaps the other's loads
-  int per_sm = p.tmem_cols <= 256 ? 2 : 1;
-  int budget = (per_sm == 2 ? 108 : 220) * 1024 - 2 * p.plane_buf - p.wbytes - 512;
-  p.NST = budget / p.raw_stage;
-  if (p.NST < 2 && per_sm == 2) {   // wide inputs: one CTA per SM with the whole shared memory
-    per_sm = 1;
-    budget = 220 * 1024 - 2 * p.plane_buf - p.wbytes - 512;
-    p.NST = budget / p.raw_stage;
+  // in order of preference: two CTAs per SM (the store-heavy epilogue of one overlaps the other's loads) with two plane buffers,
+  // two CTAs with one plane buffer (the conversion of tile i + 1 then waits for the MMAs of tile i), one CTA with two / one buffers
+  int per_sm = 1;
+  p.NST = 0;
+  for (int choice = 0; choice < 4 && p.NST < 2; ++choice) {
+    per_sm = choice < 2 ? 2 : 1;
+    p.NPL = (choice & 1) ? 1 : 2;
+    if (per_sm == 2 && p.tmem_cols > 256) continue;
+    const int budget = (per_sm == 2 ? 108 : 220) * 1024 - p.NPL * p.plane_buf - p.wbytes - 512;
+    p.NST = budget > 0 ? budget / p.raw_stage : 0;
   }
   if (p.NST < 2) return false;
   if (p.NST > MAXST) p.NST = MAXST;
   p.tiles_per_img = cdiv(d.HW, TPX);
   p.ntiles = d.B * p.tiles_per_img;
   p.ctas = p.ntiles < 148 * per_sm ? p.ntiles : 148 * per_sm;
-  p.smem = (size_t)p.NST * p.raw_stage + (size_t)2 * p.plane_buf + p.wbytes + 256;
+  p.smem = (size_t)p.NST * p.raw_stage + (size_t)p.NPL * p.plane_buf + p.wbytes + 256;
   *out = p;
   return true;
 }

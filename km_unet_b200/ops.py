@@ -165,10 +165,11 @@ class _LayerNorm1dFn(torch.autograd.Function):
         B, Cc, L = x.shape
         dy = dy.to(torch.float32).contiguous()
         dx = torch.empty_like(x)
-        dw = torch.zeros_like(w)
-        db = torch.zeros_like(w)
+        dw = torch.empty_like(w)
+        db = torch.empty_like(w)
+        ws = _workspace(lib.kmu_layernorm1d_bwd_workspace_bytes(B, Cc, L), x.device)
         check(_call("kmu_layernorm1d_bwd", (B, Cc, L), lib.kmu_layernorm1d_bwd, ptr(x), ptr(w), ptr(dy), ptr(dx), ptr(dw), ptr(db), B, Cc, L,
-                    ctx.eps, stream_ptr()), "kmu_layernorm1d_bwd")
+                    ctx.eps, ws.data_ptr(), ws.numel(), stream_ptr()), "kmu_layernorm1d_bwd")
         return dx, dw.reshape(ctx.wshape), db.reshape(ctx.wshape), None
 
 
