@@ -6,6 +6,8 @@
 // with off_x = offset[b, (g*s+i)*s+j, h, w], off_y = offset[b, G*s*s + (g*s+i)*s+j, h, w]   (SURVEY appendix A.3).
 // HBM-bound gather: reads x once, writes s*s times as much; stores are 128-bit, loads of the four taps of
 // neighbouring output pixels fall in the same cache lines.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace kmu {
@@ -155,6 +157,131 @@ __global__ void __launch_bounds__(256, 2) dys_sample_fwd_kernel(const float* __r
       for (int e = 0; e < VEC; ++e) op[(size_t)c * OHW + e] = res[e];
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------- fused forward
+// ONE kernel for DySample.forward_lp (scale 2, 4 groups): CTA = (b, band of TH input rows, full width).
+//   1. the band of x (+ one halo row above and below, all C channels) is loaded ONCE with 128-bit loads into shared memory;
+//   2. the 1x1 offset convolution (C -> 32) of the band's pixels is computed from that tile (no second pass over x, and the
+//      offset tensor is only written to HBM when the caller wants it saved for backward);
+//   3. every output pixel (2 TH rows x 2 W columns x C channels) takes its four bilinear taps from shared memory (conflict-free:
+//      a warp's taps span 17 consecutive floats) and is written with 128-byte coalesced streaming stores.  Samples whose taps leave the staged rows (|offset| > 1 row) read global memory.
+// HBM traffic = x once (+ 50 % halo rows) + out once: the algorithmic 20 B / input element + 2 B.
+constexpr int FT = 256;   // threads of the fused kernel
+// W (= H: square maps) and C are template parameters: every stride of the sampling loop is then an immediate (the first version spent
+// ~20 integer instructions per output element on address arithmetic and was issue-bound at 69 % with the LSU half idle).
+template <int TH, int W, int C>
+__global__ void __launch_bounds__(FT, 2) dys_fused_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, const float* __restrict__ init_pos,
+                                                              float* __restrict__ offset, float* __restrict__ out, int B) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int H = W, NP = TH * W, ROWS = TH + 2;
+  float* xs = sm;                                 // [C][ROWS][W]
+  float* ws = xs + (size_t)C * ROWS * W;          // [C][32]
+  float* offs = ws + (size_t)C * 32;              // [32][NP]
+  const int tid = threadIdx.x, b = blockIdx.y, h0 = blockIdx.x * TH;
+  constexpr size_t HW = (size_t)H * W;
+  const float* xb = x + (size_t)b * C * HW;
+  (void)B;
+  // ---- 1. stage
+  for (int i = tid; i < C * 32; i += FT) {
+    const int c = i >> 5, j = i & 31;
+    ws[i] = __ldg(w + (size_t)j * C + c);
+  }
+  {
+    constexpr int W4 = W >> 2, lw = W == 16 ? 2 : W == 32 ? 3 : W == 64 ? 4 : 5;
+    constexpr int n4 = C * ROWS * W4;
+    for (int i = tid; i < n4; i += FT) {
+      const int q = i & (W4 - 1), cr = i >> lw;                      // cr = c * ROWS + r
+      const int c = cr / ROWS, r = cr - c * ROWS;
+      const int gy = h0 - 1 + r;
+      if (gy >= 0 && gy < H)
+        *reinterpret_cast<float4*>(xs + (size_t)cr * W + 4 * q) = __ldg(reinterpret_cast<const float4*>(xb + (size_t)c * HW + (size_t)gy * W) + q);
+    }
+  }
+  __syncthreads();
+  // ---- 2. offsets: thread = (pixel, block of OCB offset channels), weights as broadcast 128-bit loads
+  {
+    constexpr int TPP = FT / NP, OCB = 32 / TPP;  // threads per pixel, offset channels per thread: 4, 8, 16 or 32
+    const int p = tid % NP, oc0 = (tid / NP) * OCB;
+    const int hl = p / W, wv = p - hl * W;
+    if (h0 + hl < H) {
+      float4 acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* xp = xs + (size_t)(hl + 1) * W + wv;
+      for (int c = 0; c < C; ++c) {
+        const float xv = xp[(size_t)c * ROWS * W];
+        const float4* wr = reinterpret_cast<const float4*>(ws + c * 32 + oc0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (4 * j < OCB) {
+            const float4 ww = wr[j];
+            acc[j].x = fmaf(xv, ww.x, acc[j].x); acc[j].y = fmaf(xv, ww.y, acc[j].y);
+            acc[j].z = fmaf(xv, ww.z, acc[j].z); acc[j].w = fmaf(xv, ww.w, acc[j].w);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (4 * j < OCB) {
+          const float a4[4] = {acc[j].x, acc[j].y, acc[j].z, acc[j].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int oc = oc0 + 4 * j + e;
+            const float v = (a4[e] + __ldg(bias + oc)) * 0.25f + __ldg(init_pos + oc);
+            offs[oc * NP + p] = v;
+            if (offset) offset[((size_t)b * 32 + oc) * HW + (size_t)(h0 + hl) * W + wv] = v;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- 3. sample: thread = one output pixel of one group (lanes = consecutive output columns: pairs of lanes share their taps'
+  //         columns, a warp's taps span 16 + 1 consecutive floats of a row -> conflict-free LDS, 128-byte coalesced stores)
+  constexpr int OW = 2 * W, Cg = C >> 2;
+  constexpr size_t OHW = (size_t)4 * HW;
+  constexpr int items = 4 * (2 * TH) * OW;
+  for (int it = tid; it < items; it += FT) {
+    const int ow = it % OW, orl = (it / OW) % (2 * TH), g = it / (OW * 2 * TH);
+    const int hl = orl >> 1, i = orl & 1, h = h0 + hl;
+    if (h >= H) continue;
+    const int wv = ow >> 1, j = ow & 1;
+    const int ch = (g * 2 + i) * 2 + j;
+    const float ox = offs[ch * NP + hl * W + wv], oy = offs[(16 + ch) * NP + hl * W + wv];
+    const Coord c = make_coord((float)wv + ox, (float)h + oy, W, H);
+    const int yl = c.y0 - (h0 - 1);                         // row inside the staged tile
+    const bool inwin = yl >= 0 && yl + (c.y1ok ? 1 : 0) < ROWS;
+    const int o00 = yl * W + c.x0, dxo = c.x1ok ? 1 : 0, dyo = c.y1ok ? W : 0;
+    const float wx1 = c.x1ok ? c.fx : 0.f, wy1 = c.y1ok ? c.fy : 0.f;
+    const float wx0 = 1.f - c.fx, wy0 = 1.f - c.fy;
+    const float w00 = wx0 * wy0, w01 = wx1 * wy0, w10 = wx0 * wy1, w11 = wx1 * wy1;
+    float* op = out + ((size_t)b * C + (size_t)g * Cg) * OHW + (size_t)(2 * h + i) * OW + ow;
+    if (inwin) {
+      const float* t0 = xs + (size_t)g * Cg * ROWS * W + o00;
+      const float *t1 = t0 + dxo, *t2 = t0 + dyo, *t3 = t0 + dyo + dxo;
+#pragma unroll
+      for (int cc = 0; cc < Cg; ++cc)
+        __stcs(op + (size_t)cc * OHW, t0[cc * ROWS * W] * w00 + t1[cc * ROWS * W] * w01 + t2[cc * ROWS * W] * w10 + t3[cc * ROWS * W] * w11);
+    } else {                                                // a tap left the staged rows: same arithmetic from global memory
+      const float* t0 = xb + (size_t)g * Cg * HW + (ptrdiff_t)(h0 - 1) * W + o00;
+      for (int cc = 0; cc < Cg; ++cc) {
+        const float* t = t0 + (size_t)cc * HW;
+        __stcs(op + (size_t)cc * OHW, __ldg(t) * w00 + __ldg(t + dxo) * w01 + __ldg(t + dyo) * w10 + __ldg(t + dyo + dxo) * w11);
+      }
+    }
+  }
+}
+
+static bool fused_fwd_ok(const Dims& d, int* th, size_t* smem) {
+  if (d.s != 2 || d.G != 4 || d.C != 64 || d.H != d.W) return false;
+  if (d.W != 16 && d.W != 32 && d.W != 64 && d.W != 128) return false;
+  const int TH = 2;
+  if (TH * d.W > FT) return false;
+  *th = TH;
+  *smem = ((size_t)d.C * (TH + 2) * d.W + (size_t)d.C * 32 + (size_t)32 * TH * d.W) * 4;
+  return *smem <= 200 * 1024;
 }
 
 // ---------------------------------------------------------------------------------------------- sample (bwd)
@@ -380,10 +507,34 @@ int kmu_dysample_fwd(const kmu_dysample_fwd_args* a, kmu_stream stream) {
   KMU_REQUIRE(a != nullptr, KMU_ERR_BAD_ARG, "dysample_fwd: null args");
   int st_ = check(&a->d, "dysample_fwd");
   if (st_ != KMU_OK) return st_;
-  KMU_REQUIRE(a->x && a->w_offset && a->b_offset && a->init_pos && a->offset && a->out, KMU_ERR_BAD_ARG,
-              "dysample_fwd: null tensor");
+  KMU_REQUIRE(a->x && a->w_offset && a->b_offset && a->init_pos && a->out, KMU_ERR_BAD_ARG, "dysample_fwd: null tensor");
   Dims d = make_dims(a->d);
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    int th = 0;
+    size_t fsm = 0;
+    static const bool fused_on = !(getenv("KMU_DYS_FUSED") && getenv("KMU_DYS_FUSED")[0] == '0');
+    if (fused_on && fused_fwd_ok(d, &th, &fsm) && ((uintptr_t)a->x & 15) == 0 && ((uintptr_t)a->out & 15) == 0) {
+#define KMU_DYS_FUSED(WW)                                                                                                          \
+  do {                                                                                                                             \
+    cudaError_t e = cudaFuncSetAttribute(dys_fused_fwd_kernel<2, WW, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);   \
+    KMU_REQUIRE(e == cudaSuccess, KMU_ERR_LAUNCH, "dysample_fwd: cannot opt in to %zu B shared memory: %s", fsm,                  \
+                cudaGetErrorString(e));                                                                                            \
+    dys_fused_fwd_kernel<2, WW, 64><<<dim3(cdiv(d.H, th), d.B), FT, fsm, st>>>(a->x, a->w_offset, a->b_offset, a->init_pos,       \
+                                                                                a->offset, a->out, d.B);                           \
+  } while (0)
+      switch (d.W) {
+        case 16: KMU_DYS_FUSED(16); break;
+        case 32: KMU_DYS_FUSED(32); break;
+        case 64: KMU_DYS_FUSED(64); break;
+        default: KMU_DYS_FUSED(128); break;
+      }
+#undef KMU_DYS_FUSED
+      KMU_LAUNCH_CHECK("dys_fused_fwd");
+      return KMU_OK;
+    }
+  }
+  KMU_REQUIRE(a->offset, KMU_ERR_BAD_ARG, "dysample_fwd: the two-kernel path needs the offset buffer");
   long long npix = (long long)d.B * d.H * d.W;
   size_t smem = (size_t)d.C * 32 * 4;
   if (smem > 48 * 1024)

@@ -26,7 +26,10 @@ def test_dysample_golden(name, ch):
     assert rel_err(m.offset.bias.grad, want["offset.bias"]) < TOL
 
 
-@pytest.mark.parametrize("B,C,H,W,std", [(2, 64, 16, 16, 0.001), (1, 64, 32, 32, 0.05), (2, 16, 9, 7, 0.3), (1, 8, 5, 5, 1.0)])
+@pytest.mark.parametrize("B,C,H,W,std", [(2, 64, 16, 16, 0.001), (1, 64, 32, 32, 0.05), (2, 16, 9, 7, 0.3), (1, 8, 5, 5, 1.0),
+                                         # the fused forward (W in 16..128): small offsets (taps in the staged rows), large ones (the
+                                         # global-memory path for taps that leave them), a ragged channel count, 128 wide
+                                         (2, 64, 64, 64, 0.02), (2, 64, 32, 32, 0.5), (1, 32, 16, 16, 1.0), (1, 64, 128, 128, 0.1)])
 def test_dysample_vs_oracle(B, C, H, W, std):
     from km_unet_b200 import DySample
     from oracle import dysample as O
