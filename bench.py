@@ -664,6 +664,7 @@ def run_model(h, args):
                 "buckets": len(graphed.reducer.buckets), "bytes_per_step": sum(f.numel() * 4 for _, f in graphed.reducer.buckets),
                 "ms_per_step_without_allreduce": nocomm_ms / args.steps,
                 "exposed_comm_ms": (total_ms - nocomm_ms) / args.steps}
+        nocomm.close()
         del nocomm
 
     # op-level profile of the same step: CUDA events on the launching stream around every libkmunet call
@@ -719,6 +720,8 @@ def run_model(h, args):
         sb = cpu_sample_batch(args.workload)
         v, ms, cores, kind = time_cpu_oracle(args.workload, sb, 2, 1)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": cpu_sample_text(2, 1, sb, kind)}
+    if graphed is not None:
+        graphed.close()                # a graph holding NCCL kernels must be gone before destroy_process_group()
     gpu_ref = None
     if rank == 0 and world == 1 and not args.no_gpu_reference:
         graphed = None
@@ -779,7 +782,12 @@ def main():
     else:
         run_model(h, args)
     if h.world > 1:
-        h.dist.destroy_process_group()
+        # every rank is done and the line is out: leave without tearing NCCL down.  destroy_process_group() blocks for ever when a CUDA
+        # graph that recorded NCCL kernels is still alive anywhere (measured: 900 s hang), and nothing after this point matters.
+        h.barrier()
+        _REAL_STDOUT.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 

@@ -109,6 +109,16 @@ class GraphedTrainStep:
                     torch._foreach_copy_([p.grad.reshape(-1) for p in ps], list(flat.split([p.numel() for p in ps])))
         self.optimizer.step()
 
+    def close(self):
+        """Drop the captured graphs.  With comm="captured" they hold NCCL kernels: the process group must not be destroyed
+        (dist.destroy_process_group hangs) while such a graph is alive."""
+        self.graph_a = self.graph_b = None
+        if self.reducer is not None:
+            self.reducer.remove()
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+
     def __call__(self, x=None, t=None):
         """Run one step on (x, t) (copied into the graph's static inputs; None = reuse what is there) -> loss tensor (static)."""
         if x is not None:
