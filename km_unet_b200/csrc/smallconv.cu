@@ -15,6 +15,7 @@ namespace sc {
 
 constexpr int NTH = 128;
 constexpr int MAXT = 9;
+constexpr int TP = 64;      // pixels per tile of the weight-gradient kernels
 
 struct Taps {
   int T;
@@ -101,9 +102,157 @@ __global__ void __launch_bounds__(NTH) sc_kernel(const float* __restrict__ in, c
   }
 }
 
+// ---- 1x3 / 3x1 specialisation (the DirectionViM projections): thread = 4 consecutive pixels of a row x 16 outputs.
+//      The centre tap is one 128-bit load per input channel; a horizontal conv builds its two shifted vectors from that load plus
+//      one scalar on each side, a vertical conv takes two more 128-bit loads.  64 accumulators per thread, 192 FMA per channel for
+//      3 (vertical) / 3 (horizontal: 1 vector + 2 scalars) loads and 12 broadcast LDS.128 of weights.
+//      grid (ceil(HW / 512), ceil(NJ / 16), B), 128 threads.  Needs W % 4 == 0.
+__global__ void __launch_bounds__(NTH) sc3_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                                                  float* __restrict__ out, int NC, int NJ, int H, int W, int vertical, int dgrad) {
+  extern __shared__ __align__(16) float w_s[];  // [NC * 3][16]
+  const int j0 = blockIdx.y * 16, HW = H * W;
+  for (int i = threadIdx.x; i < NC * 3 * 16; i += NTH) {
+    const int vi = i >> 4, j = i & 15;
+    const int c = vi / 3, t = vi - c * 3;
+    float v = 0.f;
+    // dgrad runs the same correlation on dy with the taps mirrored: tap index 2 - t
+    if (j0 + j < NJ) v = dgrad ? w[((size_t)c * NJ + j0 + j) * 3 + (2 - t)] : w[((size_t)(j0 + j) * NC + c) * 3 + t];
+    w_s[i] = v;
+  }
+  __syncthreads();
+  const int b = blockIdx.z;
+  const int p = (blockIdx.x * NTH + threadIdx.x) * 4;
+  if (p >= HW) return;
+  const int h = p / W, col = p - h * W;
+  const bool lo_ok = vertical ? h > 0 : col > 0;            // tap 0 (offset -1) in range for the first pixel
+  const bool hi_ok = vertical ? h < H - 1 : col + 4 < W;    // tap 2 (offset +1) in range for the last pixel
+  const float* ib = in + (size_t)b * NC * HW + p;
+  float acc[16][4];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float bv = (bias && j0 + j < NJ) ? __ldg(bias + j0 + j) : 0.f;
+    acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = bv;
+  }
+  for (int c = 0; c < NC; ++c) {
+    const float* ic = ib + (size_t)c * HW;
+    const float4 v1 = __ldg(reinterpret_cast<const float4*>(ic));
+    float4 v0, v2;
+    if (vertical) {
+      v0 = lo_ok ? __ldg(reinterpret_cast<const float4*>(ic - W)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v2 = hi_ok ? __ldg(reinterpret_cast<const float4*>(ic + W)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      const float l = lo_ok ? __ldg(ic - 1) : 0.f, r = hi_ok ? __ldg(ic + 4) : 0.f;
+      v0 = make_float4(l, v1.x, v1.y, v1.z);
+      v2 = make_float4(v1.y, v1.z, v1.w, r);
+    }
+    const float4* w4 = reinterpret_cast<const float4*>(w_s + c * 48);
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      const float4 xv = t == 0 ? v0 : (t == 1 ? v1 : v2);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 ww = w4[t * 4 + q];
+        const float wj[4] = {ww.x, ww.y, ww.z, ww.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc[4 * q + e][0] = fmaf(wj[e], xv.x, acc[4 * q + e][0]);
+          acc[4 * q + e][1] = fmaf(wj[e], xv.y, acc[4 * q + e][1]);
+          acc[4 * q + e][2] = fmaf(wj[e], xv.z, acc[4 * q + e][2]);
+          acc[4 * q + e][3] = fmaf(wj[e], xv.w, acc[4 * q + e][3]);
+        }
+      }
+    }
+  }
+  float* ob = out + (size_t)b * NJ * HW + p;
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    if (j0 + j < NJ) *reinterpret_cast<float4*>(ob + (size_t)(j0 + j) * HW) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+}
+
+// ---- weight / bias gradient of ALL THREE taps of a 1x3 / 3x1 kernel in one pass over x and dy (the per-tap version below streams
+//      both tensors once per tap).  Same thread layout as sc_wgrad_kernel with NO = 4: thread = 4 outputs x 4 inputs x 3 taps.
+__global__ void __launch_bounds__(256) sc3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                        float* __restrict__ partial, int Cin, int Cout, int H, int W, int ntiles, int TOn,
+                                                        int PG, int vertical) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int NO = 4;
+  const int HW = H * W;
+  const int OC = TOn * NO;
+  const int XP = Cin + 4, YP = OC + 4;
+  float* x_s = smem;                // [3][TP][XP]
+  float* y_s = x_s + 3 * TP * XP;   // [TP][YP]
+  const int TC = Cin >> 2, Tn = TC * TOn, tid = threadIdx.x;
+  const int pg = tid / Tn, r = tid - pg * Tn;
+  const int tc = r % TC, to = r / TC;
+  const int o0 = to * NO;
+  const bool active = pg < PG;
+  float acc[3][NO][4], bacc[NO];
+#pragma unroll
+  for (int k = 0; k < NO; ++k) {
+    bacc[k] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[t][k][e] = 0.f;
+  }
+  const int tiles_per_img = (HW + TP - 1) / TP;
+  const int sdy = vertical ? 1 : 0, sdx = vertical ? 0 : 1;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int b = tile / tiles_per_img, p0 = (tile - b * tiles_per_img) * TP;
+    __syncthreads();
+    for (int i = tid; i < 3 * Cin * TP; i += 256) {
+      const int t = i / (Cin * TP), ii = i - t * Cin * TP;
+      const int rest = ii >> 5;
+      const int p = (rest % (TP / 8)) * 8 + (ii & 7), c = (rest / (TP / 8)) * 4 + ((ii >> 3) & 3);
+      const int pp = p0 + p, hh = pp / W, ww = pp - hh * W;
+      const int dyv = (t - 1) * sdy, dxv = (t - 1) * sdx;
+      const bool ok = pp < HW && (unsigned)(hh + dyv) < (unsigned)H && (unsigned)(ww + dxv) < (unsigned)W;
+      x_s[(t * TP + p) * XP + c] = ok ? __ldg(x + ((size_t)b * Cin + c) * HW + pp + dyv * W + dxv) : 0.f;
+    }
+    for (int i = tid; i < OC * TP; i += 256) {
+      const int rest = i >> 5;
+      const int p = (rest % (TP / 8)) * 8 + (i & 7), o = (rest / (TP / 8)) * 4 + ((i >> 3) & 3);
+      y_s[p * YP + o] = (o < Cout && p0 + p < HW) ? __ldg(dy + ((size_t)b * Cout + o) * HW + p0 + p) : 0.f;
+    }
+    __syncthreads();
+    if (active) {
+      for (int p = pg; p < TP; p += PG) {
+        const float4 g4 = *reinterpret_cast<const float4*>(y_s + p * YP + o0);
+        const float g[NO] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          const float4 xv = *reinterpret_cast<const float4*>(x_s + (t * TP + p) * XP + 4 * tc);
+#pragma unroll
+          for (int k = 0; k < NO; ++k) {
+            acc[t][k][0] = fmaf(g[k], xv.x, acc[t][k][0]);
+            acc[t][k][1] = fmaf(g[k], xv.y, acc[t][k][1]);
+            acc[t][k][2] = fmaf(g[k], xv.z, acc[t][k][2]);
+            acc[t][k][3] = fmaf(g[k], xv.w, acc[t][k][3]);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < NO; ++k) bacc[k] += g[k];
+      }
+    }
+  }
+  if (active) {      // partial layout per (CTA, pixel group): dW as [o][c][t] (the weight tensor's own layout) | db
+    float* pb = partial + ((size_t)blockIdx.x * PG + pg) * ((size_t)Cout * Cin * 3 + Cout);
+#pragma unroll
+    for (int k = 0; k < NO; ++k) {
+      const int o = o0 + k;
+      if (o < Cout) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+          for (int t = 0; t < 3; ++t) pb[((size_t)o * Cin + 4 * tc + e) * 3 + t] = acc[t][k][e];
+        if (tc == 0) pb[(size_t)Cout * Cin * 3 + o] = bacc[k];
+      }
+    }
+  }
+}
+
 // ---- weight / bias gradient of ONE tap: dW[o][c][t] = sum_{b,p} dy[b,o,p] x[b,c,p+delta_t]; db[o] = sum dy (tap 0 only).
 // Same thread layout as pwconv.cu's pw_wgrad_kernel (NO outputs x 4 inputs per thread, PG pixel groups per CTA).
-constexpr int TP = 64;
 template <int NO>
 __global__ void __launch_bounds__(256) sc_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                        float* __restrict__ partial, int Cin, int Cout, int H, int W, int ntiles,
@@ -254,6 +403,18 @@ static void launch_wgrad(const kmu_smallconv_desc& d, const WgradPlan& pl, const
   sc_wgrad_kernel<NO><<<pl.ctas, 256, smem, st>>>(x, dy, partial, d.Cin, d.Cout, d.H, d.W, ntiles, pl.TOn, pl.PG, sdy, sdx);
 }
 
+// 1x3 / 3x1 fast path: one forward / dgrad kernel with 128-bit traffic, one weight-gradient pass for all three taps
+static bool three_tap(const kmu_smallconv_desc& d) { return d.kh * d.kw == 3 && d.W % 4 == 0 && d.Cin % 4 == 0 && d.Cout % 4 == 0; }
+static bool three_tap_wgrad(const kmu_smallconv_desc& d) {
+  return three_tap(d) && wgrad_ok(d) && (d.Cin / 4) * cdiv(d.Cout, 4) <= 256 && (size_t)TP * (3 * (d.Cin + 4) + d.Cout + 8) * 4 <= 200 * 1024;
+}
+static void launch3(const float* in, const float* w, const float* bias, float* out, int NC, int NJ, int H, int W, int B, int vertical,
+                    int dgrad, cudaStream_t st) {
+  const size_t smem = (size_t)NC * 3 * 16 * 4;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(sc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  sc3_kernel<<<dim3(cdiv(H * W, 4 * NTH), cdiv(NJ, 16), B), NTH, smem, st>>>(in, w, bias, out, NC, NJ, H, W, vertical, dgrad);
+}
+
 }  // namespace sc
 }  // namespace kmu
 
@@ -273,13 +434,19 @@ size_t kmu_smallconv_bwd_workspace_bytes(const kmu_smallconv_desc* d) {
   if (check(d, "smallconv_bwd_workspace_bytes") != KMU_OK) return 0;
   if (!wgrad_ok(*d)) return 256;
   WgradPlan pl = wgrad_plan(*d);
-  return align_up((size_t)pl.ctas * pl.PG * ((size_t)d->Cout * d->Cin + d->Cout) * 4, 256);
+  size_t parts = (size_t)pl.ctas * pl.PG;
+  return align_up(parts * ((size_t)d->Cout * d->Cin * 3 + d->Cout) * 4, 256);
 }
 
 int kmu_smallconv_fwd(const kmu_smallconv_desc* d, const float* x, const float* w, const float* bias, float* y, kmu_stream stream) {
   int rc = check(d, "smallconv_fwd");
   if (rc != KMU_OK) return rc;
   KMU_REQUIRE(x && w && y, KMU_ERR_BAD_ARG, "smallconv_fwd: null tensor");
+  if (three_tap(*d) && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0) {
+    launch3(x, w, bias, y, d->Cin, d->Cout, d->H, d->W, d->B, d->kh == 3, 0, (cudaStream_t)stream);
+    KMU_LAUNCH_CHECK("sc3_fwd");
+    return KMU_OK;
+  }
   launch(x, w, bias, y, d->Cin, d->Cout, d->H, d->W, d->B, make_taps(d->kh, d->kw, false), 0, (cudaStream_t)stream);
   KMU_LAUNCH_CHECK("sc_fwd");
   return KMU_OK;
@@ -292,7 +459,10 @@ int kmu_smallconv_bwd(const kmu_smallconv_desc* d, const float* x, const float* 
   KMU_REQUIRE(dy && w, KMU_ERR_BAD_ARG, "smallconv_bwd: null tensor");
   cudaStream_t st = (cudaStream_t)stream;
   if (dx) {
-    launch(dy, w, nullptr, dx, d->Cout, d->Cin, d->H, d->W, d->B, make_taps(d->kh, d->kw, true), 1, st);
+    if (three_tap(*d) && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dx & 15) == 0)
+      launch3(dy, w, nullptr, dx, d->Cout, d->Cin, d->H, d->W, d->B, d->kh == 3, 1, st);
+    else
+      launch(dy, w, nullptr, dx, d->Cout, d->Cin, d->H, d->W, d->B, make_taps(d->kh, d->kw, true), 1, st);
     KMU_LAUNCH_CHECK("sc_dgrad");
   }
   if (dw) {
@@ -304,6 +474,23 @@ int kmu_smallconv_bwd(const kmu_smallconv_desc* d, const float* x, const float* 
     const WgradPlan pl = wgrad_plan(*d);
     const Taps taps = make_taps(d->kh, d->kw, false);
     const int n_w = d->Cout * d->Cin, n_b = d->Cout;
+    if (three_tap_wgrad(*d)) {
+      WgradPlan p3 = pl;
+      p3.NO = 4;
+      p3.TOn = cdiv(d->Cout, 4);
+      p3.PG = 256 / ((d->Cin / 4) * p3.TOn);
+      if (p3.PG > 8) p3.PG = 8;
+      if (p3.PG > pl.PG) p3.PG = pl.PG;                         // the workspace was sized for pl.PG pixel groups
+      const size_t smem = (size_t)TP * (3 * (d->Cin + 4) + p3.TOn * 4 + 4) * 4;
+      if (smem > 48 * 1024) cudaFuncSetAttribute(sc3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      const int ntiles = d->B * cdiv(d->H * d->W, TP);
+      sc3_wgrad_kernel<<<pl.ctas, 256, smem, st>>>(x, dy, partial, d->Cin, d->Cout, d->H, d->W, ntiles, p3.TOn, p3.PG, d->kh == 3);
+      KMU_LAUNCH_CHECK("sc3_wgrad");
+      // the partial already has the weight tensor's [o][c][t] layout: reduce it as ONE "tap" of 3 * n_w values
+      sc_wreduce_kernel<<<cdiv(3 * n_w + n_b, 32), 256, 0, st>>>(partial, pl.ctas * p3.PG, 3 * n_w, n_b, 1, 0, dw, dbias);
+      KMU_LAUNCH_CHECK("sc_wreduce");
+      return KMU_OK;
+    }
     for (int t = 0; t < taps.T; ++t) {
       switch (pl.NO) {
         case 4: launch_wgrad<4>(*d, pl, x, dy, partial, taps.dy[t], taps.dx[t], st); break;
