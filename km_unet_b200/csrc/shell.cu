@@ -391,6 +391,78 @@ __global__ void __launch_bounds__(256) dw3x3_wgrad_kernel(const float* __restric
   }
 }
 
+// dx AND the weight / bias gradient partials in one pass (W % 4 == 0): thread = 4 consecutive columns of a row, rows strided over the
+// CTA's row slice.  x and dy are each read once (three rows x (one 128-bit load + two scalars) per item) instead of dy twice and x
+// once by the dx kernel + the weight-gradient kernel.  dx = scale * conv^T(dy) [+ add]; partials as dw3x3_wgrad_kernel writes them.
+__global__ void __launch_bounds__(256) dw3x3_bwd_fused_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                              const float* __restrict__ w, const float* __restrict__ scale,
+                                                              const float* add, float* dx, float* __restrict__ part, DwDims d,
+                                                              int rows_per_cta) {
+  __shared__ float red[8];
+  const long long plane = blockIdx.y;
+  const int c = (int)(plane % d.C);
+  const int r0 = blockIdx.x * rows_per_cta;
+  int r1 = r0 + rows_per_cta;
+  if (r1 > d.H) r1 = d.H;
+  const int wq = d.W >> 2;
+  const float* xp = x + (size_t)plane * d.H * d.W;
+  const float* gp = dy + (size_t)plane * d.H * d.W;
+  float k[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) k[i] = __ldg(w + c * 9 + 8 - i);        // flipped taps: dx = correlate(dy, flip(w))
+  const float sc = scale ? __ldg(scale + plane) : 1.f;
+  float a[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) a[i] = 0.f;
+  const int items = (r1 - r0) * wq;
+  for (int it = threadIdx.x; it < items; it += 256) {
+    const int h = r0 + it / wq, w0 = (it % wq) * 4;
+    float g[3][6], v[3][6];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int hh = h + ky - 1;
+      const bool ok = hh >= 0 && hh < d.H;
+      const float* grow = gp + (size_t)hh * d.W + w0;
+      const float* xrow = xp + (size_t)hh * d.W + w0;
+      const float4 gm = ok ? *reinterpret_cast<const float4*>(grow) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 xm = ok ? *reinterpret_cast<const float4*>(xrow) : make_float4(0.f, 0.f, 0.f, 0.f);
+      g[ky][0] = (ok && w0 > 0) ? __ldg(grow - 1) : 0.f;
+      v[ky][0] = (ok && w0 > 0) ? __ldg(xrow - 1) : 0.f;
+      g[ky][1] = gm.x; g[ky][2] = gm.y; g[ky][3] = gm.z; g[ky][4] = gm.w;
+      v[ky][1] = xm.x; v[ky][2] = xm.y; v[ky][3] = xm.z; v[ky][4] = xm.w;
+      g[ky][5] = (ok && w0 + 4 < d.W) ? __ldg(grow + 4) : 0.f;
+      v[ky][5] = (ok && w0 + 4 < d.W) ? __ldg(xrow + 4) : 0.f;
+    }
+    // weight gradient: dy of THIS row against the 3x3 neighbourhood of x
+    a[9] += (g[1][1] + g[1][2]) + (g[1][3] + g[1][4]);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx)
+        a[ky * 3 + kx] += g[1][1] * v[ky][kx] + g[1][2] * v[ky][kx + 1] + g[1][3] * v[ky][kx + 2] + g[1][4] * v[ky][kx + 3];
+    if (dx) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          acc[e] = fmaf(k[ky * 3], g[ky][e], fmaf(k[ky * 3 + 1], g[ky][e + 1], fmaf(k[ky * 3 + 2], g[ky][e + 2], acc[e])));
+      const size_t off = (size_t)plane * d.H * d.W + (size_t)h * d.W + w0;
+      float4 o = make_float4(acc[0] * sc, acc[1] * sc, acc[2] * sc, acc[3] * sc);
+      if (add) {
+        const float4 m = *reinterpret_cast<const float4*>(add + off);
+        o.x += m.x; o.y += m.y; o.z += m.z; o.w += m.w;
+      }
+      *reinterpret_cast<float4*>(dx + off) = o;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    float s = block_sum(a[i], red);
+    if (threadIdx.x == 0) part[((size_t)plane * gridDim.x + blockIdx.x) * 10 + i] = s;
+  }
+}
+
 // dw[c][t] = sum over b and row slices; warp = (c, t), lanes stride over the B * RS partials, fixed-order tree (deterministic).
 // With a per-plane scale (y = scale * (conv + bias)) every plane's partial is weighted by its scale.
 __global__ void __launch_bounds__(128) dw3x3_wreduce_kernel(const float* __restrict__ part, const float* __restrict__ scale, int B, int C,
@@ -545,7 +617,9 @@ static int dw_bwd(const kmu_dwconv3x3_desc* dd, const float* x, const float* dy,
   KMU_REQUIRE(x && dy && w, KMU_ERR_BAD_ARG, "dwconv3x3_bwd: null tensor");
   DwDims d{dd->B, dd->C, dd->H, dd->W};
   cudaStream_t st = (cudaStream_t)stream;
-  if (dx) {
+  const bool fused = (dw || dscale) && (d.W & 3) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 &&
+                     (!dx || ((uintptr_t)dx & 15) == 0) && (!dx_add || ((uintptr_t)dx_add & 15) == 0);
+  if (dx && !fused) {
     long long total = (long long)d.B * d.C * d.H * ((d.W + 3) / 4);
     dw3x3_kernel<true><<<cdiv(total, 256), 256, 0, st>>>(dy, w, nullptr, scale, dx_add, dx, d);
     KMU_LAUNCH_CHECK("dw3x3_bwd_dx");
@@ -555,7 +629,10 @@ static int dw_bwd(const kmu_dwconv3x3_desc* dd, const float* x, const float* dy,
     const int rs = dw_row_slices(*dd);
     const int rows = cdiv(d.H, rs);
     const int rs2 = cdiv(d.H, rows);
-    dw3x3_wgrad_kernel<<<dim3(rs2, d.B * d.C), 256, 0, st>>>(x, dy, (float*)workspace, d, rows);
+    if (fused)
+      dw3x3_bwd_fused_kernel<<<dim3(rs2, d.B * d.C), 256, 0, st>>>(x, dy, w, scale, dx_add, dx, (float*)workspace, d, rows);
+    else
+      dw3x3_wgrad_kernel<<<dim3(rs2, d.B * d.C), 256, 0, st>>>(x, dy, (float*)workspace, d, rows);
     KMU_LAUNCH_CHECK("dw3x3_wgrad");
     if (dw) {
       dw3x3_wreduce_kernel<<<cdiv(d.C * 10, 4), 128, 0, st>>>((const float*)workspace, scale, d.B, d.C, rs2, dw, dbias);
