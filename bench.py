@@ -519,7 +519,7 @@ def run_kan(h, args):
     fam = mb["families"]
     dom = max(fam, key=lambda k: fam[k]["ms"])
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(tpath) and args.precision == "bf16" and B == 32:
         with open(tpath) as f:
             traffic = json.load(f).get(dom)
@@ -699,7 +699,7 @@ def run_model(h, args):
     dom = table[0]
     dom_key = f"{dom['op']} {tuple(dom['shape'])}"
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get(dom_key)         # DRAM bytes per call from the committed `ncu --set full` capture

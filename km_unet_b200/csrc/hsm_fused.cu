@@ -408,23 +408,33 @@ __global__ void __launch_bounds__(NT, 2) hsm_dp_kernel(const float* __restrict__
 }
 
 // ---- merge the per-tile partials of one image (split softmax): two small kernels with fixed summation orders
-// R1: grid B, 64 threads.  m1[b][n] = max_t m_t ; sc[b][t][n] = exp(m_t - m1) ; s1[b][n] = sum_t s_t sc
-__global__ void __launch_bounds__(64) hsm_merge_stats_kernel(const float* __restrict__ part_m, const float* __restrict__ part_s,
-                                                             float* __restrict__ m1, float* __restrict__ s1, float* __restrict__ sc,
-                                                             int T) {
-  const int b = blockIdx.x, n = threadIdx.x;
+// R1: grid B, 256 threads = 64 columns x 4 interleaved slices of the tile list.
+//     m1[b][n] = max_t m_t ; sc[b][t][n] = exp(m_t - m1) ; s1[b][n] = sum_t s_t sc   (slice partials combined in slice order)
+__global__ void __launch_bounds__(256) hsm_merge_stats_kernel(const float* __restrict__ part_m, const float* __restrict__ part_s,
+                                                              float* __restrict__ m1, float* __restrict__ s1, float* __restrict__ sc,
+                                                              int T) {
+  __shared__ float red[4][64];
+  const int b = blockIdx.x, n = threadIdx.x & 63, sl = threadIdx.x >> 6;
   const float* pm = part_m + (size_t)b * T * 64 + n;
   const float* ps = part_s + (size_t)b * T * 64 + n;
   float m = -INFINITY;
-  for (int t = 0; t < T; ++t) m = fmaxf(m, pm[(size_t)t * 64]);
+  for (int t = sl; t < T; t += 4) m = fmaxf(m, __ldg(pm + (size_t)t * 64));
+  red[sl][n] = m;
+  __syncthreads();
+  m = fmaxf(fmaxf(red[0][n], red[1][n]), fmaxf(red[2][n], red[3][n]));
+  __syncthreads();
   float ssum = 0.f;
-  for (int t = 0; t < T; ++t) {
-    const float e = __expf(pm[(size_t)t * 64] - m);
+  for (int t = sl; t < T; t += 4) {
+    const float e = __expf(__ldg(pm + (size_t)t * 64) - m);
     sc[((size_t)b * T + t) * 64 + n] = e;
-    ssum = fmaf(ps[(size_t)t * 64], e, ssum);
+    ssum = fmaf(__ldg(ps + (size_t)t * 64), e, ssum);
   }
-  m1[(size_t)b * 64 + n] = m;
-  s1[(size_t)b * 64 + n] = ssum;
+  red[sl][n] = ssum;
+  __syncthreads();
+  if (sl == 0) {
+    m1[(size_t)b * 64 + n] = m;
+    s1[(size_t)b * 64 + n] = (red[0][n] + red[1][n]) + (red[2][n] + red[3][n]);
+  }
 }
 // R2: grid (C, B), 256 threads = 64 columns x 4 interleaved slices of the tile list.  hs1[b][c][n] = sum_t part_hs[b][t][c][n] sc[b][t][n]
 __global__ void __launch_bounds__(256) hsm_merge_hs_kernel(const float* __restrict__ part_hs, const float* __restrict__ sc,
@@ -453,7 +463,7 @@ int merge(const float* part_m, const float* part_s, const float* part_hs, int B,
   *m1 = (float*)ws; ws += align_up((size_t)B * 64 * 4, 256);
   *s1 = (float*)ws; ws += align_up((size_t)B * 64 * 4, 256);
   *hs1 = (float*)ws;
-  hsm_merge_stats_kernel<<<B, 64, 0, st>>>(part_m, part_s, *m1, *s1, sc, T);
+  hsm_merge_stats_kernel<<<B, 256, 0, st>>>(part_m, part_s, *m1, *s1, sc, T);
   KMU_LAUNCH_CHECK("hsm_merge_stats");
   hsm_merge_hs_kernel<<<dim3(C, B), 256, 0, st>>>(part_hs, sc, *hs1, T, C);
   KMU_LAUNCH_CHECK("hsm_merge_hs");

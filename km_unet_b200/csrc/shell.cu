@@ -69,8 +69,13 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
   const float k = __ldg(x + (size_t)c * d.HW);
   float a = 0.f, q = 0.f;
   if ((d.HW & 3) == 0) {
-    for (long long v = v0 + 4 * threadIdx.x; v < v1; v += 1024) {
-      float4 t = *reinterpret_cast<const float4*>(x + chan_off(v, c, d.C, d.HW));
+    // (sample b, offset in the plane) advance incrementally: the 64-bit division of chan_off per 16-byte load made these
+    // kernels instruction-bound
+    long long v = v0 + 4 * threadIdx.x;
+    int b = (int)(v / d.HW), off = (int)(v - (long long)b * d.HW);
+    for (; v < v1; v += 1024, off += 1024) {
+      while (off >= d.HW) { off -= d.HW; ++b; }
+      float4 t = *reinterpret_cast<const float4*>(x + ((size_t)b * d.C + c) * d.HW + off);
       t.x -= k; t.y -= k; t.z -= k; t.w -= k;
       a += (t.x + t.y) + (t.z + t.w);
       q = fmaf(t.x, t.x, fmaf(t.y, t.y, fmaf(t.z, t.z, fmaf(t.w, t.w, q))));
@@ -156,6 +161,33 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
   }
 }
 
+// Same, HW % 4 == 0: grid (chunks of 4096 elements, B * C planes) -- the channel is a property of the CTA, no per-thread divisions
+__global__ void __launch_bounds__(256) bn_apply_plane_kernel(const float* __restrict__ x, const float2* __restrict__ stat,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             const float* __restrict__ res, const float* __restrict__ alpha,
+                                                             float* __restrict__ y, int C, int HW, int relu) {
+  const int plane = blockIdx.y, c = plane % C;
+  const float2 st = stat[c];
+  const float sc = gamma[c] * st.y, sh = beta[c] - st.x * sc;
+  const float a = alpha ? 1.f / (1.f + expf(-alpha[c])) : 1.f, b = 1.f - a;
+  const size_t base = (size_t)plane * HW;
+  const int n4 = HW >> 2;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = blockIdx.x * 1024 + k * 256 + threadIdx.x;
+    if (i < n4) {
+      float4 t = *reinterpret_cast<const float4*>(x + base + 4 * (size_t)i);
+      t.x = fmaf(t.x, sc, sh); t.y = fmaf(t.y, sc, sh); t.z = fmaf(t.z, sc, sh); t.w = fmaf(t.w, sc, sh);
+      if (relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+      if (res) {
+        const float4 r = *reinterpret_cast<const float4*>(res + base + 4 * (size_t)i);
+        t.x = fmaf(a, t.x, b * r.x); t.y = fmaf(a, t.y, b * r.y); t.z = fmaf(a, t.z, b * r.z); t.w = fmaf(a, t.w, b * r.w);
+      }
+      *reinterpret_cast<float4*>(y + base + 4 * (size_t)i) = t;
+    }
+  }
+}
+
 // ---- backward statistics: part[(c*nsplit+s)*3 + {0,1,2}] = sum g, sum g xhat, sum dy (bn_out - res)
 //      g = a dy masked by the ReLU.  grid (nsplit, C), 256 threads
 __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ dy,
@@ -179,8 +211,11 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(const float* __restri
     sgx = fmaf(g, (xv - st.x) * st.y, sgx);
   };
   if ((d.HW & 3) == 0) {
-    for (long long v = v0 + 4 * threadIdx.x; v < v1; v += 1024) {
-      size_t off = chan_off(v, c, d.C, d.HW);
+    long long v = v0 + 4 * threadIdx.x;
+    int b = (int)(v / d.HW), o = (int)(v - (long long)b * d.HW);
+    for (; v < v1; v += 1024, o += 1024) {
+      while (o >= d.HW) { o -= d.HW; ++b; }
+      const size_t off = ((size_t)b * d.C + c) * d.HW + o;
       float4 xv = *reinterpret_cast<const float4*>(x + off);
       float4 g = *reinterpret_cast<const float4*>(dy + off);
       float4 r = res ? *reinterpret_cast<const float4*>(res + off) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -261,6 +296,33 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
     const float g = dy[i];
     dx[i] = one(x[i], g);
     if (dres) dres[i] = (1.f - a) * g;
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_plane_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                 const float2* __restrict__ stat, const float2* __restrict__ bstat,
+                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                 const float* __restrict__ alpha, float* __restrict__ dx,
+                                                                 float* __restrict__ dres, int C, int HW, int relu) {
+  const int plane = blockIdx.y, c = plane % C;
+  const float2 st = stat[c], bs = bstat[c];
+  const float sc = gamma[c] * st.y, sh = beta[c] - st.x * sc;
+  const float a = alpha ? 1.f / (1.f + expf(-alpha[c])) : 1.f, b = 1.f - a;
+  auto one = [&](float xv, float g) {
+    if (relu && fmaf(xv, sc, sh) <= 0.f) g = 0.f;
+    return sc * (a * g - bs.x - (xv - st.x) * st.y * bs.y);
+  };
+  const size_t base = (size_t)plane * HW;
+  const int n4 = HW >> 2;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = blockIdx.x * 1024 + k * 256 + threadIdx.x;
+    if (i < n4) {
+      const float4 xv = *reinterpret_cast<const float4*>(x + base + 4 * (size_t)i);
+      const float4 g = *reinterpret_cast<const float4*>(dy + base + 4 * (size_t)i);
+      *reinterpret_cast<float4*>(dx + base + 4 * (size_t)i) = make_float4(one(xv.x, g.x), one(xv.y, g.y), one(xv.z, g.z), one(xv.w, g.w));
+      if (dres) *reinterpret_cast<float4*>(dres + base + 4 * (size_t)i) = make_float4(b * g.x, b * g.y, b * g.z, b * g.w);
+    }
   }
 }
 
@@ -553,7 +615,10 @@ int kmu_bnmix_fwd(const kmu_bnmix_fwd_args* a, kmu_stream stream) {
   const long long total = (long long)d.B * d.C * d.HW;
   const float* res = a->d.mix ? a->res : nullptr;
   const float* alpha = a->d.mix ? a->alpha : nullptr;
-  if ((d.HW & 3) == 0)
+  if ((d.HW & 3) == 0 && (long long)d.B * d.C <= 65535)
+    bn_apply_plane_kernel<<<dim3(cdiv(d.HW, 4096), d.B * d.C), 256, 0, st>>>(a->x, stat, a->weight, a->bias, res, alpha, a->y, d.C, d.HW,
+                                                                             a->d.relu);
+  else if ((d.HW & 3) == 0)
     bn_apply_kernel<true><<<cdiv(total / 4, 256), 256, 0, st>>>(a->x, stat, a->weight, a->bias, res, alpha, a->y, d.C, d.HW, total, a->d.relu);
   else
     bn_apply_kernel<false><<<cdiv(total, 256), 256, 0, st>>>(a->x, stat, a->weight, a->bias, res, alpha, a->y, d.C, d.HW, total, a->d.relu);
@@ -582,7 +647,10 @@ int kmu_bnmix_bwd(const kmu_bnmix_bwd_args* a, kmu_stream stream) {
   KMU_LAUNCH_CHECK("bn_bwd_fin");
   const long long total = (long long)d.B * d.C * d.HW;
   float* dres = a->d.mix ? a->d_res : nullptr;
-  if ((d.HW & 3) == 0)
+  if ((d.HW & 3) == 0 && (long long)d.B * d.C <= 65535)
+    bn_bwd_apply_plane_kernel<<<dim3(cdiv(d.HW, 4096), d.B * d.C), 256, 0, st>>>(a->x, a->dy, stat, bstat, a->weight, a->bias, alpha, a->dx,
+                                                                                 dres, d.C, d.HW, a->d.relu);
+  else if ((d.HW & 3) == 0)
     bn_bwd_apply_kernel<true><<<cdiv(total / 4, 256), 256, 0, st>>>(a->x, a->dy, stat, bstat, a->weight, a->bias, alpha, a->dx, dres, d.C,
                                                                     d.HW, total, a->d.relu);
   else

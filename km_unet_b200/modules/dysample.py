@@ -2,7 +2,6 @@
 projection + point-sampling upsample run in libkmunet.so."""
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from .. import ops
 
@@ -39,19 +38,9 @@ class DySample(nn.Module):
     def sample(self, x, offset):
         return ops.dysample_sample(x, offset, self.scale, self.groups)
 
-    def forward_lp(self, x):
-        if hasattr(self, 'scope'):
-            offset = self.offset(x) * self.scope(x).sigmoid() * 0.5 + self.init_pos
-            return self.sample(x, offset)
-        return ops.dysample(x, self.offset.weight, self.offset.bias, self.init_pos, self.scale, self.groups)
-
-    def forward_pl(self, x):
-        x_ = F.pixel_shuffle(x, self.scale)
-        if hasattr(self, 'scope'):
-            offset = F.pixel_unshuffle(self.offset(x_) * self.scope(x_).sigmoid(), self.scale) * 0.5 + self.init_pos
-        else:
-            offset = F.pixel_unshuffle(self.offset(x_), self.scale) * 0.25 + self.init_pos
-        return self.sample(x, offset)
-
     def forward(self, x):
-        return self.forward_pl(x) if self.style == 'pl' else self.forward_lp(x)
+        # KM-UNet builds DySample(in_channels, scale=2, style='lp') without dyscope (KM_UNetV3_SH.py:411,425,434); the other styles
+        # of the reference class (DySample_md.py:63-76) are never executed by it and are not provided
+        if self.style != 'lp' or hasattr(self, 'scope'):
+            raise NotImplementedError("km_unet_b200.DySample implements style='lp' without dyscope (the configuration KM-UNet uses)")
+        return ops.dysample(x, self.offset.weight, self.offset.bias, self.init_pos, self.scale, self.groups)

@@ -70,7 +70,10 @@ def test_dysample_constant_image_is_reproduced_full_size():
     assert torch.allclose(y, const[:, :, :1, :1].expand_as(y), atol=1e-5)
 
 
-def test_pl_style_and_dyscope_use_the_cuda_sampler():
+def test_sampler_alone_for_a_caller_built_offset_and_unsupported_styles_raise():
+    """kmu_dysample_sample_fwd (DySample.sample, DySample_md.py:49-61) with an offset tensor built by the caller; the module itself
+    implements the configuration KM-UNet uses (style 'lp', no dyscope) and refuses the others loudly."""
+    import pytest as _pt
     from km_unet_b200 import DySample
     from oracle import dysample as O
     torch.manual_seed(4)
@@ -79,7 +82,11 @@ def test_pl_style_and_dyscope_use_the_cuda_sampler():
         m.offset.weight.normal_(0, 0.2)
         m.scope.weight.normal_(0, 0.5)
     x = torch.randn(1, 16, 6, 6)
-    off = m.offset(x) * m.scope(x).sigmoid() * 0.5 + m.init_pos
-    want = O.sample(x.double(), off.detach().double())
-    y = m.cuda()(x.cuda())
+    off = (m.offset(x) * m.scope(x).sigmoid() * 0.5 + m.init_pos).detach()
+    want = O.sample(x.double(), off.double())
+    y = m.sample(x.cuda(), off.cuda())
     assert rel_err(y, want) < TOL
+    with _pt.raises(NotImplementedError):
+        m.cuda()(x.cuda())
+    with _pt.raises(NotImplementedError):
+        DySample(16, style="pl").cuda()(x.cuda())
