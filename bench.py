@@ -357,7 +357,9 @@ def gpu_eager_reference(workload, dev, steps=3, warmup=2):
             ms = e0.elapsed_time(e1) / steps
             peak = torch.cuda.max_memory_allocated(dev) / 2 ** 30
             return {"value": B / (ms / 1e3), "unit": UNIT, "batch": B, "ms_per_step": ms, "steps": steps, "warmup": warmup,
-                    "precision": "fp16 autocast + GradScaler (train_shanghai.py:172-181), cudnn.benchmark", "mode": "eager",
+                    "precision": ("fp16 autocast + GradScaler (train_shanghai.py:172-181), cudnn.benchmark" if WORKLOADS[workload][7] else
+                                  "fp16 autocast from the model's own @autocast() decorators (KM_UNetV3_SH.py:465), no_grad, cudnn.benchmark"),
+                    "mode": "eager",
                     "loss": float(res) if not isinstance(res, float) else res, "peak_mem_gib": peak,
                     "what": "unmodified reference model (oracle/_ref) + oracle/loss.py, stock PyTorch kernels, 1 x B200"}
         except torch.cuda.OutOfMemoryError as e:
