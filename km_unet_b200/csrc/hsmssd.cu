@@ -923,6 +923,91 @@ __global__ void __launch_bounds__(256) ln1d_bwd_reduce_kernel(const float* __res
   }
 }
 
+// Register-resident forms for the widths KM-UNet uses (C = 16, 32, 64): thread = position, the C values of x (and dy) are loaded ONCE
+// (coalesced across the warp) and every later pass runs on registers -- the generic kernels above re-read x three times and dy twice.
+template <int C>
+__global__ void __launch_bounds__(256) ln1d_fwd_reg_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, float* __restrict__ y,
+                                                           float* __restrict__ rstd_out, int B, int L, float eps) {
+  const long long p = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (p >= (long long)B * L) return;
+  const int b = (int)(p / L), l = (int)(p - (long long)b * L);
+  const float* xp = x + (size_t)b * C * L + l;
+  float v[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) v[c] = __ldg(xp + (size_t)c * L);
+  float mean = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) mean += v[c];
+  mean /= (float)C;
+  float var = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float dlt = v[c] - mean;
+    var = fmaf(dlt, dlt, var);
+  }
+  var /= (float)C;
+  const float sd = sqrtf(var + eps);
+  float* yp = y + (size_t)b * C * L + l;
+#pragma unroll
+  for (int c = 0; c < C; ++c) yp[(size_t)c * L] = (v[c] - mean) / sd * __ldg(w + c) + __ldg(bias + c);
+  if (rstd_out) rstd_out[p] = 1.0f / sd;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) ln1d_bwd_reg_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ dy, float* __restrict__ dx,
+                                                           float* __restrict__ part, int B, int L, float eps) {
+  __shared__ float red[8][2 * C];
+  const long long p = (long long)blockIdx.x * 256 + threadIdx.x;
+  const bool valid = p < (long long)B * L;
+  const int b = valid ? (int)(p / L) : 0, l = valid ? (int)(p - (long long)b * L) : 0;
+  const float* xp = x + (size_t)b * C * L + l;
+  const float* gp = dy + (size_t)b * C * L + l;
+  float xh[C], gy[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    xh[c] = valid ? __ldg(xp + (size_t)c * L) : 0.f;
+    gy[c] = valid ? __ldg(gp + (size_t)c * L) : 0.f;
+  }
+  float mean = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) mean += xh[c];
+  mean /= (float)C;
+  float var = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    xh[c] -= mean;
+    var = fmaf(xh[c], xh[c], var);
+  }
+  var /= (float)C;
+  const float rstd = 1.0f / sqrtf(var + eps);
+  float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    xh[c] *= rstd;
+    const float g = gy[c] * __ldg(w + c);
+    m1 += g;
+    m2 = fmaf(g, xh[c], m2);
+  }
+  m1 /= (float)C;
+  m2 /= (float)C;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    if (valid) dx[(size_t)b * C * L + (size_t)c * L + l] = rstd * (gy[c] * __ldg(w + c) - m1 - xh[c] * m2);
+    const float sw = warp_sum(gy[c] * xh[c]), sb = warp_sum(gy[c]);
+    if (lane == 0) { red[warp][c] = sw; red[warp][C + c] = sb; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += 256) {
+    float a = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) a += red[w8][i];
+    part[(size_t)blockIdx.x * 2 * C + i] = a;
+  }
+}
+
 static int check(const kmu_hsmssd_desc* d, const char* who) {
   KMU_REQUIRE(d != nullptr, KMU_ERR_BAD_ARG, "%s: null descriptor", who);
   KMU_REQUIRE(d->B > 0 && d->C > 0 && d->L > 0 && d->H > 0, KMU_ERR_BAD_ARG, "%s: non-positive shape", who);
@@ -1191,7 +1276,14 @@ int kmu_hsmssd_bwd(const kmu_hsmssd_bwd_args* a, kmu_stream stream) {
 int kmu_layernorm1d_fwd(const float* x, const float* weight, const float* bias, float* y, float* rstd, int32_t B, int32_t C,
                         int32_t L, float eps, kmu_stream stream) {
   KMU_REQUIRE(x && weight && bias && y && B > 0 && C > 0 && L > 0, KMU_ERR_BAD_ARG, "layernorm1d_fwd: bad argument");
-  ln1d_fwd_kernel<<<cdiv((long long)B * L, 256), 256, 0, (cudaStream_t)stream>>>(x, weight, bias, y, rstd, B, C, L, eps);
+  const int nb = cdiv((long long)B * L, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (C) {
+    case 16: ln1d_fwd_reg_kernel<16><<<nb, 256, 0, st>>>(x, weight, bias, y, rstd, B, L, eps); break;
+    case 32: ln1d_fwd_reg_kernel<32><<<nb, 256, 0, st>>>(x, weight, bias, y, rstd, B, L, eps); break;
+    case 64: ln1d_fwd_reg_kernel<64><<<nb, 256, 0, st>>>(x, weight, bias, y, rstd, B, L, eps); break;
+    default: ln1d_fwd_kernel<<<nb, 256, 0, st>>>(x, weight, bias, y, rstd, B, C, L, eps);
+  }
   KMU_LAUNCH_CHECK("ln1d_fwd");
   return KMU_OK;
 }
@@ -1212,7 +1304,12 @@ int kmu_layernorm1d_bwd(const float* x, const float* weight, const float* dy, fl
   float* part = (float*)workspace;
   const size_t smem = (size_t)16 * C * 4;
   if (smem > 48 * 1024) cudaFuncSetAttribute(ln1d_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  ln1d_bwd_kernel<<<nblk, 256, smem, (cudaStream_t)stream>>>(x, weight, dy, dx, part, B, C, L, eps);
+  switch (C) {
+    case 16: ln1d_bwd_reg_kernel<16><<<nblk, 256, 0, (cudaStream_t)stream>>>(x, weight, dy, dx, part, B, L, eps); break;
+    case 32: ln1d_bwd_reg_kernel<32><<<nblk, 256, 0, (cudaStream_t)stream>>>(x, weight, dy, dx, part, B, L, eps); break;
+    case 64: ln1d_bwd_reg_kernel<64><<<nblk, 256, 0, (cudaStream_t)stream>>>(x, weight, dy, dx, part, B, L, eps); break;
+    default: ln1d_bwd_kernel<<<nblk, 256, smem, (cudaStream_t)stream>>>(x, weight, dy, dx, part, B, C, L, eps);
+  }
   KMU_LAUNCH_CHECK("ln1d_bwd");
   ln1d_bwd_reduce_kernel<<<cdiv(2 * C, 32), 256, 0, (cudaStream_t)stream>>>(part, nblk, C, dweight, dbias);
   KMU_LAUNCH_CHECK("ln1d_bwd_reduce");
