@@ -48,6 +48,11 @@ const char* kmu_last_error(void);
 int kmu_device_supported(void);
 /* number of kernels this library has launched from the calling thread (bench.py's gpu_launches). */
 uint64_t kmu_launch_count(void);
+/* Bit-reproducible mode (default off, or KMU_DETERMINISTIC=1 in the environment): every libkmunet reduction has a fixed order except
+ * DySample's dX scatter (fp32 atomics, as torch's grid_sampler backward); with the mode on that scatter accumulates in 64-bit fixed
+ * point scaled by max|dout| (integer atomics commute) at 1.75x the cost of the backward. */
+void kmu_set_deterministic(int on);
+int kmu_get_deterministic(void);
 
 /* ------------------------------------------------------------------------------------------------------------
  * K: KANConv2d / KANLinear         convKAN/KANConv2Dlayers.py:15-37, convKAN/KANlayers.py:577-610,644-660

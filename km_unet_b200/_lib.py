@@ -156,6 +156,8 @@ SYMBOLS = {
     "kmu_dysample_bwd": (C.c_int, [C.POINTER(DysBwdArgs), C.c_void_p]),
     "kmu_dysample_sample_fwd": (C.c_int, [C.POINTER(DysDesc), _f32p, _f32p, _f32p, C.c_void_p]),
     "kmu_dysample_sample_bwd": (C.c_int, [C.POINTER(DysDesc), _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
+    "kmu_set_deterministic": (None, [C.c_int]),
+    "kmu_get_deterministic": (C.c_int, []),
     "kmu_deformconv3x3_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(DeformDesc)]),
     "kmu_deformconv3x3_fwd": (C.c_int, [C.POINTER(DeformDesc), _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
     "kmu_deformconv3x3_bwd": (C.c_int, [C.POINTER(DeformDesc), _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p,

@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -16,6 +17,18 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<int> g_deterministic{-1};
+bool deterministic() {
+  int v = g_deterministic.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("KMU_DETERMINISTIC");
+    v = (e && e[0] == '1') ? 1 : 0;
+    g_deterministic.store(v, std::memory_order_relaxed);
+  }
+  return v == 1;
+}
+void set_deterministic(int on) { g_deterministic.store(on ? 1 : 0, std::memory_order_relaxed); }
 
 void count_launches(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
@@ -33,6 +46,8 @@ int finish_launch(const char* what) {
 extern "C" {
 int kmu_version(void) { return KMU_VERSION; }
 const char* kmu_last_error(void) { return kmu::g_err; }
+void kmu_set_deterministic(int on) { kmu::set_deterministic(on); }
+int kmu_get_deterministic(void) { return kmu::deterministic() ? 1 : 0; }
 uint64_t kmu_launch_count(void) { return kmu::g_launches.load(std::memory_order_relaxed); }
 int kmu_device_supported(void) {
   int dev = 0, major = 0;

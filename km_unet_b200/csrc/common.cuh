@@ -10,6 +10,8 @@ namespace kmu {
 void set_error(const char* fmt, ...);
 int finish_launch(const char* what);  // counts the launch; returns KMU_OK or KMU_ERR_LAUNCH with message set
 void count_launches(int n);
+bool deterministic();          // kmu_set_deterministic / KMU_DETERMINISTIC=1: bit-reproducible variants where a faster atomic one exists
+void set_deterministic(int on);
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

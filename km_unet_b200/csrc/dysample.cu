@@ -287,9 +287,13 @@ static bool fused_fwd_ok(const Dims& d, int* th, size_t* smem) {
 // ---------------------------------------------------------------------------------------------- sample (bwd)
 // thread = one output pixel of one (b, group): loops over the group's channels, scatters dX with fp32 atomics (like
 // PyTorch's grid_sampler backward) and keeps the offset gradient in registers (no atomics: one owner per offset).
+// FIX: dX is accumulated as 64-bit fixed point (value * 2^shift, integer atomics: the sum does not depend on the order of the adds ->
+// bit-reproducible); `fixscale` holds 2^shift chosen from max|dout| by dys_amax / dys_fixscale so that 2^20 terms cannot overflow.
+template <bool FIX>
 __global__ void __launch_bounds__(256) dys_sample_bwd_kernel(const float* __restrict__ x, const float* __restrict__ offset,
                                                              const float* __restrict__ dout, float* __restrict__ dx,
-                                                             float* __restrict__ doffset, Dims d) {
+                                                             float* __restrict__ doffset, Dims d, unsigned long long* __restrict__ acc,
+                                                             const float* __restrict__ fixscale) {
   long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   long long total = (long long)d.B * d.G * d.OH * d.OW;
   if (idx >= total) return;
@@ -311,18 +315,28 @@ __global__ void __launch_bounds__(256) dys_sample_bwd_kernel(const float* __rest
   size_t base = ((size_t)b * d.C + (size_t)g * d.Cg) * HW + (size_t)q.y0 * d.W + q.x0;
   const float* dop = dout + ((size_t)b * d.C + (size_t)g * d.Cg) * OHW + (size_t)oh * d.OW + ow;
   float gx = 0.f, gy = 0.f;
+  const float fs = FIX ? __ldg(fixscale) : 1.f;
   for (int c = 0; c < d.Cg; ++c) {
     float go = __ldg(dop + (size_t)c * OHW);
     const float* r0 = x + base + (size_t)c * HW;
-    float* g0 = dx + base + (size_t)c * HW;
     float v00 = __ldg(r0);
     float v01 = q.x1ok ? __ldg(r0 + 1) : 0.f;
     float v10 = q.y1ok ? __ldg(r0 + d.W) : 0.f;
     float v11 = (q.x1ok && q.y1ok) ? __ldg(r0 + d.W + 1) : 0.f;
-    atomicAdd(g0, go * (wx0 * wy0));
-    if (q.x1ok) atomicAdd(g0 + 1, go * (wx1 * wy0));
-    if (q.y1ok) atomicAdd(g0 + d.W, go * (wx0 * wy1));
-    if (q.x1ok && q.y1ok) atomicAdd(g0 + d.W + 1, go * (wx1 * wy1));
+    if (FIX) {
+      unsigned long long* a0 = acc + base + (size_t)c * HW;
+      const float gs = go * fs;
+      atomicAdd(a0, (unsigned long long)__float2ll_rn(gs * (wx0 * wy0)));
+      if (q.x1ok) atomicAdd(a0 + 1, (unsigned long long)__float2ll_rn(gs * (wx1 * wy0)));
+      if (q.y1ok) atomicAdd(a0 + d.W, (unsigned long long)__float2ll_rn(gs * (wx0 * wy1)));
+      if (q.x1ok && q.y1ok) atomicAdd(a0 + d.W + 1, (unsigned long long)__float2ll_rn(gs * (wx1 * wy1)));
+    } else {
+      float* g0 = dx + base + (size_t)c * HW;
+      atomicAdd(g0, go * (wx0 * wy0));
+      if (q.x1ok) atomicAdd(g0 + 1, go * (wx1 * wy0));
+      if (q.y1ok) atomicAdd(g0 + d.W, go * (wx0 * wy1));
+      if (q.x1ok && q.y1ok) atomicAdd(g0 + d.W + 1, go * (wx1 * wy1));
+    }
     gx = fmaf(go, (v01 - v00) * wy0 + (v11 - v10) * wy1, gx);
     gy = fmaf(go, (v10 - v00) * wx0 + (v11 - v01) * wx1, gy);
   }
@@ -330,12 +344,32 @@ __global__ void __launch_bounds__(256) dys_sample_bwd_kernel(const float* __rest
   doffset[offi + (size_t)d.G * ss * HW] = q.gy ? gy : 0.f;
 }
 
+// max|dout| (order-independent: integer max of the float bit patterns of |v|) and the fixed-point scale derived from it
+__global__ void __launch_bounds__(256) dys_amax_kernel(const float* __restrict__ v, long long n4, unsigned int* __restrict__ out) {
+  unsigned int m = 0u;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(v) + i);
+    m = max(max(m, __float_as_uint(fabsf(t.x))), max(__float_as_uint(fabsf(t.y)), max(__float_as_uint(fabsf(t.z)), __float_as_uint(fabsf(t.w)))));
+  }
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+__global__ void dys_fixscale_kernel(const unsigned int* __restrict__ amax_bits, float* __restrict__ scale) {
+  // 2^shift with max|dout| * 2^shift in [2^40, 2^41): a position receives far fewer than 2^20 contributions of at most that size
+  const float a = __uint_as_float(*amax_bits);
+  int e = 0;
+  if (a > 0.f && isfinite(a)) frexpf(a, &e);              // a = f * 2^e, f in [0.5, 1)
+  scale[0] = ldexpf(1.f, 41 - e);
+  scale[1] = ldexpf(1.f, e - 41);
+}
+
 // ---------------------------------------------------------------------------------------------- offset conv (bwd)
 // thread = input pixel, 32 offset channels per pass.  dX += W^T (0.25 dOff) with atomics (several passes / the sampler's
 // scatter share dX); per-block partials of dW = (0.25 dOff) x^T and db go to the workspace, reduced in fixed order.
 __global__ void __launch_bounds__(128) dys_offset_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                              const float* __restrict__ doffset, float* __restrict__ dx,
-                                                             float* __restrict__ partial, Dims d) {
+                                                             float* __restrict__ partial, Dims d, const unsigned long long* __restrict__ acc,
+                                                             const float* __restrict__ fixscale) {
   extern __shared__ __align__(16) float smem[];
   float* w_s = smem;                    // [C][32]
   float* g_s = w_s + d.C * 32;          // [128][33]
@@ -372,7 +406,10 @@ __global__ void __launch_bounds__(128) dys_offset_bwd_kernel(const float* __rest
         s2 = fmaf(g[j4 * 4 + 2], ww.z, s2);
         s3 = fmaf(g[j4 * 4 + 3], ww.w, s3);
       }
-      atomicAdd(dxp + (size_t)c * HW, (s0 + s1) + (s2 + s3));
+      if (acc)    // fixed-point sampler sums -> float, plus this (single-pass) projection term: plain store, no atomics
+        dxp[(size_t)c * HW] = (float)(long long)acc[(size_t)b * d.C * HW + (size_t)c * HW + r] * __ldg(fixscale + 1) + ((s0 + s1) + (s2 + s3));
+      else
+        atomicAdd(dxp + (size_t)c * HW, (s0 + s1) + (s2 + s3));
     }
   }
   // dW partial: thread owns offset channel j = lane, channels cq*8..cq*8+7 of each 32-channel chunk (cq = warp id)
@@ -479,12 +516,17 @@ static int launch_sample_fwd(const Dims& d, const float* x, const float* offset,
 }
 
 static int launch_sample_bwd(const Dims& d, const float* x, const float* offset, const float* dout, float* dx, float* doffset,
-                             cudaStream_t st) {
+                             cudaStream_t st, unsigned long long* acc = nullptr, const float* fixscale = nullptr) {
   long long total = (long long)d.B * d.G * d.OH * d.OW;
-  dys_sample_bwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(x, offset, dout, dx, doffset, d);
+  if (acc)
+    dys_sample_bwd_kernel<true><<<cdiv(total, 256), 256, 0, st>>>(x, offset, dout, dx, doffset, d, acc, fixscale);
+  else
+    dys_sample_bwd_kernel<false><<<cdiv(total, 256), 256, 0, st>>>(x, offset, dout, dx, doffset, d, nullptr, nullptr);
   KMU_LAUNCH_CHECK("dys_sample_bwd");
   return KMU_OK;
 }
+// deterministic path: one pass of the offset projection (NOFF <= 32) and 16-byte aligned dout
+static bool fix_ok(const Dims& d, const float* dout) { return d.NOFF <= 32 && ((uintptr_t)dout & 15) == 0 && ((long long)d.B * d.C * d.OH * d.OW) % 4 == 0; }
 
 }  // namespace dys
 }  // namespace kmu
@@ -500,7 +542,7 @@ size_t kmu_dysample_bwd_workspace_bytes(const kmu_dysample_desc* dd) {
   long long npix = (long long)d.B * d.H * d.W;
   size_t doff = align_up((size_t)d.B * d.NOFF * d.H * d.W * 4, 256);
   size_t part = (size_t)cdiv(npix, 128) * cdiv(d.NOFF, 32) * (32 * d.C + 32) * 4;
-  return doff + align_up(part, 256);
+  return doff + align_up(part, 256) + align_up((size_t)npix * d.C * 8, 256) + 256;      // + fixed-point dX accumulator + scale
 }
 
 int kmu_dysample_fwd(const kmu_dysample_fwd_args* a, kmu_stream stream) {
@@ -575,15 +617,31 @@ int kmu_dysample_bwd(const kmu_dysample_bwd_args* a, kmu_stream stream) {
   float* doff = (float*)a->workspace;
   float* partial = (float*)((char*)a->workspace + align_up((size_t)d.B * d.NOFF * d.H * d.W * 4, 256));
   long long nx = npix * d.C;
-  zero_kernel<<<(int)std::min<long long>(cdiv(nx, 1024), 148 * 8), 256, 0, st>>>(a->dx, nx);
-  KMU_LAUNCH_CHECK("dys_zero");
-  st_ = launch_sample_bwd(d, a->x, a->offset, a->dout, a->dx, doff, st);
+  size_t part_bytes = align_up((size_t)cdiv(npix, 128) * cdiv(d.NOFF, 32) * (32 * d.C + 32) * 4, 256);
+  unsigned long long* acc = nullptr;
+  float* fixscale = nullptr;
+  if (deterministic() && fix_ok(d, a->dout)) {      // bit-reproducible: fixed-point dX accumulation scaled by max|dout| (64-bit integer
+                                                    // atomics cost 1.75x the fp32 ones: 253 -> 446 us at (32,64,64x64), hence opt-in)
+    acc = (unsigned long long*)((char*)partial + part_bytes);
+    fixscale = (float*)((char*)acc + align_up((size_t)nx * 8, 256));
+    cudaMemsetAsync(acc, 0, (size_t)nx * 8, st);
+    cudaMemsetAsync(fixscale, 0, 16, st);
+    const long long n4 = (long long)d.B * d.C * d.OH * d.OW / 4;
+    dys_amax_kernel<<<(int)std::min<long long>(cdiv(n4, 256), 148 * 8), 256, 0, st>>>(a->dout, n4, (unsigned int*)(fixscale + 2));
+    KMU_LAUNCH_CHECK("dys_amax");
+    dys_fixscale_kernel<<<1, 1, 0, st>>>((const unsigned int*)(fixscale + 2), fixscale);
+    KMU_LAUNCH_CHECK("dys_fixscale");
+  } else {
+    zero_kernel<<<(int)std::min<long long>(cdiv(nx, 1024), 148 * 8), 256, 0, st>>>(a->dx, nx);
+    KMU_LAUNCH_CHECK("dys_zero");
+  }
+  st_ = launch_sample_bwd(d, a->x, a->offset, a->dout, a->dx, doff, st, acc, fixscale);
   if (st_ != KMU_OK) return st_;
   int nblk = cdiv(npix, 128), npass = cdiv(d.NOFF, 32);
   size_t smem = ((size_t)d.C * 32 + 128 * 33 + 128 * 36) * 4;
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(dys_offset_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  dys_offset_bwd_kernel<<<dim3(nblk, npass), 128, smem, st>>>(a->x, a->w_offset, doff, a->dx, partial, d);
+  dys_offset_bwd_kernel<<<dim3(nblk, npass), 128, smem, st>>>(a->x, a->w_offset, doff, a->dx, partial, d, acc, fixscale);
   KMU_LAUNCH_CHECK("dys_offset_bwd");
   int n = npass * (32 * d.C + 32);
   dys_offset_bwd_reduce_kernel<<<cdiv(n, 32), 256, 0, st>>>(partial, nblk, npass, a->d_w_offset, a->d_b_offset, d);
