@@ -29,3 +29,7 @@ def precision_code(name=None):
 conv_wide = os.environ.get("KMU_CONV_WIDE", "simt")
 # EfficientViMBlock's mixer layer-scale (torch.lerp with a broadcast weight) through kmu_lerpmix (one pass per direction)
 fused_lerp = os.environ.get("KMU_FUSED_LERP", "1") == "1"
+# EnhancedViMBlock's three direction branches (height / width / channel: independent until the fusion gate) on three CUDA streams:
+# inside the captured step graph they become parallel branches, so the many small latency-bound kernels of one branch fill the
+# drain / fill bubbles of the others (the backward nodes run on the streams their forward ran on)
+parallel_branches = os.environ.get("KMU_PARALLEL_BRANCHES", "1") == "1"

@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .. import ops
+from .. import config, ops
 from .dagem import DAGEM
 from .dysample import DySample
 from .kan import KANConv2d
@@ -144,8 +144,34 @@ class EnhancedViMBlock(nn.Module):
         self.norm = TripleNorm(dim)
         self.drop_path = DropPath(drop_path) if drop_path > 0 else nn.Identity()
 
+    _side = {}
+
+    @classmethod
+    def _side_streams(cls, device):
+        key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+        if key not in cls._side:
+            cls._side[key] = (torch.cuda.Stream(device), torch.cuda.Stream(device))
+        return cls._side[key]
+
+    def _branches(self, x):
+        blocks = (self.height_block, self.width_block, self.channel_block)
+        if not (x.is_cuda and config.parallel_branches):
+            return [b(x) for b in blocks]
+        cur = torch.cuda.current_stream(x.device)
+        feats = [None, None, None]
+        for i, s in enumerate(self._side_streams(x.device)):
+            s.wait_stream(cur)                      # x is ready
+            x.record_stream(s)
+            with torch.cuda.stream(s):
+                feats[i + 1] = blocks[i + 1](x)
+        feats[0] = blocks[0](x)
+        for i, s in enumerate(self._side_streams(x.device)):
+            cur.wait_stream(s)
+            feats[i + 1].record_stream(cur)
+        return feats
+
     def forward(self, x):
-        feats = [self.height_block(x), self.width_block(x), self.channel_block(x)]
+        feats = self._branches(x)
         g = self.fusion_gate(torch.cat(feats, dim=1))
         if ops.combine3_supported(x):
             # x + DropPath(g0 f0 + g1 f1 + g2 f2) in one pass: the per-sample DropPath factor is folded into the gate weights
