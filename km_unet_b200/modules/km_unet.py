@@ -39,6 +39,47 @@ def _run(seq, x):
     return x
 
 
+_SIDE, _LEVEL = {}, {}
+
+
+def _side_streams(device, n, level):
+    """n side streams tied to (current stream of `device`, nesting level) -- cached: the same streams every step, as graph capture
+    wants; a nested parallel region on the same stream gets its own set so it does not queue behind an outer region's branches."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, level)
+    have = _SIDE.setdefault(key, [])
+    while len(have) < n:
+        have.append(torch.cuda.Stream(device))
+    return have[:n]
+
+
+def parallel(fns, inputs, device):
+    """Run independent callables concurrently: fns[0] on the current stream, the others on side streams (fork after `inputs` are
+    ready, join before anyone consumes the results).  Inside a CUDA-graph capture these become parallel branches of the graph; the
+    backward nodes run on the streams their forward ran on.  Falls back to a plain loop on CPU / when config.parallel_branches is off."""
+    if not (device.type == "cuda" and config.parallel_branches) or len(fns) < 2:
+        return [f() for f in fns]
+    cur = torch.cuda.current_stream(device)
+    outs = [None] * len(fns)
+    lkey = (device.index, cur.cuda_stream)
+    level = _LEVEL.get(lkey, 0)
+    sides = _side_streams(device, len(fns) - 1, level)
+    for i, s in enumerate(sides):
+        s.wait_stream(cur)
+        for t in inputs:
+            t.record_stream(s)
+        with torch.cuda.stream(s):
+            outs[i + 1] = fns[i + 1]()
+    _LEVEL[lkey] = level + 1
+    try:
+        outs[0] = fns[0]()
+    finally:
+        _LEVEL[lkey] = level
+    for i, s in enumerate(sides):
+        cur.wait_stream(s)
+        outs[i + 1].record_stream(cur)
+    return outs
+
+
 class DropPath(nn.Module):
     """timm 0.9.16 DropPath: per-sample bernoulli(keep) / keep in training, identity otherwise."""
 
@@ -144,34 +185,9 @@ class EnhancedViMBlock(nn.Module):
         self.norm = TripleNorm(dim)
         self.drop_path = DropPath(drop_path) if drop_path > 0 else nn.Identity()
 
-    _side = {}
-
-    @classmethod
-    def _side_streams(cls, device):
-        key = (device.index, torch.cuda.current_stream(device).cuda_stream)
-        if key not in cls._side:
-            cls._side[key] = (torch.cuda.Stream(device), torch.cuda.Stream(device))
-        return cls._side[key]
-
-    def _branches(self, x):
-        blocks = (self.height_block, self.width_block, self.channel_block)
-        if not (x.is_cuda and config.parallel_branches):
-            return [b(x) for b in blocks]
-        cur = torch.cuda.current_stream(x.device)
-        feats = [None, None, None]
-        for i, s in enumerate(self._side_streams(x.device)):
-            s.wait_stream(cur)                      # x is ready
-            x.record_stream(s)
-            with torch.cuda.stream(s):
-                feats[i + 1] = blocks[i + 1](x)
-        feats[0] = blocks[0](x)
-        for i, s in enumerate(self._side_streams(x.device)):
-            cur.wait_stream(s)
-            feats[i + 1].record_stream(cur)
-        return feats
-
     def forward(self, x):
-        feats = self._branches(x)
+        # the three direction branches are independent until the fusion gate
+        feats = parallel([lambda: self.height_block(x), lambda: self.width_block(x), lambda: self.channel_block(x)], [x], x.device)
         g = self.fusion_gate(torch.cat(feats, dim=1))
         if ops.combine3_supported(x):
             # x + DropPath(g0 f0 + g1 f1 + g2 f2) in one pass: the per-sample DropPath factor is folded into the gate weights
@@ -205,7 +221,8 @@ class MultiScaleFusion(nn.Module):
         self.fusion = nn.Sequential(nn.Conv2d(out * 3, out, 1), nn.Conv2d(out, out, 3, padding=1), ChannelAttention(out, reduction))
 
     def forward(self, features):
-        return _run(self.fusion, torch.cat([_run(blk, f) for blk, f in zip(self.blocks, features)], dim=1))
+        branches = parallel([(lambda blk=blk, f=f: _run(blk, f)) for blk, f in zip(self.blocks, features)], list(features), features[0].device)
+        return _run(self.fusion, torch.cat(branches, dim=1))
 
 
 class LocalContrastAttention(nn.Module):
@@ -311,10 +328,13 @@ class KM_UNetV3(nn.Module):
         e3 = self.lca3(self.enc3(e2))
         if self.variant == 'SH':
             e3 = self.bridge_attention(e3)
-        d1 = self.dec1(e3)
-        d1 = torch.cat([d1, self.attention1(self._skips(e1, e2, d1.shape[2:]))], dim=1)
-        d2 = _run(self.dec2, d1)
-        d2 = torch.cat([d2, self.attention2(self._skips(e1, e2, d2.shape[2:]))], dim=1)
+        # the multi-scale skip fusions depend on e1 / e2 only: they run beside the decoder stage they are concatenated with
+        s1 = (2 * e3.shape[2], 2 * e3.shape[3])
+        d1, a1 = parallel([lambda: self.dec1(e3), lambda: self.attention1(self._skips(e1, e2, s1))], [e1, e2, e3], x.device)
+        d1 = torch.cat([d1, a1], dim=1)
+        s2 = (2 * d1.shape[2], 2 * d1.shape[3])
+        d2, a2 = parallel([lambda: _run(self.dec2, d1), lambda: self.attention2(self._skips(e1, e2, s2))], [e1, e2, d1], x.device)
+        d2 = torch.cat([d2, a2], dim=1)
         return self.activation(group_norm(self.output_norm, _run(self.dec3, d2)))
 
 
