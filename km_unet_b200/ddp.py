@@ -46,6 +46,7 @@ class BucketedGradAllReduce:
             self._close(cur)
         self._hooks = []
         self._where = {}
+        self._events = {}           # CUDA: one event per parameter, recorded on the stream its gradient was accumulated on
         self._armed = True
         for bi, (ps, _) in enumerate(self.buckets):
             for p in ps:
@@ -81,12 +82,25 @@ class BucketedGradAllReduce:
         if self._launched[bi] or self._pending[bi] == 0:
             raise RuntimeError("BucketedGradAllReduce: a parameter received a second gradient before finish() -- call finish() "
                                "after every backward(), or accumulate under no_sync()")
+        if p.is_cuda:
+            # backward nodes run on the streams their forward ran on (the model forks parallel branches): the stream that packs the
+            # bucket must wait for every gradient's own stream.  Under CUDA-graph capture these become edges of the graph.
+            ev = self._events.get(p)
+            if ev is None:
+                ev = self._events[p] = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(p.device))
         self._pending[bi] -= 1
         if self._pending[bi] == 0:
             self._launch(bi)
 
     def _launch(self, bi):
         ps, flat = self.buckets[bi]
+        if flat.is_cuda:
+            cur = torch.cuda.current_stream(flat.device)
+            for p in ps:
+                ev = self._events.get(p)
+                if ev is not None:
+                    cur.wait_event(ev)
         torch._foreach_copy_(list(flat.split([p.numel() for p in ps])), [p.grad.reshape(-1) for p in ps])
         if self.world > 1:
             self._handles[bi] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
