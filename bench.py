@@ -681,11 +681,15 @@ def run_model(h, args):
         opt.step()
         return loss
 
+    # one stream for the profiling pass: with the parallel branches on, an op's event pair would also time whatever the other
+    # branches run concurrently
+    branches, K.config.parallel_branches = K.config.parallel_branches, False
     eager_step()
     ops.profile_start()
     for _ in range(prof_steps):
         eager_step()
     prof = ops.profile_stop()
+    K.config.parallel_branches = branches
     peaks = load_peaks()
     table = []
     for (name, key), e in prof.items():
@@ -744,7 +748,7 @@ def run_model(h, args):
             "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * world, "frames": f"{fin}->{classes}",
                        "size": size, "precision": (f"KANConv2d, the HSM-SSD projection (forward, dgrad, wgrad) and the 1x1-convolution backward {args.precision} (tcgen05), torch GEMMs (SSIM filter of the loss, nn.Linear) TF32, everything else fp32"
                                      if args.precision == "bf16" else "fp32 everywhere"),
-                       "parallelism": f"dp{world}", "cuda_graph": used_graph, "optimizer": "AdamW(lr 1e-3, wd 0.05, fused)" if train else None,
+                       "parallelism": f"dp{world}", "cuda_graph": used_graph, "parallel_graph_branches": bool(K.config.parallel_branches), "optimizer": "AdamW(lr 1e-3, wd 0.05, fused)" if train else None,
                        "l2": "activations per step (hundreds of %.0f MB tensors) exceed the 126 MB L2" % (B * 16 * size * size * 4 / 1e6),
                        "grad_allreduce": ((f"bucketed NCCL all-reduce of {nlive * 4 / 1e6:.1f} MB launched from grad-ready hooks, captured inside the step graph "
                                            "(overlaps the rest of backward)" if args.comm == "captured" else

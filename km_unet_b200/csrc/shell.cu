@@ -161,13 +161,53 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
   }
 }
 
-// Same, HW % 4 == 0: grid (chunks of 4096 elements, B * C planes) -- the channel is a property of the CTA, no per-thread divisions
-__global__ void __launch_bounds__(256) bn_apply_plane_kernel(const float* __restrict__ x, const float2* __restrict__ stat,
-                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                             const float* __restrict__ res, const float* __restrict__ alpha,
-                                                             float* __restrict__ y, int C, int HW, int relu) {
-  const int plane = blockIdx.y, c = plane % C;
-  const float2 st = stat[c];
+// Same, HW % 4 == 0: grid (chunks of 4096 elements, B * C planes) -- the channel is a property of the CTA, no per-thread divisions.
+// The statistics finalize is folded in: warp 0 of EVERY CTA reduces its channel's partials in double (same order everywhere ->
+// identical values) instead of a separate one-warp-per-channel kernel between the two passes; the CTA of (sample 0, chunk 0) writes
+// stat[c] for the backward and updates the running statistics.
+__global__ void __launch_bounds__(256) bn_apply_plane_kernel(const float* __restrict__ x, const float* __restrict__ part,
+                                                             float2* __restrict__ stat, float* __restrict__ rmean,
+                                                             float* __restrict__ rvar, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, const float* __restrict__ res,
+                                                             const float* __restrict__ alpha, float* __restrict__ y, BnDims d, int training,
+                                                             float momentum, float eps, int relu) {
+  __shared__ float2 st_s;
+  const int plane = blockIdx.y, c = plane % d.C, HW = d.HW;
+  if (threadIdx.x < 32) {
+    double mean, var;
+    if (training) {
+      double s = 0.0, q = 0.0;
+      for (int i = threadIdx.x; i < d.nsplit; i += 32) {
+        s += (double)part[((size_t)c * d.nsplit + i) * 2];
+        q += (double)part[((size_t)c * d.nsplit + i) * 2 + 1];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+      }
+      const double ms = s / (double)d.per;
+      var = q / (double)d.per - ms * ms;
+      if (var < 0.0) var = 0.0;
+      mean = ms + (double)x[(size_t)c * HW];
+    } else {
+      mean = (double)rmean[c];
+      var = (double)rvar[c];
+    }
+    if (threadIdx.x == 0) {
+      st_s = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+      if (plane == c && blockIdx.x == 0) {
+        stat[c] = st_s;
+        if (training && rmean && rvar) {
+          const double unb = d.per > 1 ? var * (double)d.per / (double)(d.per - 1) : var;
+          rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)mean;
+          rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unb;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const float2 st = st_s;
   const float sc = gamma[c] * st.y, sh = beta[c] - st.x * sc;
   const float a = alpha ? 1.f / (1.f + expf(-alpha[c])) : 1.f, b = 1.f - a;
   const size_t base = (size_t)plane * HW;
@@ -300,14 +340,43 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_plane_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                                                 const float2* __restrict__ stat, const float2* __restrict__ bstat,
+                                                                 const float2* __restrict__ stat, const float* __restrict__ part,
                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                  const float* __restrict__ alpha, float* __restrict__ dx,
-                                                                 float* __restrict__ dres, int C, int HW, int relu) {
-  const int plane = blockIdx.y, c = plane % C;
-  const float2 st = stat[c], bs = bstat[c];
-  const float sc = gamma[c] * st.y, sh = beta[c] - st.x * sc;
+                                                                 float* __restrict__ dres, float* __restrict__ dgamma,
+                                                                 float* __restrict__ dbeta, float* __restrict__ dalpha, BnDims d, int training,
+                                                                 int relu) {
+  // the backward finalize folded in (see bn_apply_plane_kernel): every CTA reduces its channel's three partial sums in double
+  __shared__ float2 bs_s;
+  const int plane = blockIdx.y, c = plane % d.C, HW = d.HW;
   const float a = alpha ? 1.f / (1.f + expf(-alpha[c])) : 1.f, b = 1.f - a;
+  if (threadIdx.x < 32) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int i = threadIdx.x; i < d.nsplit; i += 32) {
+      const float* p = part + ((size_t)c * d.nsplit + i) * 3;
+      s0 += (double)p[0];
+      s1 += (double)p[1];
+      s2 += (double)p[2];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (threadIdx.x == 0) {
+      const double ad = alpha ? 1.0 / (1.0 + exp(-(double)alpha[c])) : 1.0;
+      bs_s = training ? make_float2((float)(ad * s0 / (double)d.per), (float)(ad * s1 / (double)d.per)) : make_float2(0.f, 0.f);
+      if (plane == c && blockIdx.x == 0) {
+        dbeta[c] = (float)(ad * s0);
+        dgamma[c] = (float)(ad * s1);
+        if (dalpha) dalpha[c] = (float)(s2 * ad * (1.0 - ad));
+      }
+    }
+  }
+  __syncthreads();
+  const float2 st = stat[c], bs = bs_s;
+  const float sc = gamma[c] * st.y, sh = beta[c] - st.x * sc;
   auto one = [&](float xv, float g) {
     if (relu && fmaf(xv, sc, sh) <= 0.f) g = 0.f;
     return sc * (a * g - bs.x - (xv - st.x) * st.y * bs.y);
@@ -610,14 +679,18 @@ int kmu_bnmix_fwd(const kmu_bnmix_fwd_args* a, kmu_stream stream) {
     bn_stats_kernel<<<dim3(d.nsplit, d.C), 256, 0, st>>>(a->x, part, d);
     KMU_LAUNCH_CHECK("bn_stats");
   }
-  bn_fin_kernel<<<d.C, 32, 0, st>>>(a->x, part, stat, a->running_mean, a->running_var, d, a->d.training, a->d.momentum, a->d.eps);
-  KMU_LAUNCH_CHECK("bn_fin");
   const long long total = (long long)d.B * d.C * d.HW;
   const float* res = a->d.mix ? a->res : nullptr;
   const float* alpha = a->d.mix ? a->alpha : nullptr;
-  if ((d.HW & 3) == 0 && (long long)d.B * d.C <= 65535)
-    bn_apply_plane_kernel<<<dim3(cdiv(d.HW, 4096), d.B * d.C), 256, 0, st>>>(a->x, stat, a->weight, a->bias, res, alpha, a->y, d.C, d.HW,
-                                                                             a->d.relu);
+  const bool plane_path = (d.HW & 3) == 0 && (long long)d.B * d.C <= 65535;
+  if (!plane_path) {
+    bn_fin_kernel<<<d.C, 32, 0, st>>>(a->x, part, stat, a->running_mean, a->running_var, d, a->d.training, a->d.momentum, a->d.eps);
+    KMU_LAUNCH_CHECK("bn_fin");
+  }
+  if (plane_path)
+    bn_apply_plane_kernel<<<dim3(cdiv(d.HW, 4096), d.B * d.C), 256, 0, st>>>(a->x, part, stat, a->running_mean, a->running_var, a->weight,
+                                                                             a->bias, res, alpha, a->y, d, a->d.training, a->d.momentum,
+                                                                             a->d.eps, a->d.relu);
   else if ((d.HW & 3) == 0)
     bn_apply_kernel<true><<<cdiv(total / 4, 256), 256, 0, st>>>(a->x, stat, a->weight, a->bias, res, alpha, a->y, d.C, d.HW, total, a->d.relu);
   else
@@ -643,13 +716,17 @@ int kmu_bnmix_bwd(const kmu_bnmix_bwd_args* a, kmu_stream stream) {
   const float* alpha = a->d.mix ? a->alpha : nullptr;
   bn_bwd_stats_kernel<<<dim3(d.nsplit, d.C), 256, 0, st>>>(a->x, a->dy, stat, a->weight, a->bias, res, part, d, a->d.relu);
   KMU_LAUNCH_CHECK("bn_bwd_stats");
-  bn_bwd_fin_kernel<<<d.C, 32, 0, st>>>(part, bstat, alpha, a->d_weight, a->d_bias, a->d.mix ? a->d_alpha : nullptr, d, a->d.training);
-  KMU_LAUNCH_CHECK("bn_bwd_fin");
   const long long total = (long long)d.B * d.C * d.HW;
   float* dres = a->d.mix ? a->d_res : nullptr;
-  if ((d.HW & 3) == 0 && (long long)d.B * d.C <= 65535)
-    bn_bwd_apply_plane_kernel<<<dim3(cdiv(d.HW, 4096), d.B * d.C), 256, 0, st>>>(a->x, a->dy, stat, bstat, a->weight, a->bias, alpha, a->dx,
-                                                                                 dres, d.C, d.HW, a->d.relu);
+  const bool plane_path = (d.HW & 3) == 0 && (long long)d.B * d.C <= 65535;
+  if (!plane_path) {
+    bn_bwd_fin_kernel<<<d.C, 32, 0, st>>>(part, bstat, alpha, a->d_weight, a->d_bias, a->d.mix ? a->d_alpha : nullptr, d, a->d.training);
+    KMU_LAUNCH_CHECK("bn_bwd_fin");
+  }
+  if (plane_path)
+    bn_bwd_apply_plane_kernel<<<dim3(cdiv(d.HW, 4096), d.B * d.C), 256, 0, st>>>(a->x, a->dy, stat, part, a->weight, a->bias, alpha, a->dx,
+                                                                                 dres, a->d_weight, a->d_bias,
+                                                                                 a->d.mix ? a->d_alpha : nullptr, d, a->d.training, a->d.relu);
   else if ((d.HW & 3) == 0)
     bn_bwd_apply_kernel<true><<<cdiv(total / 4, 256), 256, 0, st>>>(a->x, a->dy, stat, bstat, a->weight, a->bias, alpha, a->dx, dres, d.C,
                                                                     d.HW, total, a->d.relu);
