@@ -403,6 +403,108 @@ static void launch_wgrad(const kmu_smallconv_desc& d, const WgradPlan& pl, const
   sc_wgrad_kernel<NO><<<pl.ctas, 256, smem, st>>>(x, dy, partial, d.Cin, d.Cout, d.H, d.W, ntiles, pl.TOn, pl.PG, sdy, sdx);
 }
 
+// ---- 3-tap weight gradient, warp-per-strip form.  A warp stages a strip of 128 consecutive pixels of one image row -- 16 input
+//      channels (for a vertical kernel: the rows above and below as well) and 16 output-gradient channels -- in its own slice of
+//      shared memory with coalesced 128-bit loads, then lane = (output channel o = lane & 15, half of the strip): per pixel quad one
+//      LDS.128 of dy[o] and, per input channel, one broadcast LDS.128 of x (+ two scalars for the horizontal taps) feed 48 FMA x 4
+//      pixels into 48 accumulators (o fixed, 16 c x 3 taps) that live for the warp's whole pixel range.  Every byte of x and dy is
+//      read from HBM once; the arithmetic (0.8 GFLOP at (32,16,16,128,128)) is no issue.
+//      grid (slices, (Cin/16) * (Cout/16)), 128 threads; partial[(slice * 4 + warp)][o][c][t] (+ bias), reduced in fixed order.
+// strip width: 128 pixels for a horizontal kernel (one staged x row), 64 for a vertical one (three rows): ~17 KB of shared memory per
+// warp either way, three 4-warp CTAs per SM
+static inline int strip_width(int W, int vertical) { const int s = vertical ? 64 : 128; return W < s ? W : s; }
+static inline size_t strip_floats(int sw, int vertical) { return (size_t)(vertical ? 3 : 1) * 16 * (sw + 8) + (size_t)16 * (sw + 4); }
+__global__ void __launch_bounds__(128) sc3_wgrad_strip_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                              float* __restrict__ partial, int Cin, int Cout, int H, int W, int B,
+                                                              int vertical) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sw = W < (vertical ? 64 : 128) ? W : (vertical ? 64 : 128);      // strip width
+  const int rows = vertical ? 3 : 1, xst = sw + 8, yst = sw + 4;
+  float* xs = smem + (size_t)warp * ((size_t)rows * 16 * xst + (size_t)16 * yst);
+  float* ys = xs + (size_t)rows * 16 * xst;
+  const int cblocks = Cin >> 4;
+  const int ob = blockIdx.y / cblocks, cb = blockIdx.y - ob * cblocks;
+  const int c0 = cb * 16, o0 = ob * 16;
+  const int HW = H * W;
+  const int strips_per_row = W / sw;             // W % sw == 0 (host check)
+  const long long nstrips = (long long)B * H * strips_per_row;
+  const int o = lane & 15, half = lane >> 4;
+  float acc[16][3], bacc = 0.f;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c][0] = acc[c][1] = acc[c][2] = 0.f;
+  for (long long st = (long long)blockIdx.x * 4 + warp; st < nstrips; st += (long long)gridDim.x * 4) {
+    const int b = (int)(st / ((long long)H * strips_per_row));
+    const int rem = (int)(st - (long long)b * H * strips_per_row);
+    const int h = rem / strips_per_row, w0 = (rem - h * strips_per_row) * sw;
+    __syncwarp();
+    // stage: x rows (h - 1, h, h + 1 for a vertical kernel; h only otherwise) and dy row h, 16 channels each, 128-bit loads
+    const int q4 = sw >> 2;
+    for (int i = lane; i < rows * 16 * q4; i += 32) {
+      const int q = i % q4, rc = i / q4, c = rc & 15, r = rc >> 4;
+      const int hh = vertical ? h + r - 1 : h;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (hh >= 0 && hh < H) v = __ldg(reinterpret_cast<const float4*>(x + ((size_t)b * Cin + c0 + c) * HW + (size_t)hh * W + w0) + q);
+      *reinterpret_cast<float4*>(xs + (r * 16 + c) * xst + 4 + 4 * q) = v;
+    }
+    if (!vertical && lane < 16) {               // the two halo pixels of a horizontal kernel
+      const float* row = x + ((size_t)b * Cin + c0 + lane) * HW + (size_t)h * W;
+      xs[lane * xst + 3] = w0 > 0 ? __ldg(row + w0 - 1) : 0.f;
+      xs[lane * xst + 4 + sw] = w0 + sw < W ? __ldg(row + w0 + sw) : 0.f;
+    }
+    for (int i = lane; i < 16 * q4; i += 32) {
+      const int q = i % q4, oo = i / q4;
+      *reinterpret_cast<float4*>(ys + oo * yst + 4 * q) =
+          __ldg(reinterpret_cast<const float4*>(dy + ((size_t)b * Cout + o0 + oo) * HW + (size_t)h * W + w0) + q);
+    }
+    __syncwarp();
+    const int qh = q4 >> 1;                      // quads per half (sw % 8 == 0)
+    for (int q = half * qh; q < (half + 1) * qh; ++q) {
+      const float4 g = *reinterpret_cast<const float4*>(ys + o * yst + 4 * q);
+      bacc += (g.x + g.y) + (g.z + g.w);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        float4 v0, v1, v2;
+        if (vertical) {
+          v0 = *reinterpret_cast<const float4*>(xs + (0 * 16 + c) * xst + 4 + 4 * q);
+          v1 = *reinterpret_cast<const float4*>(xs + (1 * 16 + c) * xst + 4 + 4 * q);
+          v2 = *reinterpret_cast<const float4*>(xs + (2 * 16 + c) * xst + 4 + 4 * q);
+        } else {
+          const float* xr = xs + c * xst + 4 + 4 * q;
+          v1 = *reinterpret_cast<const float4*>(xr);
+          v0 = make_float4(xr[-1], v1.x, v1.y, v1.z);
+          v2 = make_float4(v1.y, v1.z, v1.w, xr[4]);
+        }
+        acc[c][0] += g.x * v0.x + g.y * v0.y + g.z * v0.z + g.w * v0.w;
+        acc[c][1] += g.x * v1.x + g.y * v1.y + g.z * v1.z + g.w * v1.w;
+        acc[c][2] += g.x * v2.x + g.y * v2.y + g.z * v2.z + g.w * v2.w;
+      }
+    }
+  }
+  // the two halves of the strip, then out: partial[(slice, warp)][o][c][t] | bias
+  float* pb = partial + ((size_t)blockIdx.x * 4 + warp) * ((size_t)Cout * Cin * 3 + Cout);
+#pragma unroll
+  for (int c = 0; c < 16; ++c)
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      const float v = acc[c][t] + __shfl_xor_sync(0xffffffffu, acc[c][t], 16);
+      if (half == 0) pb[((size_t)(o0 + o) * Cin + c0 + c) * 3 + t] = v;
+    }
+  const float bv = bacc + __shfl_xor_sync(0xffffffffu, bacc, 16);
+  if (half == 0 && cb == 0) pb[(size_t)Cout * Cin * 3 + o0 + o] = bv;
+}
+static bool three_tap_strip(const kmu_smallconv_desc& d) {
+  const int sw = strip_width(d.W, d.kh == 3);
+  return d.kh * d.kw == 3 && d.Cin % 16 == 0 && d.Cout % 16 == 0 && sw % 8 == 0 && d.W % sw == 0;
+}
+static int strip_slices(const kmu_smallconv_desc& d) {
+  const int blocks = (d.Cin / 16) * (d.Cout / 16);
+  int s = (148 * 3 + blocks - 1) / blocks;
+  const long long strips = (long long)d.B * d.H * (d.W / strip_width(d.W, d.kh == 3));
+  if ((long long)s * 4 > strips) s = (int)((strips + 3) / 4);
+  return s < 1 ? 1 : s;
+}
+
 // 1x3 / 3x1 fast path: one forward / dgrad kernel with 128-bit traffic, one weight-gradient pass for all three taps
 static bool three_tap(const kmu_smallconv_desc& d) { return d.kh * d.kw == 3 && d.W % 4 == 0 && d.Cin % 4 == 0 && d.Cout % 4 == 0; }
 static bool three_tap_wgrad(const kmu_smallconv_desc& d) {
@@ -435,6 +537,7 @@ size_t kmu_smallconv_bwd_workspace_bytes(const kmu_smallconv_desc* d) {
   if (!wgrad_ok(*d)) return 256;
   WgradPlan pl = wgrad_plan(*d);
   size_t parts = (size_t)pl.ctas * pl.PG;
+  if (three_tap_strip(*d) && (size_t)strip_slices(*d) * 4 > parts) parts = (size_t)strip_slices(*d) * 4;
   return align_up(parts * ((size_t)d->Cout * d->Cin * 3 + d->Cout) * 4, 256);
 }
 
@@ -474,6 +577,17 @@ int kmu_smallconv_bwd(const kmu_smallconv_desc* d, const float* x, const float* 
     const WgradPlan pl = wgrad_plan(*d);
     const Taps taps = make_taps(d->kh, d->kw, false);
     const int n_w = d->Cout * d->Cin, n_b = d->Cout;
+    if (three_tap_strip(*d) && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0) {
+      const int slices = strip_slices(*d);
+      const size_t smem = (size_t)4 * strip_floats(strip_width(d->W, d->kh == 3), d->kh == 3) * 4;
+      cudaFuncSetAttribute(sc3_wgrad_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      sc3_wgrad_strip_kernel<<<dim3(slices, (d->Cin / 16) * (d->Cout / 16)), 128, smem, st>>>(x, dy, partial, d->Cin, d->Cout, d->H, d->W,
+                                                                                            d->B, d->kh == 3);
+      KMU_LAUNCH_CHECK("sc3_wgrad_strip");
+      sc_wreduce_kernel<<<cdiv(3 * n_w + n_b, 32), 256, 0, st>>>(partial, slices * 4, 3 * n_w, n_b, 1, 0, dw, dbias);
+      KMU_LAUNCH_CHECK("sc_wreduce");
+      return KMU_OK;
+    }
     if (three_tap_wgrad(*d)) {
       WgradPlan p3 = pl;
       p3.NO = 4;
