@@ -477,6 +477,133 @@ __global__ void __launch_bounds__(256) dw3x3_kernel(const float* __restrict__ x,
   }
 }
 
+// Row-sliding forms (W % 4 == 0).  CTA = (row slice, plane); thread = (column quad, sub-slice of the rows): it walks DOWN its rows with a
+// three-row register window, so every new output row costs one row of loads (a 128-bit vector + the two neighbouring scalars)
+// instead of three, and there is no index arithmetic beyond a row pointer increment.
+struct Row6 { float v[6]; };
+__device__ __forceinline__ Row6 load_row6(const float* __restrict__ plane, int h, int H, int W, int w0) {
+  Row6 r;
+  if (h < 0 || h >= H) {
+#pragma unroll
+    for (int e = 0; e < 6; ++e) r.v[e] = 0.f;
+    return r;
+  }
+  const float* row = plane + (size_t)h * W + w0;
+  const float4 m = *reinterpret_cast<const float4*>(row);
+  r.v[0] = w0 > 0 ? __ldg(row - 1) : 0.f;
+  r.v[1] = m.x; r.v[2] = m.y; r.v[3] = m.z; r.v[4] = m.w;
+  r.v[5] = w0 + 4 < W ? __ldg(row + 4) : 0.f;
+  return r;
+}
+
+__global__ void __launch_bounds__(256) dw3x3_rows_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, const float* __restrict__ scale,
+                                                             float* __restrict__ y, DwDims d, int rows_per_cta) {
+  const int plane = blockIdx.y, c = plane % d.C;
+  const int wq = d.W >> 2, nsub = 256 / wq;                 // wq divides 256 (host check)
+  const int q = threadIdx.x % wq, sub = threadIdx.x / wq;
+  const int r0 = blockIdx.x * rows_per_cta;
+  const int r1 = min(r0 + rows_per_cta, d.H);
+  const int per = (r1 - r0 + nsub - 1) / nsub;
+  const int h0 = r0 + sub * per, h1 = min(h0 + per, r1);
+  if (h0 >= h1) return;
+  float k[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) k[i] = __ldg(w + c * 9 + i);
+  const float bv = bias ? __ldg(bias + c) : 0.f;
+  const float sc = scale ? __ldg(scale + plane) : 1.f;
+  const float* xp = x + (size_t)plane * d.H * d.W;
+  float* yp = y + (size_t)plane * d.H * d.W;
+  const int w0 = q * 4;
+  Row6 a = load_row6(xp, h0 - 1, d.H, d.W, w0), b = load_row6(xp, h0, d.H, d.W, w0);
+  for (int h = h0; h < h1; ++h) {
+    const Row6 cc = load_row6(xp, h + 1, d.H, d.W, w0);
+    float acc[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      acc[e] = bv;
+      acc[e] = fmaf(k[0], a.v[e], fmaf(k[1], a.v[e + 1], fmaf(k[2], a.v[e + 2], acc[e])));
+      acc[e] = fmaf(k[3], b.v[e], fmaf(k[4], b.v[e + 1], fmaf(k[5], b.v[e + 2], acc[e])));
+      acc[e] = fmaf(k[6], cc.v[e], fmaf(k[7], cc.v[e + 1], fmaf(k[8], cc.v[e + 2], acc[e])));
+    }
+    *reinterpret_cast<float4*>(yp + (size_t)h * d.W + w0) = make_float4(acc[0] * sc, acc[1] * sc, acc[2] * sc, acc[3] * sc);
+    a = b;
+    b = cc;
+  }
+}
+
+// dx AND the weight / bias gradient partials with the same row walk: windows of x and dy (three rows each).
+__global__ void __launch_bounds__(256) dw3x3_rows_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                             const float* __restrict__ w, const float* __restrict__ scale,
+                                                             const float* add, float* dx, float* __restrict__ part, DwDims d,
+                                                             int rows_per_cta) {
+  __shared__ float red[8][10];
+  const int plane = blockIdx.y, c = plane % d.C;
+  const int wq = d.W >> 2, nsub = 256 / wq;
+  const int q = threadIdx.x % wq, sub = threadIdx.x / wq;
+  const int r0 = blockIdx.x * rows_per_cta;
+  const int r1 = min(r0 + rows_per_cta, d.H);
+  const int per = (r1 - r0 + nsub - 1) / nsub;
+  const int h0 = r0 + sub * per, h1 = min(h0 + per, r1);
+  float k[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) k[i] = __ldg(w + c * 9 + 8 - i);        // flipped taps: dx = correlate(dy, flip(w))
+  const float sc = scale ? __ldg(scale + plane) : 1.f;
+  const float* xp = x + (size_t)plane * d.H * d.W;
+  const float* gp = dy + (size_t)plane * d.H * d.W;
+  const int w0 = q * 4;
+  float a[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) a[i] = 0.f;
+  if (h0 < h1) {
+    Row6 xa = load_row6(xp, h0 - 1, d.H, d.W, w0), xb = load_row6(xp, h0, d.H, d.W, w0);
+    Row6 ga = load_row6(gp, h0 - 1, d.H, d.W, w0), gb = load_row6(gp, h0, d.H, d.W, w0);
+    for (int h = h0; h < h1; ++h) {
+      const Row6 xc = load_row6(xp, h + 1, d.H, d.W, w0), gc = load_row6(gp, h + 1, d.H, d.W, w0);
+      // weight gradient: dy of THIS row (gb, centre 4) against the 3x3 neighbourhood of x
+      a[9] += (gb.v[1] + gb.v[2]) + (gb.v[3] + gb.v[4]);
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        a[kx] += gb.v[1] * xa.v[kx] + gb.v[2] * xa.v[kx + 1] + gb.v[3] * xa.v[kx + 2] + gb.v[4] * xa.v[kx + 3];
+        a[3 + kx] += gb.v[1] * xb.v[kx] + gb.v[2] * xb.v[kx + 1] + gb.v[3] * xb.v[kx + 2] + gb.v[4] * xb.v[kx + 3];
+        a[6 + kx] += gb.v[1] * xc.v[kx] + gb.v[2] * xc.v[kx + 1] + gb.v[3] * xc.v[kx + 2] + gb.v[4] * xc.v[kx + 3];
+      }
+      if (dx) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc[e] = fmaf(k[0], ga.v[e], fmaf(k[1], ga.v[e + 1], fmaf(k[2], ga.v[e + 2], acc[e])));
+          acc[e] = fmaf(k[3], gb.v[e], fmaf(k[4], gb.v[e + 1], fmaf(k[5], gb.v[e + 2], acc[e])));
+          acc[e] = fmaf(k[6], gc.v[e], fmaf(k[7], gc.v[e + 1], fmaf(k[8], gc.v[e + 2], acc[e])));
+        }
+        const size_t off = (size_t)plane * d.H * d.W + (size_t)h * d.W + w0;
+        float4 o = make_float4(acc[0] * sc, acc[1] * sc, acc[2] * sc, acc[3] * sc);
+        if (add) {
+          const float4 m = *reinterpret_cast<const float4*>(add + off);
+          o.x += m.x; o.y += m.y; o.z += m.z; o.w += m.w;
+        }
+        *reinterpret_cast<float4*>(dx + off) = o;
+      }
+      xa = xb; xb = xc;
+      ga = gb; gb = gc;
+    }
+  }
+  // one barrier for all ten sums: warp shuffles, then the eight warp partials are added in warp order
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const float s = warp_sum(a[i]);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 10) {
+    float s = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) s += red[w8][threadIdx.x];
+    part[((size_t)plane * gridDim.x + blockIdx.x) * 10 + threadIdx.x] = s;
+  }
+}
+static bool dw_rows_ok(const DwDims& d) { return (d.W & 3) == 0 && d.W >= 16 && d.W <= 1024 && 256 % (d.W >> 2) == 0; }
+
 // weight / bias gradient partials: part[(plane*RS + rs)*10 + t] = sum over the CTA's rows of dy(p) x(p + tap t) (t < 9), sum dy (t = 9)
 // grid (RS, B*C), 256 threads; thread = 4 consecutive columns of a row, rows strided over the CTA's row slice
 __global__ void __launch_bounds__(256) dw3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
@@ -748,6 +875,13 @@ static int dw_fwd(const kmu_dwconv3x3_desc* dd, const float* x, const float* w, 
   if (rc != KMU_OK) return rc;
   KMU_REQUIRE(x && w && y, KMU_ERR_BAD_ARG, "dwconv3x3_fwd: null tensor");
   DwDims d{dd->B, dd->C, dd->H, dd->W};
+  if (dw_rows_ok(d) && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0) {
+    const int rs = dw_row_slices(*dd);
+    const int rows = cdiv(d.H, rs);
+    dw3x3_rows_fwd_kernel<<<dim3(cdiv(d.H, rows), d.B * d.C), 256, 0, (cudaStream_t)stream>>>(x, w, bias, scale, y, d, rows);
+    KMU_LAUNCH_CHECK("dw3x3_fwd");
+    return KMU_OK;
+  }
   long long total = (long long)d.B * d.C * d.H * ((d.W + 3) / 4);
   dw3x3_kernel<false><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, w, bias, scale, nullptr, y, d);
   KMU_LAUNCH_CHECK("dw3x3_fwd");
@@ -774,7 +908,9 @@ static int dw_bwd(const kmu_dwconv3x3_desc* dd, const float* x, const float* dy,
     const int rs = dw_row_slices(*dd);
     const int rows = cdiv(d.H, rs);
     const int rs2 = cdiv(d.H, rows);
-    if (fused)
+    if (fused && dw_rows_ok(d))
+      dw3x3_rows_bwd_kernel<<<dim3(rs2, d.B * d.C), 256, 0, st>>>(x, dy, w, scale, dx_add, dx, (float*)workspace, d, rows);
+    else if (fused)
       dw3x3_bwd_fused_kernel<<<dim3(rs2, d.B * d.C), 256, 0, st>>>(x, dy, w, scale, dx_add, dx, (float*)workspace, d, rows);
     else
       dw3x3_wgrad_kernel<<<dim3(rs2, d.B * d.C), 256, 0, st>>>(x, dy, (float*)workspace, d, rows);
