@@ -61,7 +61,6 @@ __device__ __forceinline__ size_t chan_off(long long v, int c, int C, int HW) {
 //      (k is a sample of the channel, so |E[x-k]| is a few std at most); nn.BatchNorm's Welford has no such problem either.
 //      grid (nsplit, C), 256 threads
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, float* __restrict__ part, BnDims d) {
-  __shared__ float red[8];
   const int c = blockIdx.y, s = blockIdx.x;
   const long long v0 = (long long)s * d.len;
   long long v1 = v0 + d.len;
@@ -87,11 +86,17 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
       q = fmaf(t, t, q);
     }
   }
-  a = block_sum(a, red);
-  q = block_sum(q, red);
-  if (threadIdx.x == 0) {
-    part[((size_t)c * d.nsplit + s) * 2] = a;
-    part[((size_t)c * d.nsplit + s) * 2 + 1] = q;
+  // one barrier for both sums: warp shuffles, then the eight warp partials in warp order
+  __shared__ float red2[8][2];
+  a = warp_sum(a);
+  q = warp_sum(q);
+  if ((threadIdx.x & 31) == 0) { red2[threadIdx.x >> 5][0] = a; red2[threadIdx.x >> 5][1] = q; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float t = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) t += red2[w8][threadIdx.x];
+    part[((size_t)c * d.nsplit + s) * 2 + threadIdx.x] = t;
   }
 }
 
@@ -234,7 +239,6 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(const float* __restri
                                                            const float2* __restrict__ stat, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, const float* __restrict__ res,
                                                            float* __restrict__ part, BnDims d, int relu) {
-  __shared__ float red[8];
   const int c = blockIdx.y, s = blockIdx.x;
   const long long v0 = (long long)s * d.len;
   long long v1 = v0 + d.len;
@@ -267,12 +271,17 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(const float* __restri
       one(x[off], dy[off], res ? res[off] : 0.f);
     }
   }
-  sg = block_sum(sg, red);
-  sgx = block_sum(sgx, red);
-  sa = block_sum(sa, red);
-  if (threadIdx.x == 0) {
-    float* p = part + ((size_t)c * d.nsplit + s) * 3;
-    p[0] = sg; p[1] = sgx; p[2] = sa;
+  __shared__ float red3[8][3];
+  sg = warp_sum(sg);
+  sgx = warp_sum(sgx);
+  sa = warp_sum(sa);
+  if ((threadIdx.x & 31) == 0) { red3[threadIdx.x >> 5][0] = sg; red3[threadIdx.x >> 5][1] = sgx; red3[threadIdx.x >> 5][2] = sa; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float t = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) t += red3[w8][threadIdx.x];
+    part[((size_t)c * d.nsplit + s) * 3 + threadIdx.x] = t;
   }
 }
 
