@@ -25,7 +25,8 @@ for k, v in step:
     agg[key][0] += 1
     agg[key][1] += v
 tot = sum(v for _, v in step)
-ours = sum(v[1] for k, v in agg.items() if any(ns in k for ns in ("kan::", "hsm::", "dys", "dagem", "shell::", "pw::", "sc::", "glue::", "tc::", "tcb::", "fused::", "pwtc::", "iwp")))
+ours = sum(v[1] for k, v in agg.items() if any(ns in k for ns in ("kan::", "hsm::", "dys", "dagem", "shell::", "pw::", "sc::", "glue::", "tc::", "tcb::", "fused::", "pwtc::", "iwp", "fz::", "deform::", "loss::",
+                                                                    "kmu::")))
 print("# Kernel launches of one full-model training step (KM_UNetV3_SH, B=32, 128x128, tensor-core precision class as in bench.py)\n")
 print(f"Source: `{sys.argv[1].split('/')[-1]}` -- `ncu --metrics gpu__time_duration.sum --clock-control none` over `tools/prof_model_step.py`")
 print("(eager execution, one launch per kernel; ncu serialises launches and runs them cold-cache: compare SHARES, not absolutes).")
