@@ -447,7 +447,16 @@ class Harness:
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         self.barrier()
+        self.per_rank_ms = self.gather(ms)
         return self.max_over_ranks(ms)
+
+    def gather(self, obj):
+        """Every rank's value of `obj`, in rank order (diagnostics only: which rank is the slow one, and at which clock)."""
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
 
 
 def kan_microbench(h, B, steps, warmup, precision, with_total=False):
@@ -640,15 +649,18 @@ def run_model(h, args):
         torch.cuda.current_stream().synchronize()
         state["i"] += 1
 
-    sampler = ClockSampler(h.local) if rank == 0 else None
-    if sampler:
-        sampler.start()
+    sampler = ClockSampler(h.local)            # every rank samples its own GPU; rank 0's goes into `clocks`, the rest into per_rank
+    sampler.start()
     launches0 = _lib.launch_count()
     total_ms = h.timed(step_resident, args.steps, args.warmup)
+    per_rank_ms = [m / args.steps for m in h.per_rank_ms]
     launches = (_lib.launch_count() - launches0) // (args.steps + args.warmup)
     if graphed is not None:
         launches = graphed_launches            # replays do not pass through the host-side counter: count of the captured step
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop()
+    if world > 1:
+        every = h.gather({"sm_mhz": clocks["sm_mhz"], "reasons": clocks["reasons"]})
+        clocks["per_rank"] = [dict(c, ms_per_step=m) for c, m in zip(every, per_rank_ms)]
     value = world * B * args.steps / (total_ms / 1e3)
     last_loss = float(step_resident().detach().float().cpu())     # sanity: a diverged / corrupted run must not pass as a number
     e2e_ms = h.timed(step_e2e, args.steps, args.warmup)
@@ -665,6 +677,7 @@ def run_model(h, args):
         comm = {"mode": args.comm, "graph_launches_per_step": graphed.graph_launches_per_step,
                 "buckets": len(graphed.reducer.buckets), "bytes_per_step": sum(f.numel() * 4 for _, f in graphed.reducer.buckets),
                 "ms_per_step_without_allreduce": nocomm_ms / args.steps,
+                "per_rank_ms_without_allreduce": [m / args.steps for m in h.per_rank_ms],
                 "exposed_comm_ms": (total_ms - nocomm_ms) / args.steps}
         nocomm.close()
         del nocomm
