@@ -592,7 +592,9 @@ def run_model(h, args):
         live = [p for p in model.parameters() if p.grad is not None]
         for p in model.parameters():
             p.grad = None
-        opt = torch.optim.AdamW(live, lr=1e-3, weight_decay=0.05, fused=True, capturable=args.graph)
+        # train_shanghai.py:342; one launch per step (csrc/optim.cu) instead of torch's 19 multi_tensor_apply launches
+        opt = (K.FusedAdamW(live, lr=1e-3, weight_decay=0.05) if args.optimizer == "kmu" else
+               torch.optim.AdamW(live, lr=1e-3, weight_decay=0.05, fused=True, capturable=args.graph))
         reducer = BucketedGradAllReduce(live, bucket_bytes=2 << 20) if (world > 1 and not args.graph) else None
     graphed, graphed_launches = None, 0
     if train and args.graph:
@@ -761,7 +763,7 @@ def run_model(h, args):
             "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * world, "frames": f"{fin}->{classes}",
                        "size": size, "precision": (f"KANConv2d, the HSM-SSD projection (forward, dgrad, wgrad) and the 1x1-convolution backward {args.precision} (tcgen05), torch GEMMs (SSIM filter of the loss, nn.Linear) TF32, everything else fp32"
                                      if args.precision == "bf16" else "fp32 everywhere"),
-                       "parallelism": f"dp{world}", "cuda_graph": used_graph, "parallel_graph_branches": bool(K.config.parallel_branches), "optimizer": "AdamW(lr 1e-3, wd 0.05, fused)" if train else None,
+                       "parallelism": f"dp{world}", "cuda_graph": used_graph, "parallel_graph_branches": bool(K.config.parallel_branches), "optimizer": ("AdamW(lr 1e-3, wd 0.05), " + ("libkmunet kmu_adamw_step" if args.optimizer == "kmu" else "torch fused")) if train else None,
                        "l2": "activations per step (hundreds of %.0f MB tensors) exceed the 126 MB L2" % (B * 16 * size * size * 4 / 1e6),
                        "grad_allreduce": ((f"bucketed NCCL all-reduce of {nlive * 4 / 1e6:.1f} MB launched from grad-ready hooks, captured inside the step graph "
                                            "(overlaps the rest of backward)" if args.comm == "captured" else
@@ -786,6 +788,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="samples per GPU per step (0 = the workload's default)")
     ap.add_argument("--precision", default=os.environ.get("KMU_KAN_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--optimizer", default="kmu", choices=["kmu", "torch"], help="AdamW update: libkmunet's one-launch kernel or torch's fused one")
     ap.add_argument("--no-kan-microbench", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the eager fp16-autocast run of the unmodified reference on the GPU")
     ap.add_argument("--comm", default="captured", choices=["captured", "split"], help="N > 1: NCCL all-reduce inside the step graph, "

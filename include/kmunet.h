@@ -554,6 +554,34 @@ size_t kmu_pwconv_fused_bwd_workspace_bytes(const kmu_pwconv_desc* d);
 int kmu_pwconv_fused_bwd(const kmu_pwconv_desc* d, const float* x, const float* dy, const float* w, float* dx, float* dw,
                          float* dbias, void* workspace, size_t workspace_bytes, kmu_stream stream);
 
+/* kmu_adamw_step: the optimizer of train_shanghai.py:342,180 -- `optim.AdamW(params, lr, weight_decay)` / `optimizer.step()`
+ * (torch.optim.AdamW semantics: decoupled weight decay, bias-corrected moments, no amsgrad) over every tensor of a parameter group
+ * in one launch.  `entries` and `chunks` are DEVICE tables built by the caller: one entry per tensor (all fp32, contiguous), one
+ * chunk per kmu_adamw_chunk_elems() elements of a tensor, encoded as (entry index << 32) | chunk number within the tensor.
+ * `step` is a device scalar holding the number of updates applied so far; the call uses step + 1 for the bias corrections and
+ * then increments it (so the call can be captured into a CUDA graph).  `lr_dev` (optional) overrides `lr` with a device scalar;
+ * gradients are multiplied by `grad_scale` on the fly (1 / loss-scale, or 1). */
+typedef struct kmu_adamw_entry {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  int64_t n;
+} kmu_adamw_entry;
+
+typedef struct kmu_adamw_args {
+  const kmu_adamw_entry* entries;
+  const int64_t* chunks;
+  int32_t n_entries;
+  int32_t n_chunks;
+  float* step;
+  const float* lr_dev;
+  double lr, beta1, beta2, eps, weight_decay, grad_scale;   /* doubles: 1 - beta2 must not inherit the fp32 rounding of beta2 */
+} kmu_adamw_args;
+
+int32_t kmu_adamw_chunk_elems(void);
+int kmu_adamw_step(const kmu_adamw_args* a, kmu_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,4 +31,7 @@ def __getattr__(name):
             return importlib.import_module(".modules", __name__)
         from . import modules
         return getattr(modules, name)
+    if name == "FusedAdamW":
+        from .optim import FusedAdamW
+        return FusedAdamW
     raise AttributeError(name)

@@ -68,6 +68,12 @@ class DeformDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("B", "C", "H", "W", "Cout")]
 
 
+class AdamWArgs(C.Structure):          # kmu_adamw_args
+    _fields_ = [("entries", C.c_void_p), ("chunks", C.c_void_p), ("n_entries", C.c_int32), ("n_chunks", C.c_int32),
+                ("step", _f32p), ("lr_dev", _f32p)] + \
+               [(n, C.c_double) for n in ("lr", "beta1", "beta2", "eps", "weight_decay", "grad_scale")]
+
+
 class DagemDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("B", "C", "H", "W", "training")] + [("momentum", C.c_float), ("eps", C.c_float)]
 
@@ -162,6 +168,8 @@ SYMBOLS = {
     "kmu_deformconv3x3_fwd": (C.c_int, [C.POINTER(DeformDesc), _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
     "kmu_deformconv3x3_bwd": (C.c_int, [C.POINTER(DeformDesc), _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p,
                                         C.c_size_t, C.c_void_p]),
+    "kmu_adamw_chunk_elems": (C.c_int32, []),
+    "kmu_adamw_step": (C.c_int, [C.POINTER(AdamWArgs), C.c_void_p]),
     "kmu_bnmix_workspace_bytes": (C.c_size_t, [C.POINTER(BnMixDesc)]),
     "kmu_bnmix_fwd": (C.c_int, [C.POINTER(BnMixFwdArgs), C.c_void_p]),
     "kmu_bnmix_bwd": (C.c_int, [C.POINTER(BnMixBwdArgs), C.c_void_p]),

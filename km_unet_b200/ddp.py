@@ -30,8 +30,11 @@ class BucketedGradAllReduce:
       * parameters that never receive a gradient (KM-UNet has 448k of them) must not be passed in.
     """
 
-    def __init__(self, params, bucket_bytes=4 << 20, group=None):
+    def __init__(self, params, bucket_bytes=4 << 20, group=None, grad_views=False):
         self.group = group
+        # grad_views: finish() does not copy the averaged values back; it re-points every `.grad` at its slice of the flat bucket
+        # (no kernel at all).  The next backward produces fresh gradients as usual.
+        self.grad_views = grad_views
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.params = [p for p in params if p.requires_grad]
         self.buckets = []           # list of (params, flat buffer)
@@ -123,7 +126,12 @@ class BucketedGradAllReduce:
             ps, flat = self.buckets[bi]
             if self.world > 1:
                 flat.div_(self.world)
-            torch._foreach_copy_([p.grad.reshape(-1) for p in ps], list(flat.split([p.numel() for p in ps])))
+            pieces = flat.split([p.numel() for p in ps])
+            if self.grad_views:
+                for p, piece in zip(ps, pieces):
+                    p.grad = piece.view_as(p)
+            else:
+                torch._foreach_copy_([p.grad.reshape(-1) for p in ps], list(pieces))
             total += flat.numel() * flat.element_size()
         self.reset()
         return total

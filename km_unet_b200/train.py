@@ -43,7 +43,8 @@ class GraphedTrainStep:
         self.x.copy_(x_example)
         self.t.copy_(t_example)
         self.params = [p for g in optimizer.param_groups for p in g["params"]]
-        self.reducer = BucketedGradAllReduce(self.params, bucket_bytes=bucket_bytes, group=group) if world > 1 else None
+        self.reducer = BucketedGradAllReduce(self.params, bucket_bytes=bucket_bytes, group=group,
+                                             grad_views=comm == "captured") if world > 1 else None
         if self.reducer is not None and comm == "split":
             self.reducer.remove()                  # no hooks: buckets are packed after backward and reduced between two graphs
         # the parameters' AccumulateGrad nodes may predate this object (created on the default stream): harmless here, the

@@ -15,7 +15,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, views=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -24,7 +24,7 @@ def _worker(rank, world, port, out):
     net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
     dead = torch.nn.Parameter(torch.ones(4))           # never used, like the dead KAN twin in StableHybridKANConv
     broadcast_parameters(net)
-    red = BucketedGradAllReduce(list(net.parameters()), bucket_bytes=64)   # tiny buckets -> several of them
+    red = BucketedGradAllReduce(list(net.parameters()), bucket_bytes=64, grad_views=views)   # tiny buckets -> several of them
     assert len(red.buckets) >= 2
     g = torch.Generator().manual_seed(7)
     data = torch.randn(world, 4, 6, generator=g)
@@ -33,6 +33,9 @@ def _worker(rank, world, port, out):
         loss = net(data[rank]).square().mean()
         loss.backward()
         nbytes = red.finish()
+        if views:                                      # .grad now aliases the flat buckets: no copy back
+            flat_ptrs = {f.data_ptr(): f.numel() * 4 for _, f in red.buckets}
+            assert all(any(b <= p.grad.data_ptr() < b + n for b, n in flat_ptrs.items()) for p in net.parameters())
     grads = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
     if rank == 0:
         torch.save({"grads": grads, "state": net.state_dict(), "nbytes": nbytes}, out)
@@ -41,10 +44,14 @@ def _worker(rank, world, port, out):
     assert dead.grad is None
 
 
-def test_bucketed_allreduce_equals_mean_of_per_rank_grads(tmp_path):
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("views", [False, True])
+def test_bucketed_allreduce_equals_mean_of_per_rank_grads(tmp_path, views):
     world = 2
     out = str(tmp_path / "rank0.pt")
-    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), out, views), nprocs=world, join=True)
     got = torch.load(out)
     net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
     net.load_state_dict(got["state"])

@@ -163,6 +163,7 @@ def test_train_step_fp32_class_matches_reference(tag):
 def test_train_step_bench_configuration_graphed_matches_reference_and_eager(tag):
     """bf16 class through GraphedTrainStep (what bench.py times): first replay == the reference's step within 2e-2, and the
     replay == the same step run eagerly."""
+    import km_unet_b200 as K
     from km_unet_b200.loss import HybridLoss
     from km_unet_b200.modules import km_unet as MM
     from km_unet_b200.train import GraphedTrainStep
@@ -207,7 +208,7 @@ def test_train_step_bench_configuration_graphed_matches_reference_and_eager(tag)
         model.load_state_dict(state0)
         for p in model.parameters():
             p.grad = None
-        opt = torch.optim.AdamW(live, lr=1e-3, weight_decay=0.05, fused=True, capturable=True)
+        opt = K.FusedAdamW(live, lr=1e-3, weight_decay=0.05)           # as bench.py builds it (one launch per step, csrc/optim.cu)
         step = GraphedTrainStep(model, crit, opt, x, t, world=1, warmup=3)
         # warm-up must have left no trace: parameters, BatchNorm statistics, optimizer step counters
         for k, v in model.state_dict().items():
@@ -240,6 +241,14 @@ def test_train_step_bench_configuration_graphed_matches_reference_and_eager(tag)
     # the optimizer really stepped inside the graph
     assert all(float(s["step"]) == 1.0 for s in opt.state.values())
     assert any(not torch.equal(p.detach(), state0[k]) for k, p in model.named_parameters() if p.grad is not None)
+    # ... and did what torch.optim.AdamW (train_shanghai.py:342) does with the same gradients
+    named = [(k, p) for k, p in model.named_parameters() if p.grad is not None]
+    twins = [torch.nn.Parameter(state0[k].clone()) for k, _ in named]
+    for q, (_, p) in zip(twins, named):
+        q.grad = p.grad.clone()
+    torch.optim.AdamW(twins, lr=1e-3, weight_decay=0.05).step()
+    for q, (k, p) in zip(twins, named):
+        assert float((p.detach() - q.detach()).abs().max()) <= 1e-6 * max(float(q.detach().abs().max()), 1e-3), k
     # vs the reference
     assert rep["out_err"] <= 2e-2 and rep["loss_err"] <= 2e-2 and rep["running_stat_err"] <= 2e-2, rep
     _assert_grads(rep, e, ref, ref_med, 2e-2, 2.0, k=0)
