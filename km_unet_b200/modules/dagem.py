@@ -10,6 +10,7 @@ import torch.nn as nn
 from torchvision.ops import DeformConv2d
 
 from .. import ops
+from .vim import count_batch
 
 
 class DAGEM(nn.Module):
@@ -47,5 +48,5 @@ class DAGEM(nn.Module):
                              bns[0].momentum, bns[0].eps)
         if self.training:
             for bn in bns:
-                bn.num_batches_tracked += 1
+                count_batch(bn)
         return out

@@ -22,7 +22,7 @@ from .. import config, ops
 from .dagem import DAGEM
 from .dysample import DySample
 from .kan import KANConv2d
-from .vim import EfficientViMBlock, conv1x1, conv_same
+from .vim import EfficientViMBlock, batch_counters, conv1x1, conv_same
 
 
 def group_norm(m, x):
@@ -322,6 +322,10 @@ class KM_UNetV3(nn.Module):
         return [r1, r2, r2]            # the reference feeds e2 twice (KM_UNetV3_SH.py:495)
 
     def forward(self, x):
+        with batch_counters():          # the 65 BatchNorm counters of a training step: one multi-tensor add at the end
+            return self._forward(x)
+
+    def _forward(self, x):
         x = self.conv_f(x)
         e1 = self.lca1(self.enc1(x))
         e2 = self.lca2(self.enc2(e1))

@@ -92,12 +92,49 @@ def conv_same(conv, x):
     return conv(x)
 
 
+_PENDING_COUNTS = None       # list while a whole-model forward collects its BatchNorm counters (batch_counters below)
+
+
+def count_batch(bn):
+    """`bn.num_batches_tracked += 1` as nn.BatchNorm2d.forward does in training -- immediately, or deferred to one multi-tensor
+    add at the end of the enclosing model forward (65 counters per KM_UNetV3 step, each its own 1-thread kernel otherwise)."""
+    if bn.training and bn.num_batches_tracked is not None:
+        if _PENDING_COUNTS is not None:
+            _PENDING_COUNTS.append(bn.num_batches_tracked)
+        else:
+            bn.num_batches_tracked += 1
+
+
+class batch_counters:
+    """Context of one model forward: BatchNorm counters touched inside are incremented together on exit (only if the forward
+    completed).  Nested use joins the outer context."""
+
+    def __enter__(self):
+        global _PENDING_COUNTS
+        self.outer = _PENDING_COUNTS is not None
+        if not self.outer:
+            _PENDING_COUNTS = []
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        global _PENDING_COUNTS
+        if self.outer:
+            return False
+        pending, _PENDING_COUNTS = _PENDING_COUNTS, None
+        if exc_type is None and pending:
+            by_dev = {}
+            for t in pending:
+                by_dev.setdefault(t.device, []).append(t)
+            for ts in by_dev.values():
+                torch._foreach_add_(ts, 1)
+        return False
+
+
 def _bn2d(bn, x, relu=False, res=None, alpha=None):
     """BatchNorm2d module `bn` applied through the fused CUDA op (keeps the module's parameters, buffers and counters)."""
     training = bn.training or bn.running_mean is None
     y = ops.bnmix(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, bn.momentum, bn.eps, relu, res, alpha)
-    if bn.training and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked += 1
+    count_batch(bn)
     return y
 
 
@@ -127,8 +164,7 @@ class ConvLayer2D(_ConvLayer):
             bn = self.norm
             y = ops.dwconv_bnmix(x, self.conv.weight, bn.weight, bn.bias, alpha, bn.running_mean, bn.running_var,
                                  bn.training or bn.running_mean is None, bn.momentum, bn.eps)
-            if bn.training and bn.num_batches_tracked is not None:
-                bn.num_batches_tracked += 1
+            count_batch(bn)
             return y
         x = self.conv_out(x)
         if fusable:
