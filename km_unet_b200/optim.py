@@ -15,6 +15,11 @@ from . import _lib
 from ._lib import AdamWArgs, check, stream_ptr
 
 
+def chunk_codes(numels, chunk):
+    """The chunk list kmu_adamw_step walks: one int64 per `chunk` elements of every tensor, (tensor index << 32) | chunk number."""
+    return np.concatenate([(np.int64(i) << 32) | np.arange((int(n) + chunk - 1) // chunk, dtype=np.int64) for i, n in enumerate(numels)])
+
+
 class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
         if not (0.0 <= betas[0] < 1.0 and 0.0 <= betas[1] < 1.0):
@@ -68,7 +73,7 @@ class FusedAdamW(torch.optim.Optimizer):
             return tab
         chunk = int(_lib.lib().kmu_adamw_chunk_elems())
         ent = np.array(key, dtype=np.int64)                                         # (n, 5): p, g, m, v, n  == kmu_adamw_entry
-        codes = np.concatenate([(np.int64(i) << 32) | np.arange((k[4] + chunk - 1) // chunk, dtype=np.int64) for i, k in enumerate(key)])
+        codes = chunk_codes([k[4] for k in key], chunk)
         words = torch.from_numpy(np.concatenate([ent.reshape(-1), codes]))
         if capturing:
             # page-locked memory cannot be allocated while a stream is capturing: take the buffer the last eager step set aside.  The
