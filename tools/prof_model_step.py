@@ -24,7 +24,7 @@ data = torch.rand(B, 25, 128, 128, generator=g).cuda()
 x, t = data[:, :5].contiguous(), data[:, 5:].contiguous()
 crit(m(x[:2]), t[:2]).backward()
 live = [p for p in m.parameters() if p.grad is not None]
-opt = torch.optim.AdamW(live, lr=1e-3, weight_decay=0.05, fused=True)
+opt = K.FusedAdamW(live, lr=1e-3, weight_decay=0.05)          # as bench.py
 def step():
     opt.zero_grad(set_to_none=True)
     loss = crit(m(x), t)
