@@ -22,6 +22,15 @@ struct BnDims {
   long long len;   // elements per CTA (multiple of 4 when HW % 4 == 0)
 };
 
+// KMU_BN_ORDER=0 restores the plain traversal (channel-major statistics, ascending applies) for A/B timing
+static int bn_order() {
+  static const int v = [] {
+    const char* e = getenv("KMU_BN_ORDER");
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  return v;
+}
+
 static BnDims bn_dims(const kmu_bnmix_desc& s) {
   BnDims d;
   d.B = s.B; d.C = s.C; d.HW = s.HW;
@@ -60,8 +69,13 @@ __device__ __forceinline__ size_t chan_off(long long v, int c, int C, int HW) {
 //      The shift keeps var = E[(x-k)^2] - E[x-k]^2 free of the catastrophic cancellation of E[x^2] - mean^2 when |mean| >> std
 //      (k is a sample of the channel, so |E[x-k]| is a few std at most); nn.BatchNorm's Welford has no such problem either.
 //      grid (nsplit, C), 256 threads
-__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, float* __restrict__ part, BnDims d) {
-  const int c = blockIdx.y, s = blockIdx.x;
+//      Traversal order (`order` != 0, default): the passes over one tensor are laid out so that each starts where the previous one
+//      ended and finds the tail of that pass in L2 (the FFN's hidden tensors are 134 MB against 126 MB of L2: re-reading them from the
+//      start evicts every line just before it is needed).  The producing convolution writes batch-major ascending; the forward statistics
+//      walk the splits DESCENDING with the split index slowest (all channels of the last samples first); the forward apply walks planes
+//      ascending; the backward statistics ascending with the split index slowest; the backward apply descending.
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, float* __restrict__ part, BnDims d, int order) {
+  const int c = order ? blockIdx.x : blockIdx.y, s = order ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.x;
   const long long v0 = (long long)s * d.len;
   long long v1 = v0 + d.len;
   if (v1 > d.per) v1 = d.per;
@@ -238,8 +252,8 @@ __global__ void __launch_bounds__(256) bn_apply_plane_kernel(const float* __rest
 __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                            const float2* __restrict__ stat, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, const float* __restrict__ res,
-                                                           float* __restrict__ part, BnDims d, int relu) {
-  const int c = blockIdx.y, s = blockIdx.x;
+                                                           float* __restrict__ part, BnDims d, int relu, int order) {
+  const int c = order ? blockIdx.x : blockIdx.y, s = order ? blockIdx.y : blockIdx.x;
   const long long v0 = (long long)s * d.len;
   long long v1 = v0 + d.len;
   if (v1 > d.per) v1 = d.per;
@@ -354,10 +368,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_plane_kernel(const float* __
                                                                  const float* __restrict__ alpha, float* __restrict__ dx,
                                                                  float* __restrict__ dres, float* __restrict__ dgamma,
                                                                  float* __restrict__ dbeta, float* __restrict__ dalpha, BnDims d, int training,
-                                                                 int relu) {
+                                                                 int relu, int order) {
   // the backward finalize folded in (see bn_apply_plane_kernel): every CTA reduces its channel's three partial sums in double
   __shared__ float2 bs_s;
-  const int plane = blockIdx.y, c = plane % d.C, HW = d.HW;
+  const int plane = order ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y, c = plane % d.C, HW = d.HW;
+  const int chunk = order ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
   const float a = alpha ? 1.f / (1.f + expf(-alpha[c])) : 1.f, b = 1.f - a;
   if (threadIdx.x < 32) {
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
@@ -376,7 +391,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_plane_kernel(const float* __
     if (threadIdx.x == 0) {
       const double ad = alpha ? 1.0 / (1.0 + exp(-(double)alpha[c])) : 1.0;
       bs_s = training ? make_float2((float)(ad * s0 / (double)d.per), (float)(ad * s1 / (double)d.per)) : make_float2(0.f, 0.f);
-      if (plane == c && blockIdx.x == 0) {
+      if (plane == c && chunk == 0) {
         dbeta[c] = (float)(ad * s0);
         dgamma[c] = (float)(ad * s1);
         if (dalpha) dalpha[c] = (float)(s2 * ad * (1.0 - ad));
@@ -394,7 +409,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_plane_kernel(const float* __
   const int n4 = HW >> 2;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int i = blockIdx.x * 1024 + k * 256 + threadIdx.x;
+    const int i = chunk * 1024 + k * 256 + threadIdx.x;
     if (i < n4) {
       const float4 xv = *reinterpret_cast<const float4*>(x + base + 4 * (size_t)i);
       const float4 g = *reinterpret_cast<const float4*>(dy + base + 4 * (size_t)i);
@@ -812,7 +827,8 @@ int kmu_bnmix_fwd(const kmu_bnmix_fwd_args* a, kmu_stream stream) {
   float* part = (float*)a->workspace;
   float2* stat = (float2*)a->stat;
   if (a->d.training) {
-    bn_stats_kernel<<<dim3(d.nsplit, d.C), 256, 0, st>>>(a->x, part, d);
+    const int order = bn_order();
+    bn_stats_kernel<<<order ? dim3(d.C, d.nsplit) : dim3(d.nsplit, d.C), 256, 0, st>>>(a->x, part, d, order);
     KMU_LAUNCH_CHECK("bn_stats");
   }
   const long long total = (long long)d.B * d.C * d.HW;
@@ -850,7 +866,9 @@ int kmu_bnmix_bwd(const kmu_bnmix_bwd_args* a, kmu_stream stream) {
   const float2* stat = (const float2*)a->stat;
   const float* res = a->d.mix ? a->res : nullptr;
   const float* alpha = a->d.mix ? a->alpha : nullptr;
-  bn_bwd_stats_kernel<<<dim3(d.nsplit, d.C), 256, 0, st>>>(a->x, a->dy, stat, a->weight, a->bias, res, part, d, a->d.relu);
+  const int order = bn_order();
+  bn_bwd_stats_kernel<<<order ? dim3(d.C, d.nsplit) : dim3(d.nsplit, d.C), 256, 0, st>>>(a->x, a->dy, stat, a->weight, a->bias, res, part, d,
+                                                                                          a->d.relu, order);
   KMU_LAUNCH_CHECK("bn_bwd_stats");
   const long long total = (long long)d.B * d.C * d.HW;
   float* dres = a->d.mix ? a->d_res : nullptr;
@@ -862,7 +880,8 @@ int kmu_bnmix_bwd(const kmu_bnmix_bwd_args* a, kmu_stream stream) {
   if (plane_path)
     bn_bwd_apply_plane_kernel<<<dim3(cdiv(d.HW, 4096), d.B * d.C), 256, 0, st>>>(a->x, a->dy, stat, part, a->weight, a->bias, alpha, a->dx,
                                                                                  dres, a->d_weight, a->d_bias,
-                                                                                 a->d.mix ? a->d_alpha : nullptr, d, a->d.training, a->d.relu);
+                                                                                 a->d.mix ? a->d_alpha : nullptr, d, a->d.training, a->d.relu,
+                                                                                 order);
   else if ((d.HW & 3) == 0)
     bn_bwd_apply_kernel<true><<<cdiv(total / 4, 256), 256, 0, st>>>(a->x, a->dy, stat, bstat, a->weight, a->bias, alpha, a->dx, dres, d.C,
                                                                     d.HW, total, a->d.relu);
