@@ -3,7 +3,9 @@
 km_unet_b200.enable_dropin() in front, so their `from convKAN.KANConv2Dlayers import *`, `from vim_block_init.efficient_vim_init
 import EfficientViMBlock`, `from DAGEM_md import DAGEM`, `from DySample_md import DySample` resolve to the CUDA-backed modules
 while every other line of the model (StableHybridKANConv, EnhancedViMBlock, DirectionViM, TripleNorm, MultiScaleFusion, IWP with
-its numpy matrices, ...) is the reference's own torch code on the GPU.  fp16 autocast is neutralised on both sides (section 8c).
+its numpy matrices, ...) is the reference's own torch code on the GPU.  fp16 autocast is neutralised on both sides (section 8c) -- except
+in the last test, which runs the file exactly as shipped: its `@autocast()` forwards (KM_UNetV3_SH.py:71,306,327,465) inside the fp16
+autocast + GradScaler step of train_shanghai.py:159-181.
 
 Checked against (i) the fp64 fixture of the same reference file on its own operators (tests/golden/km_unetv3_*_train_128.npz)
 and (ii) the same reference file on its own operators run live on the same GPU in fp32.  Also K5: the reference's
@@ -115,3 +117,73 @@ def test_k5_reference_stable_hybrid_kanconv_on_dropin_kanconv2d(cin, cout):
     for k, want in live.items():
         assert got[k].grad is not None, k
         assert rel_err(got[k].grad, want) <= 1e-4, k
+
+
+def _amp_step(cls, classes, masks, loss_fn):
+    """One iteration of train_shanghai.py:159-181: autocast forward + loss, scaled backward, scaler.step(AdamW), scaler.update()."""
+    torch.manual_seed(TF.SEED_WEIGHTS)
+    model = cls(num_classes=classes)
+    TF.perturb_(model)
+    model = model.cuda().train()
+    before = {k: p.detach().clone() for k, p in model.named_parameters()}
+    x, t = TF.make_batch(classes)
+    x, t = x.cuda(), t.cuda()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.05)          # train_shanghai.py:342
+    scaler = torch.amp.GradScaler("cuda")
+    skipped = 0
+    for _ in range(6):                  # GradScaler starts at 65536: it may skip (and halve) a few times before the first real step
+        scale = scaler.get_scale()
+        with TF.DropPathReplayer(shims._DropPath, masks):
+            opt.zero_grad()
+            with torch.autocast("cuda", dtype=torch.float16):
+                out = model(x)
+                loss = loss_fn(out, t)
+            scaler.scale(loss).backward()
+            scaler.step(opt)                                                        # unscales .grad in place, skips on inf / nan
+            scaler.update()
+        if scaler.get_scale() >= scale:
+            break
+        skipped += 1
+    torch.cuda.synchronize()
+    moved = sum(int(not torch.equal(p.detach(), before[k])) for k, p in model.named_parameters())
+    return model, out.detach().float(), loss.detach().float(), moved, skipped
+
+
+@pytest.mark.parametrize("tag", ["sh", "laps"])
+def test_reference_model_file_as_shipped_fp16_autocast_and_gradscaler_on_the_dropin(tag):
+    """What a user of the reference gets after switching: nothing neutralised.  The drop-in operators compute in fp32 / bf16-tcgen05
+    inside the autocast region (custom_fwd casts their inputs); everything else is the reference's fp16 torch code.  Compared with
+    the same file on its own operators under the same autocast (fp16 everywhere) and with the fp64 fixture."""
+    from oracle import loss as OL
+    variant, classes = TF.VARIANTS[tag]
+    z = np.load(os.path.join(GOLDEN, f"km_unetv3_{tag}_train_128.npz"))
+    masks = list(z["masks"])
+    D = ref_loader.load_models(dropin=True, autocast=True)
+    R = ref_loader.load_models(dropin=False, autocast=True)
+    dcls = D.KM_UNetV3_SH if variant == "SH" else D.KM_UNetV3_LAPS
+    rcls = R.KM_UNetV3_SH if variant == "SH" else R.KM_UNetV3_LAPS
+    ours, out_o, loss_o, moved_o, skipped_o = _amp_step(dcls, classes, masks, OL.hybrid_loss)
+    ref, out_r, loss_r, moved_r, skipped_r = _amp_step(rcls, classes, masks, OL.hybrid_loss)
+    assert out_o.shape == out_r.shape and bool(torch.isfinite(out_o).all()) and bool(torch.isfinite(loss_o))
+    # a real step was taken (GradScaler found no inf / nan after at most as many halvings as the reference's own operators need + 1)
+    # and it moved every live parameter
+    live = [k for k, p in ours.named_parameters() if p.grad is not None and bool(p.grad.any())]
+    assert skipped_o <= skipped_r + 1 and skipped_o < 6 and moved_o >= 0.98 * len(live), (skipped_o, skipped_r, moved_o, moved_r, len(live))
+    want = torch.from_numpy(z["out0"].astype(np.float64))
+    g_o = {k: p.grad.float() for k, p in ours.named_parameters() if p.grad is not None}
+    g_r = {k: p.grad.float() for k, p in ref.named_parameters() if p.grad is not None}
+    assert all(bool(torch.isfinite(v).all()) for v in g_o.values())
+    rep = {"dropin_amp_vs_fp64": {"out": rel_err(out_o, want), "loss": abs(loss_o.item() - float(z["loss"])) / float(z["loss"]),
+                                  "grad_l2": TF.grad_global_l2(g_o, z)},
+           "reference_amp_vs_fp64": {"out": rel_err(out_r, want), "loss": abs(loss_r.item() - float(z["loss"])) / float(z["loss"]),
+                                     "grad_l2": TF.grad_global_l2(g_r, z)},
+           "dropin_amp_vs_reference_amp": {"out": rel_err(out_o, out_r), "loss": abs(loss_o.item() - loss_r.item()) / abs(loss_r.item())},
+           "gradscaler_skips": {"dropin": skipped_o, "reference": skipped_r}}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", f"parity_{tag}_reference_dropin_amp.json"), "w") as f:
+        json.dump(rep, f, indent=1)
+    d, r = rep["dropin_amp_vs_fp64"], rep["reference_amp_vs_fp64"]
+    # fp16 autocast is the reference's own precision class here: the drop-in run (fp32 operators inside fp16 glue) must be at least as
+    # close to fp64 as the reference's fp16 run is, up to the 2e-2 class gate
+    assert d["out"] <= max(2e-2, 2 * r["out"]) and d["loss"] <= max(2e-2, 2 * r["loss"]), rep
+    assert d["grad_l2"] <= max(5e-2, 2 * r["grad_l2"]), rep
