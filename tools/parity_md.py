@@ -47,3 +47,13 @@ print("| parameter | err | norm err | ref32 err |")
 print("|---|---|---|---|")
 for w in r["worst"][:8]:
     print(f"| `{w['param']}` | {w['err']:.2e} | {w['norm_err']:.2e} | {w['ref32_err']:.1e} |")
+print("\nThe reference's model file AS SHIPPED (its `@autocast()` forwards active) inside the fp16 autocast + GradScaler + AdamW iteration of "
+      "`train_shanghai.py:159-181`, on the drop-in operators and on its own; both against the fp64 fixture:\n")
+print("| model | run | output | loss | grad global L2 | GradScaler skips before the first step |")
+print("|---|---|---|---|---|---|")
+for tag in ("sh", "laps"):
+    r = load(f"parity_{tag}_reference_dropin_amp.json")
+    for k, label, who in (("dropin_amp_vs_fp64", "reference file + drop-in operators, fp16 autocast", "dropin"),
+                          ("reference_amp_vs_fp64", "reference file + its own operators, fp16 autocast", "reference")):
+        d = r[k]
+        print(f"| {tag.upper()} | {label} | {d['out']:.2e} | {d['loss']:.2e} | {d['grad_l2']:.2e} | {r['gradscaler_skips'][who]} |")
