@@ -22,7 +22,8 @@ that bounds it (`roofline.kan` = the KANConv2d microbench fractions of the tenso
 reference model (byte-for-byte mirror oracle/_ref/, recipe oracle/make_ref.py; kind "reference") on the box's host cores,
 bounded sample -- or, when the mirror is absent, the CPU oracle port (oracle/model.py; kind "port");
 `gpu_eager_reference` = the same unmodified reference run eagerly on the B200 under fp16 autocast + GradScaler exactly as
-train_shanghai.py:159-181 does, at the largest batch that fits.
+train_shanghai.py:159-181 does, at the largest batch that fits; `gpu_eager_reference_dropin` = that same unmodified model file and
+iteration with its operator imports resolved to the libkmunet drop-in modules (what switching alone buys, no graph, no mirror).
 `--impl reference` times the reference's CPU path alone; that arm never imports km_unet_b200.
 """
 import argparse
@@ -249,17 +250,18 @@ def reference_mirror_available():
     return ref_loader.available()
 
 
-def reference_model_step_factory(workload, batch, device="cpu", fp16_autocast=False):
+def reference_model_step_factory(workload, batch, device="cpu", fp16_autocast=False, dropin=False):
     """The UNMODIFIED reference (oracle/_ref mirror or /root/reference; imported through oracle/ref_loader.py with the timm /
     fvcore / pywt stand-ins of oracle/shims.py) running train_shanghai.py's train() body (:159-181): zero_grad, forward, loss,
     backward, AdamW(lr 1e-3, wd 0.05) (:342).  HybridLoss = oracle/loss.py (train_shanghai.py:298-326; torchmetrics is absent).
-    Nothing of km_unet_b200 is imported."""
+    Nothing of km_unet_b200 is imported -- unless dropin=True: then the same unmodified model file resolves its operator imports to
+    the drop-in modules (km_unet_b200.enable_dropin()), which is what a user of the reference gets by switching and nothing else."""
     import warnings
     import torch
     from oracle import loss as OL
     from oracle import ref_loader
     _, _, variant, classes, fin, size, _, train = WORKLOADS[workload]
-    R = ref_loader.load_models(dropin=False, autocast=True)            # decorators as shipped (inert on CPU tensors)
+    R = ref_loader.load_models(dropin=dropin, autocast=True)           # decorators as shipped (inert on CPU tensors)
     torch.manual_seed(1234)
     model = (R.KM_UNetV3_SH if variant == "SH" else R.KM_UNetV3_LAPS)(num_classes=classes).to(device)
     model.train(train)
@@ -334,7 +336,7 @@ def cpu_sample_text(steps, warmup, sb, kind):
     return f"{steps} steps x {sb} sample(s) of the workload after {warmup} warm-up, {what}"
 
 
-def gpu_eager_reference(workload, dev, steps=3, warmup=2):
+def gpu_eager_reference(workload, dev, steps=3, warmup=2, dropin=False):
     """The unmodified reference on the B200, eager, fp16 autocast + GradScaler as train_shanghai.py:159-181 -- 'the meaningful GPU
     baseline' of SURVEY section 8d.  Largest batch of 32 / 16 / 8 / 4 that fits (its B-spline temporaries are GBs each)."""
     import torch
@@ -344,7 +346,7 @@ def gpu_eager_reference(workload, dev, steps=3, warmup=2):
     last = None
     for B in (32, 16, 8, 4):
         try:
-            step = reference_model_step_factory(workload, B, device=dev, fp16_autocast=WORKLOADS[workload][7])
+            step = reference_model_step_factory(workload, B, device=dev, fp16_autocast=WORKLOADS[workload][7], dropin=dropin)
             for _ in range(warmup):
                 step()
             torch.cuda.synchronize()
@@ -361,7 +363,9 @@ def gpu_eager_reference(workload, dev, steps=3, warmup=2):
                                   "fp16 autocast from the model's own @autocast() decorators (KM_UNetV3_SH.py:465), no_grad, cudnn.benchmark"),
                     "mode": "eager",
                     "loss": float(res) if not isinstance(res, float) else res, "peak_mem_gib": peak,
-                    "what": "unmodified reference model (oracle/_ref) + oracle/loss.py, stock PyTorch kernels, 1 x B200"}
+                    "what": ("unmodified reference model file (oracle/_ref) on the libkmunet drop-in operators (enable_dropin()), the rest stock "
+                             "PyTorch, + oracle/loss.py, 1 x B200" if dropin else
+                             "unmodified reference model (oracle/_ref) + oracle/loss.py, stock PyTorch kernels, 1 x B200")}
         except torch.cuda.OutOfMemoryError as e:
             last = str(e).split("\n")[0]
             step = None
@@ -743,12 +747,14 @@ def run_model(h, args):
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": cpu_sample_text(2, 1, sb, kind)}
     if graphed is not None:
         graphed.close()                # a graph holding NCCL kernels must be gone before destroy_process_group()
-    gpu_ref = None
+    gpu_ref = gpu_ref_dropin = None
     if rank == 0 and world == 1 and not args.no_gpu_reference:
         graphed = None
         torch.cuda.empty_cache()
         torch.cuda.reset_peak_memory_stats(dev)
         gpu_ref = gpu_eager_reference(args.workload, dev)
+        torch.cuda.reset_peak_memory_stats(dev)
+        gpu_ref_dropin = gpu_eager_reference(args.workload, dev, dropin=True)
     if kan is not None:
         roofline["kan"] = {k: {"ms": v["ms"], "achieved": v["achieved"], "frac": v["frac"]} for k, v in kan["families"].items()}
         roofline["kan"].update({"unit": "TFLOP/s", "peak": kan["peak"], "peak_source": kan["peak_source"], "workload": kan["workload"],
@@ -772,6 +778,7 @@ def run_model(h, args):
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches), "loss_after_timed_steps": last_loss, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "kan_microbench": kan,
             "gpu_eager_reference": gpu_ref,
+            "gpu_eager_reference_dropin": gpu_ref_dropin,
         }
         if comm is not None:
             line["comm"] = comm
