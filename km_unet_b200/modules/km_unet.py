@@ -32,6 +32,13 @@ def group_norm(m, x):
     return m(x)
 
 
+def global_mean(x):
+    """Mean over (H, W) of (B,C,H,W) -> (B,C), written as sum * (1 / HW): autograd's backward of `sum` is an expanded VIEW of
+    the pooled gradient, whereas the backward of `mean` materialises a full-size tensor (one extra write + read of the feature
+    map per call; 28 such poolings per KM_UNetV3 training step)."""
+    return x.sum(dim=(2, 3)) * (1.0 / (x.shape[2] * x.shape[3]))
+
+
 def _run(seq, x):
     """nn.Sequential forward with the plain convolutions / GroupNorms routed through the CUDA kernels where they apply."""
     for m in seq:
@@ -52,11 +59,12 @@ def _side_streams(device, n, level):
     return have[:n]
 
 
-def parallel(fns, inputs, device):
+def parallel(fns, inputs, device, enabled=True):
     """Run independent callables concurrently: fns[0] on the current stream, the others on side streams (fork after `inputs` are
     ready, join before anyone consumes the results).  Inside a CUDA-graph capture these become parallel branches of the graph; the
-    backward nodes run on the streams their forward ran on.  Falls back to a plain loop on CPU / when config.parallel_branches is off."""
-    if not (device.type == "cuda" and config.parallel_branches) or len(fns) < 2:
+    backward nodes run on the streams their forward ran on.  Falls back to a plain loop on CPU / when config.parallel_branches
+    (or the call site's own `enabled` switch) is off."""
+    if not (device.type == "cuda" and config.parallel_branches and enabled) or len(fns) < 2:
         return [f() for f in fns]
     cur = torch.cuda.current_stream(device)
     outs = [None] * len(fns)
@@ -132,8 +140,9 @@ class DirectionAttention(nn.Module):
 
     def forward(self, x):
         # the three pooling modes of the reference (mean over W then H, over H then W, or both) are the same global mean
-        weight = self.fc(x.mean(dim=(2, 3)))
-        attn = ops.qkv_gate(conv1x1(x, self.qkv.weight, self.qkv.bias))          # sigmoid(q k) v
+        # the squeeze-excite chain (a pooling + four tiny kernels) is independent of the q k v product until the last kernel
+        attn, weight = parallel([lambda: ops.qkv_gate(conv1x1(x, self.qkv.weight, self.qkv.bias)),    # sigmoid(q k) v
+                                 lambda: self.fc(global_mean(x))], [x], x.device, config.parallel_extra)
         return ops.dwconv3x3(attn, self.conv.weight, self.conv.bias, scale=weight)   # conv(attn) * weight[:, :, None, None]
 
 
@@ -188,7 +197,8 @@ class EnhancedViMBlock(nn.Module):
     def forward(self, x):
         # the three direction branches are independent until the fusion gate
         feats = parallel([lambda: self.height_block(x), lambda: self.width_block(x), lambda: self.channel_block(x)], [x], x.device)
-        g = self.fusion_gate(torch.cat(feats, dim=1))
+        # fusion_gate[0] is a global average pool: pool the three branches separately instead of concatenating the feature maps
+        g = _run(self.fusion_gate[1:], torch.cat([global_mean(f) for f in feats], dim=1)[:, :, None, None])
         if ops.combine3_supported(x):
             # x + DropPath(g0 f0 + g1 f1 + g2 f2) in one pass: the per-sample DropPath factor is folded into the gate weights
             coef = g.reshape(g.shape[0], 3)
@@ -198,7 +208,11 @@ class EnhancedViMBlock(nn.Module):
         else:
             x = x + self.drop_path(g[:, 0:1] * feats[0] + g[:, 1:2] * feats[1] + g[:, 2:3] * feats[2])
         h = F.gelu(conv1x1(self.norm(x), self.ffn[0].weight, self.ffn[0].bias))
-        return x + self.drop_path(conv1x1(h, self.ffn[2].weight, self.ffn[2].bias))
+        y = conv1x1(h, self.ffn[2].weight, self.ffn[2].bias)
+        if isinstance(self.drop_path, DropPath) and self.training and self.drop_path.drop_prob > 0.0:
+            # x + DropPath(y) in one pass: the per-sample factor (same draw as DropPath(y)) as the multiplier of an addcmul
+            return torch.addcmul(x, y, self.drop_path(x.new_ones((x.shape[0], 1, 1, 1))))
+        return x + y
 
 
 class ChannelAttention(nn.Module):
@@ -209,7 +223,7 @@ class ChannelAttention(nn.Module):
                                 nn.Sigmoid())
 
     def forward(self, x):
-        return x * self.fc(x.mean(dim=(2, 3)))[:, :, None, None]
+        return x * self.fc(global_mean(x))[:, :, None, None]
 
 
 class MultiScaleFusion(nn.Module):
@@ -232,9 +246,9 @@ class LocalContrastAttention(nn.Module):
         self.fc = nn.Sequential(nn.Linear(in_channels // reduction_ratio, 64), nn.ReLU(), nn.Linear(64, in_channels), nn.Sigmoid())
 
     def forward(self, x):
-        avg = x.mean(dim=(2, 3))
+        avg = global_mean(x)
         g = self.fc(avg.view(avg.size(0), -1, self.reduction_ratio).mean(-1))[:, :, None, None]
-        return x * (1 - g) + g
+        return torch.addcmul(g, x, 1 - g)           # x (1 - g) + g in one pass
 
 
 class _NoParams(nn.Module):

@@ -238,12 +238,15 @@ class EfficientViMBlock(nn.Module):
     def forward(self, x):
         # x <- (1 - sigmoid(alpha_i)) x + sigmoid(alpha_i) f_i(x): the mix of the three conv branches is the epilogue of
         # their BatchNorm kernel; the mixer's is one lerp
-        x = self.dwconv1(x, res=x, alpha=self.alpha[0])
+        # one unbind instead of four selects: its backward is ONE stack of the four row gradients (a select's backward is a
+        # zero-fill + a copy, and the four results are then summed: 11 tiny launches per block and step)
+        a0, a1, a2, a3 = self.alpha.unbind(0)
+        x = self.dwconv1(x, res=x, alpha=a0)
         mixed, _ = self.mixer(self.norm(x.flatten(2)))
         from .. import config
         if config.fused_lerp and ops.lerpmix_supported(x):
-            x = ops.lerpmix(x, mixed, self.alpha[1])
+            x = ops.lerpmix(x, mixed, a1)
         else:
-            x = torch.lerp(x, mixed, torch.sigmoid(self.alpha[1]).view(1, -1, 1, 1))
-        x = self.dwconv2(x, res=x, alpha=self.alpha[2])
-        return self.ffn(x, res=x, alpha=self.alpha[3])
+            x = torch.lerp(x, mixed, torch.sigmoid(a1).view(1, -1, 1, 1))
+        x = self.dwconv2(x, res=x, alpha=a2)
+        return self.ffn(x, res=x, alpha=a3)
