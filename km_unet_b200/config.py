@@ -33,5 +33,3 @@ fused_lerp = os.environ.get("KMU_FUSED_LERP", "1") == "1"
 # inside the captured step graph they become parallel branches, so the many small latency-bound kernels of one branch fill the
 # drain / fill bubbles of the others (the backward nodes run on the streams their forward ran on)
 parallel_branches = os.environ.get("KMU_PARALLEL_BRANCHES", "1") == "1"
-# second-level forks inside a direction branch (DirectionAttention's squeeze-excite chain beside its q k v product)
-parallel_extra = os.environ.get("KMU_PARALLEL_EXTRA", "0") == "1"

@@ -59,12 +59,11 @@ def _side_streams(device, n, level):
     return have[:n]
 
 
-def parallel(fns, inputs, device, enabled=True):
+def parallel(fns, inputs, device):
     """Run independent callables concurrently: fns[0] on the current stream, the others on side streams (fork after `inputs` are
     ready, join before anyone consumes the results).  Inside a CUDA-graph capture these become parallel branches of the graph; the
-    backward nodes run on the streams their forward ran on.  Falls back to a plain loop on CPU / when config.parallel_branches
-    (or the call site's own `enabled` switch) is off."""
-    if not (device.type == "cuda" and config.parallel_branches and enabled) or len(fns) < 2:
+    backward nodes run on the streams their forward ran on.  Falls back to a plain loop on CPU / when config.parallel_branches is off."""
+    if not (device.type == "cuda" and config.parallel_branches) or len(fns) < 2:
         return [f() for f in fns]
     cur = torch.cuda.current_stream(device)
     outs = [None] * len(fns)
@@ -140,9 +139,8 @@ class DirectionAttention(nn.Module):
 
     def forward(self, x):
         # the three pooling modes of the reference (mean over W then H, over H then W, or both) are the same global mean
-        # the squeeze-excite chain (a pooling + four tiny kernels) is independent of the q k v product until the last kernel
-        attn, weight = parallel([lambda: ops.qkv_gate(conv1x1(x, self.qkv.weight, self.qkv.bias)),    # sigmoid(q k) v
-                                 lambda: self.fc(global_mean(x))], [x], x.device, config.parallel_extra)
+        weight = self.fc(global_mean(x))
+        attn = ops.qkv_gate(conv1x1(x, self.qkv.weight, self.qkv.bias))          # sigmoid(q k) v
         return ops.dwconv3x3(attn, self.conv.weight, self.conv.bias, scale=weight)   # conv(attn) * weight[:, :, None, None]
 
 
