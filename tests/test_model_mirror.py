@@ -163,3 +163,31 @@ def test_hybrid_loss_ssim_properties():
     p = b.clone().requires_grad_(True)
     loss(p, a).backward()
     assert torch.isfinite(p.grad).all()
+
+
+def test_global_mean_gradient_is_an_expanded_view():
+    """The pooled gradient must reach autograd's accumulation as a stride-0 view (what `sum` gives), not as a materialised
+    full-size tensor (what `mean` gives): that is the point of km_unet.global_mean."""
+    from km_unet_b200.modules.km_unet import global_mean
+    x = torch.randn(2, 3, 4, 6, dtype=torch.float64, requires_grad=True)
+    y = global_mean(x)
+    assert rel_err(y, x.mean(dim=(2, 3))) < 1e-14
+    g, = torch.autograd.grad(y.sum(), x)
+    assert g.stride()[2:] == (0, 0)
+    assert rel_err(g, torch.full_like(x, 1.0 / 24)) < 1e-14
+
+
+def test_ffn_residual_addcmul_draws_the_same_droppath_mask():
+    """EnhancedViMBlock folds `x + DropPath(y)` into one addcmul whose multiplier is DropPath applied to ones: same RNG consumption
+    (B bernoulli draws) and the same per-sample factor as timm's DropPath(y)."""
+    from km_unet_b200.modules.km_unet import DropPath
+    dp = DropPath(0.3).train()
+    x, y = torch.randn(5, 2, 3, 3), torch.randn(5, 2, 3, 3)
+    torch.manual_seed(3)
+    want = x + dp(y)
+    after_want = torch.rand(1)
+    torch.manual_seed(3)
+    got = torch.addcmul(x, y, dp(x.new_ones((5, 1, 1, 1))))
+    after_got = torch.rand(1)
+    assert torch.equal(after_want, after_got)            # the generator advanced by the same amount
+    assert rel_err(got, want) < 1e-6
