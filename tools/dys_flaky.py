@@ -1,3 +1,5 @@
+"""Debug aid: repeat the 128x128 DySample backward on the GPU and list where dX / dW differ from the fp64 oracle between runs
+(how the derivative jumps at integer sample coordinates were told apart from a real defect; see tools/dys_flip_check.py)."""
 import sys
 import torch
 sys.path.insert(0, ".")

@@ -1,3 +1,4 @@
+"""ncu driver: forward + backward of the 1x3 / 3x1 projections (ops.smallconv) at the model's shapes: python tools/prof_smallconv.py"""
 import sys
 import torch
 sys.path.insert(0, ".")

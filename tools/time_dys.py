@@ -1,3 +1,4 @@
+"""Device time of DySample forward / backward at 16..128 px (CUDA events around the C-ABI calls): python tools/time_dys.py"""
 import sys
 import torch
 sys.path.insert(0, ".")

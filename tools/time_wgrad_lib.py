@@ -1,3 +1,4 @@
+"""Library reference point: cuDNN's weight gradient of the 1x3 / 3x1 convolutions at the model's shapes (what sc3_wgrad_strip_kernel replaced)."""
 import torch
 torch.backends.cudnn.benchmark = True
 for (C, S, kh, kw) in [(16, 128, 3, 1), (16, 128, 1, 3), (32, 64, 3, 1), (64, 32, 1, 3)]:
