@@ -98,3 +98,27 @@ def test_second_backward_before_finish_raises_and_no_sync_accumulates():
     lin(x).sum().backward()
     red.finish()
     assert torch.allclose(lin.weight.grad, torch.ones(2, 3))
+
+
+def test_bucket_with_a_missing_gradient_is_reduced_by_finish():
+    """A parameter that received no gradient this step (same set on every rank, per the contract): finish() zero-fills it and reduces
+    the bucket; with grad_views the gradients afterwards alias the flat bucket."""
+    from km_unet_b200.ddp import BucketedGradAllReduce
+    a, b = torch.nn.Linear(3, 2), torch.nn.Linear(3, 2)
+    params = list(a.parameters()) + list(b.parameters())
+    red = BucketedGradAllReduce(params, bucket_bytes=1 << 20, grad_views=True)       # one bucket holding all four tensors
+    a(torch.ones(1, 3)).sum().backward()                                             # b gets no gradient
+    assert red._launched == [False]
+    nbytes = red.finish()
+    assert nbytes == 4 * sum(p.numel() for p in params)
+    assert torch.equal(a.weight.grad, torch.ones(2, 3)) and torch.equal(b.weight.grad, torch.zeros(2, 3))
+    flat = red.buckets[0][1]
+    for p in params:                                                                 # views of the flat buffer, no copy back
+        assert p.grad.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr()
+    # next step: fresh gradients accumulate into the views in place (zero_grad(set_to_none=False)) and the bucket launches from the hooks
+    for p in params:
+        p.grad.zero_()
+    (a(torch.ones(1, 3)).sum() + b(torch.ones(1, 3)).sum()).backward()
+    assert red._launched == [True]
+    red.finish()
+    assert torch.equal(b.weight.grad, torch.ones(2, 3))
