@@ -38,3 +38,16 @@ def test_step_on_cpu_parameters_raises_instead_of_falling_back():
     with pytest.raises(RuntimeError, match="CUDA"):
         FusedAdamW([p]).step()
     assert torch.equal(p.detach(), before)
+
+
+def test_graphed_train_step_rejects_a_non_capturable_optimizer_before_touching_the_gpu():
+    """a default AdamW used to fail in the middle of the capture with an opaque error."""
+    import pytest
+    import torch
+    from km_unet_b200.train import GraphedTrainStep
+    net = torch.nn.Linear(3, 2)
+    opt = torch.optim.AdamW(net.parameters())                       # capturable=False
+    with pytest.raises(ValueError, match="capturable=True"):
+        GraphedTrainStep(net, torch.nn.MSELoss(), opt, torch.zeros(1, 3), torch.zeros(1, 2))
+    with pytest.raises(ValueError):
+        GraphedTrainStep(net, torch.nn.MSELoss(), opt, torch.zeros(1, 3), torch.zeros(1, 2), comm="nope")
